@@ -1,0 +1,827 @@
+/*
+ * Scalar C restatement of the reference's RADAU stepper  --  TEST INFRASTRUCTURE ONLY.
+ *
+ * Nothing under janus_ode_b200/ links, loads or calls this file.  It is the parity checker
+ * used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+ *
+ * PARITY STATUS: "parity unpinned" for final states / accepted-step counts: the reference
+ * (optstat/janus-ode) cannot be built here (un-vendored janus-tensor-dual / janus-linear,
+ * Eigen3, SUNDIALS, PETSc) and ships no golden vectors of a solve.  Pinned instead: the
+ * coefficient tables (oracle/tools/gen_tables.py), the reference's closed-form GTest
+ * fixtures, SciPy Radau at tolerance level, and agreement with the independent Python
+ * restatement oracle/radau_scalar.py (tests/test_oracle_*.py).
+ *
+ * Restates, per trajectory:
+ *   control flow   /root/reference/src/matlab/radau.m:630-1256  (== masked form in
+ *                  src/cpp/radauted_impl.hpp:620-1645, src/cpp/radaute_impl.hpp:537-1345)
+ *   DecomRC        src/cpp/radaute_impl.hpp:1502-1661   LU with partial pivoting, LAPACK
+ *                  zgetf2 rules: pivot = first max |re|+|im| (izamax), column scaled by the
+ *                  reciprocal of the pivot; the real block is done in real arithmetic (the
+ *                  reference promotes it to complex128 with zero imaginary part: same pivots,
+ *                  same values)
+ *   Solvrad        src/cpp/radaute_impl.hpp:1721-1897
+ *   Estrad         src/cpp/radaute_impl.hpp:1902-1986
+ *   tables         src/cpp/radaute_impl.hpp:2187-2644  -> radau_tables.h (generated)
+ *   Hamiltonian dynamics: hand-derived closed forms of ydot = [sigma dH/dx ; dH/dp] and
+ *                  J = d ydot/d y  (src/cpp/janus_ode_common.hpp:2161-2299); fixtures
+ *                  tests/cpp/ode_solver_test.cpp:228-248,299-334
+ * Deviations Q3,Q4,Q6,Q7,Q8,Q9: see oracle/radau_scalar.py header (identical here).
+ *
+ * Compile with -ffp-contract=off: the reference's libtorch CPU ops never fuse mul+add.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "radau_tables.h"
+
+#define NYMAX 16
+#define SMAX 7
+#define EPS 2.220446049250313e-16
+
+/* ---- problem ids (shared numbering with include/janus_b200.h JB200_HAM_*) ---- */
+enum {
+  PB_HARMONIC = 0,      /* par[0]=omega                      N=1 */
+  PB_VDP = 1,           /* par[0]=mu                         N=2 */
+  PB_VDP_PMP_SMOOTH = 2,/* par[0]=W          Hu test form, u=-p2((1-x1^2)x2-x1)/W frozen */
+  PB_VDP_PMP_BANG = 3,  /* par[0]=W,par[1]=umin,par[2]=umax  Hu test form, bang-bang u   */
+  PB_VDP_AUG_BANG = 4,  /* par[0]=umin,par[1]=umax  H=p1x2+p2(u(1-x1^2)x2-x1), bang-bang */
+  PB_MLP = 5            /* par = [N, width, W1,b1,W2,b2,W3,b3,W4,b4]  tanh MLP, input [x;p] */
+};
+
+typedef struct {
+  double RelTol[NYMAX], AbsTol[NYMAX];
+  double InitialStep, JacRecompute;
+  int Start_Newt, MaxNbrNewton, NbrStg, MinNbrStg, MaxNbrStg;
+  long long MaxNbrStep;
+  double Safe, Quot1, Quot2, FacL, FacR, Vitu, Vitd, hhou, hhod;
+  int Gustafsson;
+} oracle_opts;
+
+typedef struct {
+  int id, Ny;
+  double sign;
+  const double *par;
+} problem_t;
+
+/* ------------------------------------------------------------------ dynamics */
+static double bang(double p2, double x1, double x2, double umin, double umax) {
+  return (p2 * (1.0 - x1 * x1) * x2 < 0.0) ? umax : umin;
+}
+
+static void mlp_eval(const problem_t *pb, const double *y, double *f, double *J);
+
+static void rhs(const problem_t *pb, double t, const double *y, double *f) {
+  (void)t;
+  const double sg = pb->sign;
+  switch (pb->id) {
+    case PB_HARMONIC: {
+      double w = pb->par[0];
+      f[0] = sg * (w * w * y[1]);
+      f[1] = y[0];
+    } break;
+    case PB_VDP: {
+      double mu = pb->par[0], p1 = y[0], p2 = y[1], x1 = y[2], x2 = y[3];
+      f[0] = sg * (p2 * (-2.0 * mu * x1 * x2 - 1.0));
+      f[1] = sg * (p1 + p2 * (mu * (1.0 - x1 * x1)));
+      f[2] = x2;
+      f[3] = mu * (1.0 - x1 * x1) * x2 - x1;
+    } break;
+    case PB_VDP_PMP_SMOOTH:
+    case PB_VDP_PMP_BANG: {
+      double W = pb->par[0], p1 = y[0], p2 = y[1], x1 = y[2], x2 = y[3], u;
+      if (pb->id == PB_VDP_PMP_SMOOTH) u = -p2 * ((1.0 - x1 * x1) * x2 - x1) / W;
+      else u = bang(p2, x1, x2, pb->par[1], pb->par[2]);
+      f[0] = sg * (p2 * u * (-2.0 * x1 * x2 - 1.0));
+      f[1] = sg * (p1 + p2 * u * (1.0 - x1 * x1));
+      f[2] = x2;
+      f[3] = u * ((1.0 - x1 * x1) * x2 - x1);
+    } break;
+    case PB_VDP_AUG_BANG: {
+      double p1 = y[0], p2 = y[1], x1 = y[2], x2 = y[3];
+      double u = bang(p2, x1, x2, pb->par[0], pb->par[1]);
+      f[0] = sg * (p2 * u * (-2.0 * x1) * x2 - p2);
+      f[1] = sg * (p1 + p2 * u * (1.0 - x1 * x1));
+      f[2] = x2;
+      f[3] = u * (1.0 - x1 * x1) * x2 - x1;
+    } break;
+    case PB_MLP:
+      mlp_eval(pb, y, f, NULL);
+      break;
+  }
+}
+
+static void jacobian(const problem_t *pb, double t, const double *y, double *J /*[Ny*Ny] row-major*/) {
+  (void)t;
+  const int n = pb->Ny;
+  const double sg = pb->sign;
+  memset(J, 0, sizeof(double) * n * n);
+  switch (pb->id) {
+    case PB_HARMONIC: {
+      double w = pb->par[0];
+      J[0 * 2 + 1] = sg * w * w;
+      J[1 * 2 + 0] = 1.0;
+    } break;
+    case PB_VDP: {
+      double mu = pb->par[0], p2 = y[1], x1 = y[2], x2 = y[3];
+      J[0 * 4 + 1] = sg * (-2.0 * mu * x1 * x2 - 1.0);
+      J[0 * 4 + 2] = sg * (p2 * (-2.0 * mu * x2));
+      J[0 * 4 + 3] = sg * (p2 * (-2.0 * mu * x1));
+      J[1 * 4 + 0] = sg * 1.0;
+      J[1 * 4 + 1] = sg * (mu * (1.0 - x1 * x1));
+      J[1 * 4 + 2] = sg * (p2 * mu * (-2.0 * x1));
+      J[2 * 4 + 3] = 1.0;
+      J[3 * 4 + 2] = -2.0 * mu * x1 * x2 - 1.0;
+      J[3 * 4 + 3] = mu * (1.0 - x1 * x1);
+    } break;
+    case PB_VDP_PMP_SMOOTH:
+    case PB_VDP_PMP_BANG: {
+      double W = pb->par[0], p2 = y[1], x1 = y[2], x2 = y[3], u;
+      if (pb->id == PB_VDP_PMP_SMOOTH) u = -p2 * ((1.0 - x1 * x1) * x2 - x1) / W;
+      else u = bang(p2, x1, x2, pb->par[1], pb->par[2]);
+      J[0 * 4 + 1] = sg * (u * (-2.0 * x1 * x2 - 1.0));
+      J[0 * 4 + 2] = sg * (p2 * u * (-2.0 * x2));
+      J[0 * 4 + 3] = sg * (p2 * u * (-2.0 * x1));
+      J[1 * 4 + 0] = sg * 1.0;
+      J[1 * 4 + 1] = sg * (u * (1.0 - x1 * x1));
+      J[1 * 4 + 2] = sg * (p2 * u * (-2.0 * x1));
+      J[2 * 4 + 3] = 1.0;
+      J[3 * 4 + 2] = u * (-2.0 * x1 * x2 - 1.0);
+      J[3 * 4 + 3] = u * (1.0 - x1 * x1);
+    } break;
+    case PB_VDP_AUG_BANG: {
+      double p2 = y[1], x1 = y[2], x2 = y[3];
+      double u = bang(p2, x1, x2, pb->par[0], pb->par[1]);
+      J[0 * 4 + 1] = sg * (u * (-2.0 * x1) * x2 - 1.0);
+      J[0 * 4 + 2] = sg * (-p2 * u * 2.0 * x2);
+      J[0 * 4 + 3] = sg * (-p2 * u * 2.0 * x1);
+      J[1 * 4 + 0] = sg * 1.0;
+      J[1 * 4 + 1] = sg * (u * (1.0 - x1 * x1));
+      J[1 * 4 + 2] = sg * (p2 * u * (-2.0 * x1));
+      J[2 * 4 + 3] = 1.0;
+      J[3 * 4 + 2] = u * (-2.0 * x1 * x2) - 1.0;
+      J[3 * 4 + 3] = u * (1.0 - x1 * x1);
+    } break;
+    case PB_MLP: {
+      double f[NYMAX];
+      mlp_eval(pb, y, f, J);
+    } break;
+  }
+}
+
+/* MLP Hamiltonian H(v), v=[x;p] (2N inputs), 3 tanh hidden layers of `width`, scalar output.
+ * gradient g = dH/dv by back-propagation, Hessian Hvv by forward-over-reverse (one tangent per
+ * input).  ydot = [sg*dH/dx ; dH/dp], J = d ydot/d y with y=[p;x].                         */
+static void mlp_eval(const problem_t *pb, const double *y, double *f, double *J) {
+  const int N = (int)pb->par[0], Wd = (int)pb->par[1], n = 2 * N;
+  const double *W1 = pb->par + 2, *b1 = W1 + (size_t)Wd * n;
+  const double *W2 = b1 + Wd, *b2 = W2 + (size_t)Wd * Wd;
+  const double *W3 = b2 + Wd, *b3 = W3 + (size_t)Wd * Wd;
+  const double *W4 = b3 + Wd;
+  double v[NYMAX];
+  for (int i = 0; i < N; i++) { v[i] = y[N + i]; v[N + i] = y[i]; }   /* v=[x;p] */
+  double *a1 = (double *)malloc(sizeof(double) * Wd * 12);
+  double *a2 = a1 + Wd, *a3 = a2 + Wd, *d1 = a3 + Wd, *d2 = d1 + Wd, *d3 = d2 + Wd;
+  double *ta1 = d3 + Wd, *ta2 = ta1 + Wd, *ta3 = ta2 + Wd, *td1 = ta3 + Wd, *td2 = td1 + Wd, *td3 = td2 + Wd;
+  for (int i = 0; i < Wd; i++) { double s = b1[i]; for (int j = 0; j < n; j++) s += W1[(size_t)i * n + j] * v[j]; a1[i] = tanh(s); }
+  for (int i = 0; i < Wd; i++) { double s = b2[i]; for (int j = 0; j < Wd; j++) s += W2[(size_t)i * Wd + j] * a1[j]; a2[i] = tanh(s); }
+  for (int i = 0; i < Wd; i++) { double s = b3[i]; for (int j = 0; j < Wd; j++) s += W3[(size_t)i * Wd + j] * a2[j]; a3[i] = tanh(s); }
+  /* reverse: d3 = W4 .* (1-a3^2); d2 = (W3^T d3) .* (1-a2^2); d1 = (W2^T d2) .* (1-a1^2); g = W1^T d1 */
+  for (int i = 0; i < Wd; i++) d3[i] = W4[i] * (1.0 - a3[i] * a3[i]);
+  for (int j = 0; j < Wd; j++) { double s = 0; for (int i = 0; i < Wd; i++) s += W3[(size_t)i * Wd + j] * d3[i]; d2[j] = s * (1.0 - a2[j] * a2[j]); }
+  for (int j = 0; j < Wd; j++) { double s = 0; for (int i = 0; i < Wd; i++) s += W2[(size_t)i * Wd + j] * d2[i]; d1[j] = s * (1.0 - a1[j] * a1[j]); }
+  double g[NYMAX];
+  for (int j = 0; j < n; j++) { double s = 0; for (int i = 0; i < Wd; i++) s += W1[(size_t)i * n + j] * d1[i]; g[j] = s; }
+  /* g = [dH/dx ; dH/dp];  ydot = [sg dH/dx ; dH/dp] */
+  for (int i = 0; i < N; i++) { f[i] = pb->sign * g[i]; f[N + i] = g[N + i]; }
+  if (J) {
+    double Hvv[NYMAX * NYMAX];
+    for (int k = 0; k < n; k++) {   /* tangent direction e_k in v */
+      for (int i = 0; i < Wd; i++) ta1[i] = (1.0 - a1[i] * a1[i]) * W1[(size_t)i * n + k];
+      for (int i = 0; i < Wd; i++) { double s = 0; for (int j = 0; j < Wd; j++) s += W2[(size_t)i * Wd + j] * ta1[j]; ta2[i] = (1.0 - a2[i] * a2[i]) * s; }
+      for (int i = 0; i < Wd; i++) { double s = 0; for (int j = 0; j < Wd; j++) s += W3[(size_t)i * Wd + j] * ta2[j]; ta3[i] = (1.0 - a3[i] * a3[i]) * s; }
+      for (int i = 0; i < Wd; i++) td3[i] = W4[i] * (-2.0 * a3[i] * ta3[i]);
+      for (int j = 0; j < Wd; j++) {
+        double s = 0, ts = 0;
+        for (int i = 0; i < Wd; i++) { s += W3[(size_t)i * Wd + j] * d3[i]; ts += W3[(size_t)i * Wd + j] * td3[i]; }
+        td2[j] = ts * (1.0 - a2[j] * a2[j]) + s * (-2.0 * a2[j] * ta2[j]);
+      }
+      for (int j = 0; j < Wd; j++) {
+        double s = 0, ts = 0;
+        for (int i = 0; i < Wd; i++) { s += W2[(size_t)i * Wd + j] * d2[i]; ts += W2[(size_t)i * Wd + j] * td2[i]; }
+        td1[j] = ts * (1.0 - a1[j] * a1[j]) + s * (-2.0 * a1[j] * ta1[j]);
+      }
+      for (int j = 0; j < n; j++) { double s = 0; for (int i = 0; i < Wd; i++) s += W1[(size_t)i * n + j] * td1[i]; Hvv[j * n + k] = s; }
+    }
+    /* map v-index -> y-index: v_i (x_i) = y_{N+i}; v_{N+i} (p_i) = y_i.
+     * ydot_r: r<N  -> sg*g[r]   (g index r = x_r);  r>=N -> g[r] (p_{r-N})
+     * column c of y: c<N -> p_c = v_{N+c}; c>=N -> x_{c-N} = v_{c-N}                     */
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < n; c++) {
+        int vc = (c < N) ? (N + c) : (c - N);
+        double val = Hvv[r * n + vc];
+        J[r * n + c] = (r < N) ? pb->sign * val : val;
+      }
+  }
+  free(a1);
+}
+
+/* ------------------------------------------------------------------ LU (zgetf2 rules) */
+typedef struct {
+  double a[NYMAX * NYMAX];   /* L\U, row-major */
+  double rd[NYMAX];          /* reciprocal of U's diagonal */
+  int piv[NYMAX];
+} rlu_t;
+
+typedef struct {
+  double re[NYMAX * NYMAX], im[NYMAX * NYMAX];
+  double rdre[NYMAX], rdim[NYMAX];
+  int piv[NYMAX];
+} zlu_t;
+
+static void rlu_factor(int n, rlu_t *L) {
+  double *a = L->a;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    double best = fabs(a[k * n + k]);
+    for (int i = k + 1; i < n; i++) {
+      double v = fabs(a[i * n + k]);
+      if (v > best) { best = v; p = i; }
+    }
+    L->piv[k] = p;
+    if (p != k)
+      for (int j = 0; j < n; j++) { double tmp = a[k * n + j]; a[k * n + j] = a[p * n + j]; a[p * n + j] = tmp; }
+    double r = 1.0 / a[k * n + k];
+    L->rd[k] = r;
+    for (int i = k + 1; i < n; i++) {
+      double l = a[i * n + k] * r;
+      a[i * n + k] = l;
+      for (int j = k + 1; j < n; j++) a[i * n + j] = a[i * n + j] - l * a[k * n + j];
+    }
+  }
+}
+
+static void rlu_solve(int n, const rlu_t *L, double *b) {
+  const double *a = L->a;
+  for (int k = 0; k < n; k++) {
+    int p = L->piv[k];
+    if (p != k) { double tmp = b[k]; b[k] = b[p]; b[p] = tmp; }
+  }
+  for (int i = 1; i < n; i++) {
+    double s = b[i];
+    for (int j = 0; j < i; j++) s = s - a[i * n + j] * b[j];
+    b[i] = s;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double s = b[i];
+    for (int j = i + 1; j < n; j++) s = s - a[i * n + j] * b[j];
+    b[i] = s * L->rd[i];
+  }
+}
+
+static void zlu_factor(int n, zlu_t *L) {
+  double *ar = L->re, *ai = L->im;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    double best = fabs(ar[k * n + k]) + fabs(ai[k * n + k]);
+    for (int i = k + 1; i < n; i++) {
+      double v = fabs(ar[i * n + k]) + fabs(ai[i * n + k]);
+      if (v > best) { best = v; p = i; }
+    }
+    L->piv[k] = p;
+    if (p != k)
+      for (int j = 0; j < n; j++) {
+        double tmp = ar[k * n + j]; ar[k * n + j] = ar[p * n + j]; ar[p * n + j] = tmp;
+        tmp = ai[k * n + j]; ai[k * n + j] = ai[p * n + j]; ai[p * n + j] = tmp;
+      }
+    double c = ar[k * n + k], d = ai[k * n + k];
+    double inv = 1.0 / (c * c + d * d);
+    double rr = c * inv, ri = -d * inv;
+    L->rdre[k] = rr; L->rdim[k] = ri;
+    for (int i = k + 1; i < n; i++) {
+      double xr = ar[i * n + k], xi = ai[i * n + k];
+      double lr = xr * rr - xi * ri, li = xr * ri + xi * rr;
+      ar[i * n + k] = lr; ai[i * n + k] = li;
+      for (int j = k + 1; j < n; j++) {
+        double ur = ar[k * n + j], ui = ai[k * n + j];
+        ar[i * n + j] = ar[i * n + j] - (lr * ur - li * ui);
+        ai[i * n + j] = ai[i * n + j] - (lr * ui + li * ur);
+      }
+    }
+  }
+}
+
+static void zlu_solve(int n, const zlu_t *L, double *br, double *bi) {
+  const double *ar = L->re, *ai = L->im;
+  for (int k = 0; k < n; k++) {
+    int p = L->piv[k];
+    if (p != k) {
+      double tmp = br[k]; br[k] = br[p]; br[p] = tmp;
+      tmp = bi[k]; bi[k] = bi[p]; bi[p] = tmp;
+    }
+  }
+  for (int i = 1; i < n; i++) {
+    double sr = br[i], si = bi[i];
+    for (int j = 0; j < i; j++) {
+      double lr = ar[i * n + j], li = ai[i * n + j];
+      sr = sr - (lr * br[j] - li * bi[j]);
+      si = si - (lr * bi[j] + li * br[j]);
+    }
+    br[i] = sr; bi[i] = si;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double sr = br[i], si = bi[i];
+    for (int j = i + 1; j < n; j++) {
+      double ur = ar[i * n + j], ui = ai[i * n + j];
+      sr = sr - (ur * br[j] - ui * bi[j]);
+      si = si - (ur * bi[j] + ui * br[j]);
+    }
+    double rr = L->rdre[i], ri = L->rdim[i];
+    br[i] = sr * rr - si * ri;
+    bi[i] = sr * ri + si * rr;
+  }
+}
+
+/* ------------------------------------------------------------------ tables */
+typedef struct {
+  int s, Nit;
+  const double *C, *Dd, *ValP;
+  double T[SMAX][SMAX], TI[SMAX][SMAX];
+} tab_t;
+
+static void set_tables(tab_t *tb, int s, int MaxNbrNewton) {
+  tb->s = s;
+  const double *T, *TI;
+  switch (s) {
+    case 1:
+      tb->C = RADAU_C1; tb->Dd = RADAU_Dd1; tb->ValP = RADAU_ValP1; tb->Nit = MaxNbrNewton - 3;
+      T = &RADAU_T1[0][0]; TI = &RADAU_TI1[0][0];
+      break;
+    case 3:
+      tb->C = RADAU_C3; tb->Dd = RADAU_Dd3; tb->ValP = RADAU_ValP3; tb->Nit = MaxNbrNewton;
+      T = &RADAU_T3[0][0]; TI = &RADAU_TI3[0][0];
+      break;
+    case 5:
+      tb->C = RADAU_C5; tb->Dd = RADAU_Dd5; tb->ValP = RADAU_ValP5; tb->Nit = MaxNbrNewton + 5;
+      T = &RADAU_T5[0][0]; TI = &RADAU_TI5[0][0];
+      break;
+    default:
+      tb->C = RADAU_C7; tb->Dd = RADAU_Dd7; tb->ValP = RADAU_ValP7; tb->Nit = MaxNbrNewton + 10;
+      T = &RADAU_T7[0][0]; TI = &RADAU_TI7[0][0];
+      break;
+  }
+  for (int i = 0; i < s; i++)
+    for (int j = 0; j < s; j++) {
+      tb->T[i][j] = T[i * s + j];
+      tb->TI[i][j] = TI[i * s + j];
+    }
+}
+
+static int any_nan(const double *v, int n) {
+  for (int i = 0; i < n; i++) if (isnan(v[i])) return 1;
+  return 0;
+}
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* stats index: 0 FcnNbr 1 JacNbr 2 DecompNbr 3 SolveNbr 4 StepNbr 5 AccptNbr 6 StepRejNbr 7 NewtRejNbr */
+enum { ST_FCN, ST_JAC, ST_DEC, ST_SOL, ST_STEP, ST_ACC, ST_REJ, ST_NREJ };
+
+typedef struct {
+  rlu_t L0;
+  zlu_t Lc[(SMAX - 1) / 2];
+} lus_t;
+
+static void decomrc(int n, const tab_t *tb, double h, const double *Jac, lus_t *lu) {
+  double rh = 1.0 / h;
+  double valp[SMAX];
+  for (int q = 0; q < tb->s; q++) valp[q] = tb->ValP[q] * rh;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) lu->L0.a[i * n + j] = -Jac[i * n + j] + ((i == j) ? valp[0] : 0.0);
+  rlu_factor(n, &lu->L0);
+  for (int q = 1; q <= (tb->s - 1) / 2; q++) {
+    zlu_t *Z = &lu->Lc[q - 1];
+    double al = valp[2 * q - 1], be = valp[2 * q];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        Z->re[i * n + j] = ((i == j) ? al : 0.0) - Jac[i * n + j];
+        Z->im[i * n + j] = (i == j) ? be : 0.0;
+      }
+    zlu_factor(n, Z);
+  }
+}
+
+/* z, w : [s][n] (stage-major) */
+static void solvrad(int n, const tab_t *tb, double h, const lus_t *lu, double z[SMAX][NYMAX], double w[SMAX][NYMAX]) {
+  double rh = 1.0 / h;
+  double valp[SMAX];
+  for (int q = 0; q < tb->s; q++) valp[q] = tb->ValP[q] * rh;
+  for (int i = 0; i < n; i++) z[0][i] = z[0][i] - valp[0] * w[0][i];
+  rlu_solve(n, &lu->L0, z[0]);
+  for (int q = 1; q <= (tb->s - 1) / 2; q++) {
+    int q2 = 2 * q - 1, q3 = 2 * q;
+    double z2[NYMAX], z3[NYMAX];
+    for (int i = 0; i < n; i++) {
+      z2[i] = z[q2][i] - valp[q2] * w[q2][i] + valp[q3] * w[q3][i];
+      z3[i] = z[q3][i] - valp[q3] * w[q2][i] - valp[q2] * w[q3][i];
+    }
+    zlu_solve(n, &lu->Lc[q - 1], z2, z3);
+    for (int i = 0; i < n; i++) { z[q2][i] = z2[i]; z[q3][i] = z3[i]; }
+  }
+}
+
+static double scaled_norm(int n, const double *v, const double *Scal) {
+  double s = 0.0;
+  for (int i = 0; i < n; i++) { double q = v[i] / Scal[i]; s += q * q; }
+  return sqrt(s);
+}
+
+static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t *lu, double z[SMAX][NYMAX],
+                     const double *Scal, const double *f0, int First, int Reject, double t, const double *y,
+                     long long *st) {
+  int n = pb->Ny;
+  double rh = 1.0 / h, temp[NYMAX], ev[NYMAX];
+  for (int i = 0; i < n; i++) {
+    double s = 0.0;
+    for (int q = 0; q < tb->s; q++) s += z[q][i] * (tb->Dd[q] * rh);
+    temp[i] = s;
+    ev[i] = f0[i] + s;
+  }
+  rlu_solve(n, &lu->L0, ev);
+  double err = scaled_norm(n, ev, Scal);
+  err = fmax(err / sqrt((double)n), 1e-10);
+  if (err >= 1.0 && (First || Reject)) {
+    double ya[NYMAX];
+    for (int i = 0; i < n; i++) ya[i] = y[i] + err;
+    rhs(pb, t, ya, ev);
+    st[ST_FCN] += 1;
+    for (int i = 0; i < n; i++) ev[i] = ev[i] + temp[i];
+    rlu_solve(n, &lu->L0, ev);
+    err = scaled_norm(n, ev, Scal);
+    err = fmax(err / sqrt((double)n), 1e-10);
+  }
+  return err;
+}
+
+/* one trajectory; returns res code */
+static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, double tfinal, const double *y0,
+                     double *y_out, double *t_out, double *h_out, long long *st, int *nstg_out,
+                     double *rec_h, int rec_cap, int *rec_n) {
+  const int n = pb->Ny;
+  double y[NYMAX], f0[NYMAX], Scal[NYMAX], RelTol1[NYMAX], AbsTol1[NYMAX], QuotTol[NYMAX];
+  double Jac[NYMAX * NYMAX];
+  double z[SMAX][NYMAX], w[SMAX][NYMAX], cont[SMAX][NYMAX], fq[SMAX][NYMAX];
+  lus_t lu;
+  tab_t tb;
+  int res = 0;
+  memset(st, 0, 8 * sizeof(long long));
+  memset(z, 0, sizeof z); memset(w, 0, sizeof w); memset(cont, 0, sizeof cont);
+  for (int i = 0; i < n; i++) y[i] = y0[i];
+  double t = t0;
+  double PosNeg = (tfinal - t0) >= 0 ? 1.0 : -1.0;
+  const double Thet = op->JacRecompute, Safe = op->Safe, Quot1 = op->Quot1, Quot2 = op->Quot2;
+  const double FacL = 1.0 / op->FacL, FacR = 1.0 / op->FacR;
+  int NbrStg = op->NbrStg;
+  const int MinNbrStg = op->MinNbrStg, MaxNbrStg = op->MaxNbrStg;
+  const int Variab = (MaxNbrStg - MinNbrStg) != 0;
+  set_tables(&tb, NbrStg, op->MaxNbrNewton);
+  int UnExpStepRej = 0, UnExpNewtRej = 0, Keep = 0, ChangeFlag = 0, ChangeNbr = 0;
+  double Theta = 0.0, Thetat = 0.0;
+  double hmaxn = fabs(tfinal - t0);
+  double h = op->InitialStep;
+  if (fabs(h) <= 10 * EPS) h = 1e-6;
+  h = PosNeg * fmin(fabs(h), hmaxn);
+  double h_old = h, hopt = h;
+  int Last;
+  if ((t + h * 1.0001 - tfinal) * PosNeg >= 0) { h = tfinal - t; Last = 1; } else Last = 0;
+  double FacConv = 1.0;
+  int Reject = 0, First = 1;
+  double ExpmNs = (NbrStg + 1.0) / (2.0 * NbrStg);
+  for (int i = 0; i < n; i++) {
+    QuotTol[i] = op->AbsTol[i] / op->RelTol[i];
+    RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
+    AbsTol1[i] = RelTol1[i] * QuotTol[i];
+    Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+  }
+  rhs(pb, t, y, f0);
+  st[ST_FCN] += 1;
+  if (any_nan(f0, n)) { res = 2; goto done; }
+  int NeedNewJac = 1, NeedNewLU = 1, Newt = 0;
+  double SqrtStgNy = sqrt((double)(NbrStg * n));
+  double hacc = 0.0, erracc = 0.0, thqold = 0.0, OldNrm = 0.0;
+  if (rec_n) *rec_n = 0;
+
+  while (st[ST_STEP] <= op->MaxNbrStep && PosNeg * t < PosNeg * tfinal) {
+    st[ST_STEP] += 1;
+    FacConv = pow(fmax(FacConv, EPS), 0.8);
+    if (NeedNewJac) {
+      jacobian(pb, t, y, Jac);
+      if (any_nan(Jac, n * n)) { res = 2; break; }
+      st[ST_JAC] += 1;
+      NeedNewJac = 0;
+      NeedNewLU = 1;
+    }
+    if (Variab && !Keep) {
+      ChangeNbr += 1;
+      int NbrStgNew = NbrStg;
+      double hquot = h / h_old;
+      Thetat = fmin(10.0, fmax(Theta, Thetat * 0.5));
+      if (Newt > 1 && Thetat <= op->Vitu && hquot < op->hhou && hquot > op->hhod) NbrStgNew = imin(MaxNbrStg, NbrStg + 2);
+      if (Thetat >= op->Vitd || UnExpStepRej) NbrStgNew = imax(MinNbrStg, NbrStg - 2);
+      if (ChangeNbr >= 1 && UnExpNewtRej) NbrStgNew = imax(MinNbrStg, NbrStg - 2);
+      if (ChangeNbr <= 10) NbrStgNew = imin(NbrStg, NbrStgNew);
+      ChangeFlag = NbrStg != NbrStgNew;
+      UnExpNewtRej = 0;
+      UnExpStepRej = 0;
+      if (ChangeFlag) {
+        NbrStg = NbrStgNew;
+        ChangeNbr = 1;
+        ExpmNs = (NbrStg + 1.0) / (2.0 * NbrStg);
+        for (int i = 0; i < n; i++) {
+          RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
+          AbsTol1[i] = RelTol1[i] * QuotTol[i];
+          Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+        }
+        NeedNewLU = 1;
+        SqrtStgNy = sqrt((double)(NbrStg * n));
+        set_tables(&tb, NbrStg, op->MaxNbrNewton);
+      }
+    }
+    if (NeedNewLU) {
+      decomrc(n, &tb, h, Jac, &lu);
+      st[ST_DEC] += 1;
+      NeedNewLU = 0;
+    }
+    if (Variab && Keep) {
+      Keep = 0;
+      ChangeNbr += 1;
+      if (ChangeNbr >= 10 && NbrStg < MaxNbrStg) NeedNewJac = 0;
+    }
+    if (0.1 * fabs(h) <= fabs(t) * EPS) { res = 1; break; }
+    ExpmNs = (NbrStg + 1.0) / (2.0 * NbrStg);
+    double mrt = INFINITY;
+    for (int i = 0; i < n; i++) {
+      QuotTol[i] = op->AbsTol[i] / op->RelTol[i];
+      RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
+      AbsTol1[i] = RelTol1[i] * QuotTol[i];
+      Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+      mrt = fmin(mrt, RelTol1[i]);
+    }
+    const int s = NbrStg;
+    if (First || op->Start_Newt || ChangeFlag) {
+      memset(z, 0, sizeof z); memset(w, 0, sizeof w); memset(cont, 0, sizeof cont);
+    } else {
+      double hquot = h / h_old;
+      for (int q = 0; q < s; q++) {
+        double cq = tb.C[q] * hquot;
+        for (int i = 0; i < n; i++) {
+          double zq = (cq - tb.C[0] + 1.0) * cont[s - 1][i];
+          for (int q1 = 2; q1 <= s; q1++) zq = (zq + cont[s - q1][i]) * (cq - tb.C[q1 - 1] + 1.0);
+          z[q][i] = zq;
+        }
+      }
+      for (int j = 0; j < s; j++)
+        for (int i = 0; i < n; i++) {
+          double acc = tb.TI[j][0] * z[0][i];
+          for (int q = 1; q < s; q++) acc = acc + tb.TI[j][q] * z[q][i];
+          w[j][i] = acc;
+        }
+    }
+    double FNewt = fmax(10 * EPS / mrt, fmin(0.03, pow(mrt, 1.0 / ExpmNs - 1.0)));
+    if (s == 1) FNewt = fmax(10 * EPS / mrt, 0.03);
+    FacConv = pow(fmax(FacConv, EPS), 0.8);
+    Theta = fabs(Thet);
+    Newt = 0;
+    int newton_failed = 0, nan_fail = 0;
+    double NewNrm = 0.0;
+    for (;;) {
+      Reject = 0;
+      Newt += 1;
+      if (Newt > tb.Nit) {
+        UnExpStepRej = 1;
+        st[ST_REJ] += 1; st[ST_NREJ] += 1;
+        h = h * 0.5;
+        Reject = 1; Last = 0; NeedNewLU = 1; newton_failed = 1;
+        break;
+      }
+      for (int q = 0; q < s; q++) {
+        double yq[NYMAX];
+        for (int i = 0; i < n; i++) yq[i] = y[i] + z[q][i];
+        rhs(pb, t + tb.C[q] * h, yq, fq[q]);
+        if (any_nan(fq[q], n)) nan_fail = 1;
+      }
+      if (nan_fail) break;
+      st[ST_FCN] += s;
+      for (int j = 0; j < s; j++)
+        for (int i = 0; i < n; i++) {
+          double acc = tb.TI[j][0] * fq[0][i];
+          for (int q = 1; q < s; q++) acc = acc + tb.TI[j][q] * fq[q][i];
+          z[j][i] = acc;
+        }
+      solvrad(n, &tb, h, &lu, z, w);
+      st[ST_SOL] += 1;
+      NewNrm = 0.0;
+      for (int q = 0; q < s; q++) NewNrm += scaled_norm(n, z[q], Scal);
+      NewNrm = NewNrm / SqrtStgNy;
+      if (!isfinite(NewNrm)) { nan_fail = 1; break; }
+      if (Newt > 1 && Newt < tb.Nit) {
+        double thq = NewNrm / OldNrm;
+        if (Newt == 2) Theta = thq; else Theta = sqrt(thq * thqold);
+        thqold = thq;
+        if (Theta < 0.99) {
+          FacConv = Theta / (1.0 - Theta);
+          double dyth = FacConv * NewNrm * pow(Theta, (double)(tb.Nit - 1 - Newt)) / FNewt;
+          if (dyth >= 1.0) {
+            double qNewt = fmax(1.0e-4, fmin(20.0, dyth));
+            double hhfac = 0.8 * pow(qNewt, -1.0 / (4.0 + tb.Nit - 1 - Newt));
+            h = hhfac * h;
+            Reject = 1; Last = 0;
+            UnExpNewtRej = hhfac <= 0.5;
+            st[ST_NREJ] += 1; st[ST_REJ] += 1;
+            NeedNewLU = 1; newton_failed = 1;
+            break;
+          }
+        } else {
+          h = h * 0.5;
+          Reject = 1; Last = 0; UnExpStepRej = 1;
+          st[ST_REJ] += 1;
+          NeedNewLU = 1; newton_failed = 1;
+          break;
+        }
+      }
+      OldNrm = fmax(NewNrm, EPS);
+      for (int q = 0; q < s; q++) for (int i = 0; i < n; i++) w[q][i] = w[q][i] + z[q][i];
+      for (int j = 0; j < s; j++)
+        for (int i = 0; i < n; i++) {
+          double acc = tb.T[j][0] * w[0][i];
+          for (int q = 1; q < s; q++) acc = acc + tb.T[j][q] * w[q][i];
+          z[j][i] = acc;
+        }
+      if (FacConv * NewNrm > FNewt) continue;
+      break;
+    }
+    if (nan_fail) { res = 2; break; }
+    if (newton_failed) continue;
+
+    double err = estrad(pb, &tb, h, &lu, z, Scal, f0, First, Reject, t, y, st);
+    if (!isfinite(err)) { res = 2; break; }
+    double fac = fmin(Safe, (2.0 * tb.Nit + 1.0) / (2.0 * tb.Nit + Newt));
+    double exponent = 1.0 / s + 1.0;
+    double quot = fmax(FacR, fmin(FacL, pow(err, exponent) / fac));
+    double hnew = h / quot;
+    if (err < 1.0) {
+      First = 0;
+      st[ST_ACC] += 1;
+      if (op->Gustafsson && !ChangeFlag) {
+        if (st[ST_ACC] > 1) {
+          double facgus = (hacc / h) * pow(err * err / erracc, 1.0 / (s + 1.0)) / Safe;
+          facgus = fmax(FacR, fmin(FacL, facgus));
+          quot = fmax(quot, facgus);
+          hnew = h / quot;
+        }
+        hacc = h;
+        erracc = fmax(1.0e-2, err);
+      }
+      h_old = h;
+      t = t + h;
+      for (int i = 0; i < n; i++) y[i] = y[i] + z[s - 1][i];
+      for (int i = 0; i < n; i++) cont[s - 1][i] = z[0][i] / tb.C[0];
+      for (int q = 1; q <= s - 1; q++) {
+        double Fact = 1.0 / (tb.C[s - q - 1] - tb.C[s - q]);
+        for (int i = 0; i < n; i++) cont[q - 1][i] = (z[s - q - 1][i] - z[s - q][i]) * Fact;
+      }
+      for (int jj = 2; jj <= s; jj++)
+        for (int k = s; k >= jj; k--) {
+          double Fact = (s - k == 0) ? 1.0 / (-tb.C[jj - 1]) : 1.0 / (tb.C[s - k - 1] - tb.C[s - k + jj - 1]);
+          for (int i = 0; i < n; i++) cont[k - 1][i] = (cont[k - 1][i] - cont[k - 2][i]) * Fact;
+        }
+      if (rec_h && rec_n && *rec_n < rec_cap) rec_h[(*rec_n)++] = h;
+      NeedNewJac = 1;
+      if (Last) {
+        h = hopt;
+        st[ST_REJ] += 1;
+        break;
+      }
+      rhs(pb, t, y, f0);
+      st[ST_FCN] += 1;
+      if (any_nan(f0, n)) { res = 2; break; }
+      hnew = PosNeg * fmin(fabs(hnew), fabs(hmaxn));
+      hopt = PosNeg * fmin(fabs(h), fabs(hnew));
+      if (Reject) hnew = PosNeg * fmin(fabs(hnew), fabs(h));
+      Reject = 0;
+      if ((t + hnew / Quot1 - tfinal) * PosNeg >= 0) {
+        h = tfinal - t;
+        Last = 1;
+      } else {
+        double qt = hnew / h;
+        if (Theta <= Thet && qt >= Quot1 && qt <= Quot2) {
+          Keep = 1; NeedNewJac = 0; NeedNewLU = 0;
+          continue;
+        }
+        h = hnew;
+      }
+      NeedNewLU = 1;
+      if (Theta <= Thet) NeedNewJac = 0;
+    } else {
+      Reject = 1; Last = 0;
+      if (First) h = h / 10.0; else h = hnew;
+      if (st[ST_ACC] >= 1) st[ST_REJ] += 1;
+      NeedNewLU = 1;
+    }
+  }
+  if (res == 0 && PosNeg * t < PosNeg * tfinal) res = 3;
+done:
+  for (int i = 0; i < n; i++) y_out[i] = y[i];
+  *t_out = t;
+  *h_out = h;
+  *nstg_out = NbrStg;
+  return res;
+}
+
+/* ------------------------------------------------------------------ public entry points */
+/* y0 [M][Ny] row-major, tspan [M][2]; outputs y_out [M][Ny], t_out[M], h_out[M], res[M],
+ * stats [M][8], nstg[M].  nthreads <= 0 -> all.  Returns 0.                               */
+int oracle_radau_solve(int problem, const double *par, int sign, int Ny, long long M, const double *y0,
+                       const double *tspan, const oracle_opts *op, double *y_out, double *t_out, double *h_out,
+                       int *res, long long *stats, int *nstg, int nthreads) {
+  problem_t pb;
+  pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+  if (Ny > NYMAX) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+  for (long long m = 0; m < M; m++) {
+    res[m] = radau_one(&pb, op, tspan[2 * m], tspan[2 * m + 1], y0 + m * Ny, y_out + m * Ny, t_out + m,
+                       h_out + m, stats + 8 * m, nstg + m, NULL, 0, NULL);
+  }
+  return 0;
+}
+
+/* single trajectory with the accepted step sizes recorded (debug / desync analysis) */
+int oracle_radau_trace(int problem, const double *par, int sign, int Ny, const double *y0, const double *tspan,
+                       const oracle_opts *op, double *y_out, double *t_out, long long *stats, double *rec_h,
+                       int rec_cap, int *rec_n) {
+  problem_t pb;
+  pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+  double h_out; int nstg;
+  return radau_one(&pb, op, tspan[0], tspan[1], y0, y_out, t_out, &h_out, stats, &nstg, rec_h, rec_cap, rec_n);
+}
+
+/* batched dynamics / Jacobian (checks the stage-eval kernel) */
+int oracle_eval_dyns(int problem, const double *par, int sign, int Ny, long long M, const double *y, double *f) {
+  problem_t pb; pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+#pragma omp parallel for
+  for (long long m = 0; m < M; m++) rhs(&pb, 0.0, y + m * Ny, f + m * Ny);
+  return 0;
+}
+
+int oracle_eval_jac(int problem, const double *par, int sign, int Ny, long long M, const double *y, double *J) {
+  problem_t pb; pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+#pragma omp parallel for
+  for (long long m = 0; m < M; m++) jacobian(&pb, 0.0, y + m * Ny, J + m * Ny * Ny);
+  return 0;
+}
+
+/* batched LU factor+solve: A [M][n][n] (complex as separate re/im, im may be NULL), b [M][n] */
+int oracle_lu_solve(int n, long long M, const double *Are, const double *Aim, const double *bre, const double *bim,
+                    double *xre, double *xim) {
+  if (n > NYMAX) return -1;
+#pragma omp parallel for
+  for (long long m = 0; m < M; m++) {
+    if (Aim == NULL) {
+      rlu_t L;
+      memcpy(L.a, Are + m * n * n, sizeof(double) * n * n);
+      rlu_factor(n, &L);
+      double b[NYMAX];
+      memcpy(b, bre + m * n, sizeof(double) * n);
+      rlu_solve(n, &L, b);
+      memcpy(xre + m * n, b, sizeof(double) * n);
+    } else {
+      zlu_t L;
+      memcpy(L.re, Are + m * n * n, sizeof(double) * n * n);
+      memcpy(L.im, Aim + m * n * n, sizeof(double) * n * n);
+      zlu_factor(n, &L);
+      double br[NYMAX], bi[NYMAX];
+      memcpy(br, bre + m * n, sizeof(double) * n);
+      memcpy(bi, bim + m * n, sizeof(double) * n);
+      zlu_solve(n, &L, br, bi);
+      memcpy(xre + m * n, br, sizeof(double) * n);
+      memcpy(xim + m * n, bi, sizeof(double) * n);
+    }
+  }
+  return 0;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,160 @@
+"""ctypes binding of oracle/c/libradau_oracle.so (the C parity oracle).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/c/radau_oracle.c header.  Never imported by
+janus_ode_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "c", "libradau_oracle.so")
+
+NYMAX = 16
+PB = dict(harmonic=0, vdp=1, vdp_pmp_smooth=2, vdp_pmp_bang=3, vdp_aug_bang=4, mlp=5)
+STAT_NAMES = ("FcnNbr", "JacNbr", "DecompNbr", "SolveNbr", "StepNbr", "AccptNbr",
+              "StepRejNbr", "NewtRejNbr")
+
+
+class OracleOpts(C.Structure):
+    _fields_ = [("RelTol", C.c_double * NYMAX), ("AbsTol", C.c_double * NYMAX),
+                ("InitialStep", C.c_double), ("JacRecompute", C.c_double),
+                ("Start_Newt", C.c_int), ("MaxNbrNewton", C.c_int), ("NbrStg", C.c_int),
+                ("MinNbrStg", C.c_int), ("MaxNbrStg", C.c_int), ("MaxNbrStep", C.c_longlong),
+                ("Safe", C.c_double), ("Quot1", C.c_double), ("Quot2", C.c_double),
+                ("FacL", C.c_double), ("FacR", C.c_double), ("Vitu", C.c_double),
+                ("Vitd", C.c_double), ("hhou", C.c_double), ("hhod", C.c_double),
+                ("Gustafsson", C.c_int)]
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "c", "radau_oracle.c")
+    if force or not os.path.exists(_SO) or (
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_SO)):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "c"), "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+def _opts(opts, Ny):
+    """opts: oracle.radau_scalar.RadauOptions (or anything with the same attributes)."""
+    o = OracleOpts()
+    rt = np.broadcast_to(np.asarray(opts.RelTol, dtype=np.float64), (Ny,))
+    at = np.broadcast_to(np.asarray(opts.AbsTol, dtype=np.float64), (Ny,))
+    for i in range(Ny):
+        o.RelTol[i] = rt[i]
+        o.AbsTol[i] = at[i]
+    for k in ("InitialStep", "JacRecompute", "Safe", "Quot1", "Quot2", "FacL", "FacR", "Vitu",
+              "Vitd", "hhou", "hhod"):
+        setattr(o, k, float(getattr(opts, k)))
+    for k in ("MaxNbrNewton", "NbrStg", "MinNbrStg", "MaxNbrStg", "MaxNbrStep"):
+        setattr(o, k, int(getattr(opts, k)))
+    o.Start_Newt = int(bool(opts.Start_Newt))
+    o.Gustafsson = int(bool(opts.Gustafsson))
+    return o
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def solve(problem, par, sign, y0, tspan, opts, nthreads=0):
+    """y0 [M,Ny], tspan [M,2] -> dict(y, t, h, res, stats[M,8], nstg)."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, Ny = y0.shape
+    y = np.empty_like(y0)
+    t = np.empty(M)
+    h = np.empty(M)
+    res = np.empty(M, dtype=np.int32)
+    stats = np.empty((M, 8), dtype=np.int64)
+    nstg = np.empty(M, dtype=np.int32)
+    o = _opts(opts, Ny)
+    rc = lib().oracle_radau_solve(
+        C.c_int(PB[problem] if isinstance(problem, str) else problem), _dp(par), C.c_int(sign),
+        C.c_int(Ny), C.c_longlong(M), _dp(y0), _dp(tspan), C.byref(o), _dp(y), _dp(t), _dp(h),
+        res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+        nstg.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(nthreads))
+    assert rc == 0
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)
+
+
+def trace(problem, par, sign, y0, tspan, opts, cap=100000):
+    """one trajectory, with the accepted step sizes."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    Ny = y0.shape[0]
+    y = np.empty(Ny)
+    t = C.c_double()
+    stats = np.empty(8, dtype=np.int64)
+    rec = np.empty(cap)
+    n = C.c_int()
+    o = _opts(opts, Ny)
+    res = lib().oracle_radau_trace(
+        C.c_int(PB[problem] if isinstance(problem, str) else problem), _dp(par), C.c_int(sign),
+        C.c_int(Ny), _dp(y0), _dp(tspan), C.byref(o), _dp(y), C.byref(t),
+        stats.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(rec), C.c_int(cap), C.byref(n))
+    return dict(y=y, t=t.value, res=res, stats=stats, h_accept=rec[:n.value].copy())
+
+
+def eval_dyns(problem, par, sign, y):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, Ny = y.shape
+    f = np.empty_like(y)
+    lib().oracle_eval_dyns(C.c_int(PB[problem]), _dp(par), C.c_int(sign), C.c_int(Ny),
+                           C.c_longlong(M), _dp(y), _dp(f))
+    return f
+
+
+def eval_jac(problem, par, sign, y):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, Ny = y.shape
+    J = np.empty((M, Ny, Ny))
+    lib().oracle_eval_jac(C.c_int(PB[problem]), _dp(par), C.c_int(sign), C.c_int(Ny),
+                          C.c_longlong(M), _dp(y), _dp(J))
+    return J
+
+
+def lu_solve(A, b):
+    """A [M,n,n] real or complex, b [M,n] -> x (zgetf2-rule LU with reciprocal pivots)."""
+    A = np.asarray(A)
+    b = np.asarray(b)
+    M, n, _ = A.shape
+    if np.iscomplexobj(A) or np.iscomplexobj(b):
+        Ar = np.ascontiguousarray(A.real, dtype=np.float64)
+        Ai = np.ascontiguousarray(A.imag, dtype=np.float64)
+        br = np.ascontiguousarray(b.real, dtype=np.float64)
+        bi = np.ascontiguousarray(b.imag, dtype=np.float64)
+        xr = np.empty_like(br)
+        xi = np.empty_like(bi)
+        lib().oracle_lu_solve(C.c_int(n), C.c_longlong(M), _dp(Ar), _dp(Ai), _dp(br), _dp(bi),
+                              _dp(xr), _dp(xi))
+        return xr + 1j * xi
+    Ar = np.ascontiguousarray(A, dtype=np.float64)
+    br = np.ascontiguousarray(b, dtype=np.float64)
+    xr = np.empty_like(br)
+    lib().oracle_lu_solve(C.c_int(n), C.c_longlong(M), _dp(Ar), None, _dp(br), None, _dp(xr), None)
+    return xr
+
+
+def max_threads():
+    return lib().oracle_max_threads()
