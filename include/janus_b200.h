@@ -1,0 +1,133 @@
+/*
+ * janus_b200.h -- C ABI of the B200-native batched Hamiltonian Radau integrator.
+ *
+ * Drop-in boundary for ONE path of optstat/janus-ode: the batched implicit Radau IIA solve of
+ * a Hamiltonian system (H -> dynamics/Jacobian -> simplified Newton + LU -> error estimate ->
+ * per-trajectory step/order control).  Plain pointers and sizes only, no torch types.
+ * Every function returns 0 on success or a negative JB200_E* code; jb200_last_error() gives
+ * the text.  Nothing here ever calls exit() (the reference does: radaute_impl.hpp:10-214).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   jb200_opts              <- struct OptionsTe               src/cpp/radaute.hpp:52-96
+ *   jb200_create            <- RadauTe::RadauTe(OdeFcn, JacFn, tspan, y0, Op, params)
+ *                                                             src/cpp/radaute.hpp:424-425,
+ *                                                             src/cpp/radaute_impl.hpp:5-535
+ *                              with OdeFcn/JacFn = evalDyns/evalJac of a Hamiltonian
+ *                                                             src/cpp/janus_ode_common.hpp:2161-2299
+ *                                                             examples/cpp/radaute_hamiltonian_example.cpp:44-62
+ *   jb200_solve[_host]      <- Tensor RadauTe::solve() + public fields y, t, h, stats
+ *                                                             src/cpp/radaute.hpp:427,296,253,98-108
+ *                                                             src/cpp/radaute_impl.hpp:537-1345
+ *   jb200_eval_dyns/_jac    <- evalDyns(U) / evalJac(U)       src/cpp/janus_ode_common.hpp:2161-2299
+ *   jb200_lu_solve          <- torch::linalg_lu_factor + lu_solve on [m,Ny,Ny] (the janus-linear
+ *                              role)                          src/cpp/radaute_impl.hpp:1558,1611,1754,1832
+ * Layouts are the reference's: y [M,Ny] row-major with y = [p(0:N), x(N:2N)]
+ * (janus_ode_common.hpp:2167-2169), tspan [M,2], J [M,Ny,Ny] rows = ydot, cols = y.
+ *
+ * Thread-compatibility: one handle per (device, stream); calls on one handle must not overlap.
+ */
+#ifndef JANUS_B200_H
+#define JANUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB200_NYMAX 16
+#define JB200_MAX_HAM_PARAMS 8
+
+/* error codes */
+#define JB200_OK 0
+#define JB200_EINVAL (-1)   /* bad option / argument (the reference exit(1)s) */
+#define JB200_ECUDA (-2)    /* CUDA runtime error                              */
+#define JB200_ENOTSUP (-3)  /* Hamiltonian / size not compiled in              */
+
+/* built-in Hamiltonians, y = [p, x] */
+#define JB200_HAM_HARMONIC 0        /* N=1 par: omega              H=(p^2+w^2 x^2)/2                      */
+#define JB200_HAM_VDP 1             /* N=2 par: mu                 H=p1 x2+p2(mu(1-x1^2)x2-x1)            */
+#define JB200_HAM_VDP_PMP_SMOOTH 2  /* N=2 par: W                  Hu=p1x2+p2u((1-x1^2)x2-x1)+W/2u^2+1,
+                                                                   u=-p2((1-x1^2)x2-x1)/W frozen         */
+#define JB200_HAM_VDP_PMP_BANG 3    /* N=2 par: W,umin,umax        same Hu, u=umax if p2(1-x1^2)x2<0 else umin */
+#define JB200_HAM_VDP_AUG_BANG 4    /* N=2 par: umin,umax          H=p1x2+p2(u(1-x1^2)x2-x1), bang-bang u */
+
+/* result codes per trajectory (res[]) -- src/cpp/radaute_impl.hpp:711-719,873-877,1245-1255 */
+#define JB200_RES_OK 0
+#define JB200_RES_STEP_TOO_SMALL 1
+#define JB200_RES_NAN 2
+#define JB200_RES_MAX_STEPS 3
+
+/* stats columns: StatsTe, src/cpp/radaute.hpp:98-108 (MATLAB counting rules, radau.m) */
+enum {
+  JB200_ST_FCN = 0, JB200_ST_JAC, JB200_ST_DECOMP, JB200_ST_SOLVE,
+  JB200_ST_STEP, JB200_ST_ACCPT, JB200_ST_STEPREJ, JB200_ST_NEWTREJ, JB200_NSTATS
+};
+
+/* mirrors OptionsTe field for field (solver knobs), plus costate_sign */
+typedef struct jb200_opts {
+  double RelTol[JB200_NYMAX];   /* n_tol entries used (1 = scalar, broadcast) */
+  double AbsTol[JB200_NYMAX];
+  int n_tol;
+  double InitialStep;           /* 1e-2 */
+  double MaxStep;               /* accepted and ignored like the reference (hmax = tfinal - t0) */
+  double JacRecompute;          /* 1e-3 */
+  int Start_Newt;               /* 0 */
+  int MaxNbrNewton;             /* 7 */
+  int NbrStg, MinNbrStg, MaxNbrStg; /* 3, 3, 7 */
+  int64_t MaxNbrStep;           /* 10000 */
+  double Safe, Quot1, Quot2;    /* 0.9, 1, 1.2 */
+  double FacL, FacR;            /* 0.2, 8 */
+  double Vitu, Vitd, hhou, hhod;/* 0.002, 0.8, 1.2, 0.8 */
+  int Gustafsson;               /* 1 */
+  int costate_sign;             /* +1: pdot=+dH/dx (reference), -1: canonical */
+} jb200_opts;
+
+/* fill *o with the reference defaults (src/cpp/radaute.hpp:52-96) */
+int jb200_opts_default(jb200_opts* o);
+
+/* validate options + Hamiltonian and build a solver handle on the current CUDA device */
+int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int n_ham_params,
+                 void** handle);
+void jb200_destroy(void* handle);
+
+/* number of state components Ny = 2N of the handle's Hamiltonian */
+int jb200_ny(void* handle);
+
+/* Integrate M trajectories.  All pointers are DEVICE pointers; stream is a cudaStream_t.
+ * y0 [M,Ny], tspan [M,2] -> y_out [M,Ny], t_out [M], h_out [M], res [M], stats [M,8] (int64),
+ * nstg [M] (final stage count; may be NULL).  Asynchronous on `stream`.                   */
+int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
+                double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
+                void* stream);
+
+/* Same with HOST pointers (what a reference caller holds: CPU tensors).  Copies in, solves,
+ * copies out and synchronises; the device workspace lives in the handle.                   */
+int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
+                     double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg);
+
+/* kernels launched by the last jb200_solve* call on this handle */
+int jb200_last_launches(void* handle);
+
+/* stage evaluation: ydot [M,Ny] and J [M,Ny,Ny] of the handle's Hamiltonian (device pointers) */
+int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void* stream);
+int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream);
+
+/* batched small dense LU factor + solve, n in {2,3,4}: A [M,n,n], b [M,n] -> x [M,n].
+ * Aim/bim/xim == NULL selects the real path, otherwise complex (separate re/im planes).    */
+int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre,
+                   const double* bim, double* xre, double* xim, void* stream);
+
+/* deterministic pow used by the controller (test hook): out[i] = x[i]^y[i], device pointers */
+int jb200_det_pow(const double* x, const double* y, int64_t n, double* out, void* stream);
+
+/* FP64 roofline probe: runs a dependent-chain-free DFMA kernel and returns achieved TFLOP/s */
+int jb200_fp64_peak(int iters, double* tflops);
+
+const char* jb200_last_error(void);
+const char* jb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JANUS_B200_H */

@@ -1,0 +1,575 @@
+// C ABI (include/janus_b200.h) + the CUDA kernels of the Hamiltonian Radau path, sm_100a.
+//
+// Kernels:
+//   radau_kernel<Ham,SM,VAR>   persistent fused integrator: one thread = one trajectory, lanes
+//                              refill from a global work counter when their trajectory ends
+//                              (active-set maintenance: finished trajectories stop costing work)
+//   dyns_kernel / jac_kernel   stage evaluation only (dual / hyper-dual), for the dyns /
+//                              dyns.jacobian surface of the API and for parity tests
+//   lu_kernel                  batched small dense LU factor+solve, real / complex
+//   detpow_kernel, dfma_kernel test hook and FP64 roofline probe
+// Compiled with -fmad=false: every fused multiply-add is an explicit fma() (arithmetic contract,
+// see radau_core.cuh).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/janus_b200.h"
+#include "radau_core.cuh"
+
+namespace jb {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define JB_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(JB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+// ------------------------------------------------------------------ kernels
+template <int NY>
+__device__ __forceinline__ void load_row(const double* __restrict__ src, long long m, double* dst) {
+  if (NY % 2 == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(src + m * NY);
+#pragma unroll
+    for (int i = 0; i < NY / 2; i++) {
+      const double2 v = __ldg(s2 + i);
+      dst[2 * i] = v.x;
+      dst[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NY; i++) dst[i] = __ldg(src + m * NY + i);
+  }
+}
+template <int NY>
+__device__ __forceinline__ void store_row(double* __restrict__ dst, long long m, const double* src) {
+  if (NY % 2 == 0) {
+    double2* d2 = reinterpret_cast<double2*>(dst + m * NY);
+#pragma unroll
+    for (int i = 0; i < NY / 2; i++) d2[i] = make_double2(src[2 * i], src[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NY; i++) dst[m * NY + i] = src[i];
+  }
+}
+
+template <class Ham, int SM, bool VAR>
+__global__ void __launch_bounds__(128) radau_kernel(const __grid_constant__ RadauParams P,
+                                                    const double* __restrict__ y0,
+                                                    const double* __restrict__ tspan, long long M,
+                                                    double* __restrict__ y_out, double* __restrict__ t_out,
+                                                    double* __restrict__ h_out, int* __restrict__ res,
+                                                    long long* __restrict__ stats, int* __restrict__ nstg,
+                                                    unsigned long long* __restrict__ counter) {
+  constexpr int NY = Ham::NV;
+  Traj<NY, SM> T;
+  long long m = -1;
+  bool have = false;
+  for (;;) {
+    if (!have) {
+      m = (long long)atomicAdd(counter, 1ull);
+      if (m >= M) break;
+      double y[NY];
+      load_row<NY>(y0, m, y);
+      const double2 ts = __ldg(reinterpret_cast<const double2*>(tspan) + m);
+      traj_init<Ham, NY, SM>(T, P, y, ts.x, ts.y);
+      have = true;
+    }
+    bool done = (T.res != 0) || !traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep);
+    if (!done) done = one_pass<Ham, NY, SM, VAR>(T, P);
+    if (done) {
+      if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
+      store_row<NY>(y_out, m, T.y);
+      t_out[m] = T.t;
+      h_out[m] = T.h;
+      res[m] = T.res;
+#pragma unroll
+      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
+      if (nstg) nstg[m] = T.NbrStg;
+      have = false;
+    }
+  }
+}
+
+template <class Ham>
+__global__ void dyns_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
+                            double* __restrict__ f) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double yy[NY], ff[NY];
+    load_row<NY>(y, m, yy);
+    ham_dyns<Ham>(yy, P.ham_par, P.sign, ff);
+    store_row<NY>(f, m, ff);
+  }
+}
+
+template <class Ham>
+__global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
+                           double* __restrict__ J) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double yy[NY], JJ[NY * NY];
+    load_row<NY>(y, m, yy);
+    ham_jac<Ham>(yy, P.ham_par, P.sign, JJ);
+#pragma unroll
+    for (int r = 0; r < NY; r++) store_row<NY>(J, m * NY + r, &JJ[r * NY]);
+  }
+}
+
+template <int N, bool CPLX>
+__global__ void lu_kernel(long long M, const double* __restrict__ Are, const double* __restrict__ Aim,
+                          const double* __restrict__ bre, const double* __restrict__ bim, double* __restrict__ xre,
+                          double* __restrict__ xim) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    if (!CPLX) {
+      RLU<N> L;
+#pragma unroll
+      for (int k = 0; k < N * N; k++) L.a[k] = Are[m * N * N + k];
+      rlu_factor<N>(L);
+      double b[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) b[k] = bre[m * N + k];
+      rlu_solve<N>(L, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) xre[m * N + k] = b[k];
+    } else {
+      ZLU<N> L;
+#pragma unroll
+      for (int k = 0; k < N * N; k++) {
+        L.re[k] = Are[m * N * N + k];
+        L.im[k] = Aim[m * N * N + k];
+      }
+      zlu_factor<N>(L);
+      double br[N], bi[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        br[k] = bre[m * N + k];
+        bi[k] = bim[m * N + k];
+      }
+      zlu_solve<N>(L, br, bi);
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        xre[m * N + k] = br[k];
+        xim[m * N + k] = bi[k];
+      }
+    }
+  }
+}
+
+__global__ void detpow_kernel(const double* x, const double* y, long long n, double* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = det_pow(x[i], y[i]);
+}
+
+// FP64 roofline probe: 16 independent DFMA chains per thread
+__global__ void dfma_kernel(int iters, double seed, double* sink) {
+  double a[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = seed + k * 1e-3 + threadIdx.x * 1e-6;
+  const double b = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = fma(a[k], b, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += a[k];
+  if (s == 123.456) sink[0] = s;
+}
+
+// ------------------------------------------------------------------ host side
+struct Handle {
+  int ham_id = 0, ny = 0, device = 0, sm_count = 148;
+  RadauParams P;
+  int kernel_sm = 3;     // SM template value in use
+  bool kernel_var = false;
+  unsigned long long* d_counter = nullptr;
+  int launches = 0;
+  // workspace of jb200_solve_host
+  long long cap = 0;
+  double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
+  int *d_res = nullptr, *d_nstg = nullptr;
+  long long* d_stats = nullptr;
+  cudaStream_t own_stream = nullptr;
+};
+
+static int ham_ny(int ham_id) {
+  switch (ham_id) {
+    case JB200_HAM_HARMONIC: return 2;
+    case JB200_HAM_VDP:
+    case JB200_HAM_VDP_PMP_SMOOTH:
+    case JB200_HAM_VDP_PMP_BANG:
+    case JB200_HAM_VDP_AUG_BANG: return 4;
+    default: return -1;
+  }
+}
+static int ham_npar(int ham_id) {
+  switch (ham_id) {
+    case JB200_HAM_HARMONIC: return 1;
+    case JB200_HAM_VDP: return 1;
+    case JB200_HAM_VDP_PMP_SMOOTH: return 1;
+    case JB200_HAM_VDP_PMP_BANG: return 3;
+    case JB200_HAM_VDP_AUG_BANG: return 2;
+    default: return -1;
+  }
+}
+
+// option checks of the reference constructor (radaute_impl.hpp:65-214), returned not exit()ed
+static int validate(const jb200_opts* o, int ny) {
+  if (o->n_tol != 1 && o->n_tol != ny) return fail(JB200_EINVAL, "RelTol/AbsTol: vector of length 1 or Ny");
+  for (int i = 0; i < o->n_tol; i++) {
+    if (!(o->AbsTol[i] >= 0)) return fail(JB200_EINVAL, "Wrong input AbsTol must be a positive number");
+    if (!(o->RelTol[i] >= 10 * EPS)) return fail(JB200_EINVAL, "Relative tolerance are too small.");
+  }
+  if (!(o->JacRecompute >= 0)) return fail(JB200_EINVAL, "JacRecompute must be positive");
+  if (o->JacRecompute >= 1.0) return fail(JB200_EINVAL, "Invalid JacRecompute must be less than one");
+  if (o->MaxNbrNewton < 4) return fail(JB200_EINVAL, "MaxNbrNewton integer >= 4");
+  const int stg[3] = {o->NbrStg, o->MinNbrStg, o->MaxNbrStg};
+  const char* nm[3] = {"NbrStg", "MinNbrStg", "MaxNbrStg"};
+  for (int k = 0; k < 3; k++)
+    if (stg[k] != 1 && stg[k] != 3 && stg[k] != 5 && stg[k] != 7)
+      return fail(JB200_EINVAL, std::string(nm[k]) + " must be 1, 3, 5 or 7");
+  if (o->NbrStg < o->MinNbrStg || o->NbrStg > o->MaxNbrStg)
+    return fail(JB200_EINVAL, "NbrStg must be between MinNbrStg and MaxNbrStg");
+  if (!(o->Safe > 0.001 && o->Safe < 1)) return fail(JB200_EINVAL, "Curious input for Safe, must be in ]0.001 .. 1[");
+  if (o->Quot1 > 1) return fail(JB200_EINVAL, "Curious input for Quot1, must be <=1");
+  if (o->Quot2 < 1) return fail(JB200_EINVAL, "Curious input for Quot2, must be >1");
+  if (!(o->FacL <= 1.0) || !(o->FacL > 0)) return fail(JB200_EINVAL, "Curious input for FacL default is 0.2");
+  if (!(o->FacR >= 1.0)) return fail(JB200_EINVAL, "Curious input for FacR default is 8.0");
+  if (!(o->Vitu >= 0)) return fail(JB200_EINVAL, "Curious input for Vitu default is 0.002");
+  if (!(o->Vitd >= 0)) return fail(JB200_EINVAL, "Curious input for Vitd default is 0.8");
+  if (!(o->hhou >= 1)) return fail(JB200_EINVAL, "Curious input for hhou default is 1.2");
+  if (!(o->hhod >= 0)) return fail(JB200_EINVAL, "Curious input for hhod default is 0.8");
+  if (o->costate_sign != 1 && o->costate_sign != -1) return fail(JB200_EINVAL, "costate_sign must be +1 or -1");
+  if (o->MaxNbrStep < 1 || o->MaxNbrStep > 2000000000LL) return fail(JB200_EINVAL, "MaxNbrStep out of range");
+  return 0;
+}
+
+// per-stage-count constants (radau.m:858-862, 897-900), computed once on the host
+static void fill_params(RadauParams& P, const jb200_opts* o, int ny, const double* hp, int nhp) {
+  std::memset(&P, 0, sizeof P);
+  for (int k = 0; k < 4; k++) {
+    const int s = 2 * k + 1;
+    const double ExpmNs = (s + 1.0) / (2.0 * s);
+    double mrt = INFINITY;
+    for (int i = 0; i < ny; i++) {
+      const double rt = o->RelTol[o->n_tol == 1 ? 0 : i], at = o->AbsTol[o->n_tol == 1 ? 0 : i];
+      const double quot = at / rt;
+      P.RelTol1[k][i] = 0.1 * std::pow(rt, ExpmNs);
+      P.AbsTol1[k][i] = P.RelTol1[k][i] * quot;
+      mrt = std::fmin(mrt, P.RelTol1[k][i]);
+    }
+    P.FNewt[k] = std::fmax(10 * EPS / mrt, std::fmin(0.03, std::pow(mrt, 1.0 / ExpmNs - 1.0)));
+    if (s == 1) P.FNewt[k] = std::fmax(10 * EPS / mrt, 0.03);
+    P.inv_sqrt_sn[k] = 1.0 / std::sqrt((double)(s * ny));
+  }
+  P.inv_sqrt_n = 1.0 / std::sqrt((double)ny);
+  P.InitialStep = o->InitialStep;
+  P.Thet = o->JacRecompute;
+  P.Safe = o->Safe;
+  P.Quot1 = o->Quot1;
+  P.Quot2 = o->Quot2;
+  P.FacL = 1.0 / o->FacL;  // radaute_impl.hpp:185,191
+  P.FacR = 1.0 / o->FacR;
+  P.Vitu = o->Vitu;
+  P.Vitd = o->Vitd;
+  P.hhou = o->hhou;
+  P.hhod = o->hhod;
+  P.sign = (double)o->costate_sign;
+  P.MaxNbrStep = o->MaxNbrStep;
+  P.Start_Newt = o->Start_Newt;
+  P.MaxNbrNewton = o->MaxNbrNewton;
+  P.NbrStg = o->NbrStg;
+  P.MinNbrStg = o->MinNbrStg;
+  P.MaxNbrStg = o->MaxNbrStg;
+  P.Gustafsson = o->Gustafsson;
+  for (int i = 0; i < nhp && i < JB200_MAX_HAM_PARAMS; i++) P.ham_par[i] = hp[i];
+}
+
+template <class Ham, int SM, bool VAR>
+static int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                        double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+  auto kern = radau_kernel<Ham, SM, VAR>;
+  int bps = 0;
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 128, 0));
+  if (bps < 1) bps = 1;
+  long long blocks = (long long)H->sm_count * bps;
+  const long long need = (M + 127) / 128;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
+  kern<<<(unsigned)blocks, 128, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, H->d_counter);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  return 0;
+}
+
+template <class Ham>
+static int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                          double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+  const RadauParams& P = H->P;
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
+    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
+    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+  if (P.MaxNbrStg <= 3)
+    return launch_radau<Ham, 3, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+  return launch_radau<Ham, 7, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+}
+
+#define JB_HAM_SWITCH(ID, CALL)                                              \
+  switch (ID) {                                                              \
+    case JB200_HAM_HARMONIC: { using HamT = HamHarmonic; return CALL; }      \
+    case JB200_HAM_VDP: { using HamT = HamVdp; return CALL; }                \
+    case JB200_HAM_VDP_PMP_SMOOTH: { using HamT = HamVdpPmp<false>; return CALL; } \
+    case JB200_HAM_VDP_PMP_BANG: { using HamT = HamVdpPmp<true>; return CALL; }    \
+    case JB200_HAM_VDP_AUG_BANG: { using HamT = HamVdpAugBang; return CALL; }      \
+    default: return fail(JB200_ENOTSUP, "unknown Hamiltonian id");           \
+  }
+
+static int solve_dev(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                     double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+  if (M <= 0) {
+    H->launches = 0;
+    return 0;
+  }
+  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st)));
+}
+
+template <class Ham>
+static int launch_dyns(Handle* H, const double* y, long long M, double* f, cudaStream_t st) {
+  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
+  dyns_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, f);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <class Ham>
+static int launch_jac(Handle* H, const double* y, long long M, double* J, cudaStream_t st) {
+  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
+  jac_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, J);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+static int launch_lu(long long M, const double* Are, const double* Aim, const double* bre, const double* bim,
+                     double* xre, double* xim, cudaStream_t st) {
+  const long long blocks = std::max<long long>(1, std::min<long long>((M + 127) / 128, 148 * 16));
+  if (Aim)
+    lu_kernel<N, true><<<(unsigned)blocks, 128, 0, st>>>(M, Are, Aim, bre, bim, xre, xim);
+  else
+    lu_kernel<N, false><<<(unsigned)blocks, 128, 0, st>>>(M, Are, nullptr, bre, nullptr, xre, nullptr);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_workspace(Handle* H, long long M) {
+  if (M <= H->cap) return 0;
+  cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats);
+  H->cap = 0;
+  const int ny = H->ny;
+  JB_CUDA(cudaMalloc(&H->d_y0, sizeof(double) * M * ny));
+  JB_CUDA(cudaMalloc(&H->d_ts, sizeof(double) * M * 2));
+  JB_CUDA(cudaMalloc(&H->d_y, sizeof(double) * M * ny));
+  JB_CUDA(cudaMalloc(&H->d_t, sizeof(double) * M));
+  JB_CUDA(cudaMalloc(&H->d_h, sizeof(double) * M));
+  JB_CUDA(cudaMalloc(&H->d_res, sizeof(int) * M));
+  JB_CUDA(cudaMalloc(&H->d_nstg, sizeof(int) * M));
+  JB_CUDA(cudaMalloc(&H->d_stats, sizeof(long long) * M * 8));
+  H->cap = M;
+  return 0;
+}
+
+}  // namespace jb
+
+using namespace jb;
+
+extern "C" {
+
+int jb200_opts_default(jb200_opts* o) {
+  if (!o) return fail(JB200_EINVAL, "null opts");
+  std::memset(o, 0, sizeof *o);
+  o->RelTol[0] = 1.0e-3;
+  o->AbsTol[0] = 1.0e-6;
+  o->n_tol = 1;
+  o->InitialStep = 1.0e-2;
+  o->MaxStep = 1.0;
+  o->JacRecompute = 1.0e-3;
+  o->Start_Newt = 0;
+  o->MaxNbrNewton = 7;
+  o->NbrStg = 3;
+  o->MinNbrStg = 3;
+  o->MaxNbrStg = 7;
+  o->MaxNbrStep = 10000;
+  o->Safe = 0.9;
+  o->Quot1 = 1.0;
+  o->Quot2 = 1.2;
+  o->FacL = 0.2;
+  o->FacR = 8.0;
+  o->Vitu = 0.002;
+  o->Vitd = 0.8;
+  o->hhou = 1.2;
+  o->hhod = 0.8;
+  o->Gustafsson = 1;
+  o->costate_sign = 1;
+  return 0;
+}
+
+int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int n_ham_params, void** handle) {
+  if (!o || !handle) return fail(JB200_EINVAL, "null argument");
+  const int ny = ham_ny(ham_id);
+  if (ny < 0) return fail(JB200_ENOTSUP, "unknown Hamiltonian id");
+  if (n_ham_params < ham_npar(ham_id) || (n_ham_params > 0 && !ham_params))
+    return fail(JB200_EINVAL, "Hamiltonian needs " + std::to_string(ham_npar(ham_id)) + " parameters");
+  int rc = validate(o, ny);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(JB200_ECUDA, "no CUDA device: janus_b200 has no CPU fallback");
+  Handle* H = new Handle();
+  H->ham_id = ham_id;
+  H->ny = ny;
+  fill_params(H->P, o, ny, ham_params, n_ham_params);
+  cudaError_t e = cudaGetDevice(&H->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&H->sm_count, cudaDevAttrMultiProcessorCount, H->device);
+  if (e == cudaSuccess) e = cudaMalloc(&H->d_counter, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete H;
+    return fail(JB200_ECUDA, std::string("jb200_create: ") + cudaGetErrorString(e));
+  }
+  *handle = H;
+  return 0;
+}
+
+void jb200_destroy(void* handle) {
+  Handle* H = (Handle*)handle;
+  if (!H) return;
+  cudaFree(H->d_counter);
+  cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats);
+  if (H->own_stream) cudaStreamDestroy(H->own_stream);
+  delete H;
+}
+
+int jb200_ny(void* handle) { return handle ? ((Handle*)handle)->ny : JB200_EINVAL; }
+
+int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
+                double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (M > 0 && (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats)) return fail(JB200_EINVAL, "null buffer");
+  return solve_dev(H, y0, tspan, (long long)M, y_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
+                   (cudaStream_t)stream);
+}
+
+int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
+                     double* h_out, int32_t* res, int64_t* stats, int32_t* nstg) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (M == 0) {
+    H->launches = 0;
+    return 0;
+  }
+  if (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats) return fail(JB200_EINVAL, "null buffer");
+  // tspan must be strictly monotonic (radaute_impl.hpp:54-59) -- checked here on the host copy
+  for (int64_t m = 0; m < M; m++)
+    if (!(tspan[2 * m + 1] != tspan[2 * m])) return fail(JB200_EINVAL, "Time vector must be strictly monotonic");
+  int rc = ensure_workspace(H, M);
+  if (rc) return rc;
+  cudaStream_t st = H->own_stream;
+  const int ny = H->ny;
+  JB_CUDA(cudaMemcpyAsync(H->d_y0, y0, sizeof(double) * M * ny, cudaMemcpyHostToDevice, st));
+  JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
+  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, st);
+  if (rc) return rc;
+  JB_CUDA(cudaMemcpyAsync(y_out, H->d_y, sizeof(double) * M * ny, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaMemcpyAsync(t_out, H->d_t, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaMemcpyAsync(h_out, H->d_h, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaMemcpyAsync(res, H->d_res, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaMemcpyAsync(stats, H->d_stats, sizeof(long long) * M * 8, cudaMemcpyDeviceToHost, st));
+  if (nstg) JB_CUDA(cudaMemcpyAsync(nstg, H->d_nstg, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int jb200_last_launches(void* handle) { return handle ? ((Handle*)handle)->launches : 0; }
+
+int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  JB_HAM_SWITCH(H->ham_id, (launch_dyns<HamT>(H, y, M, ydot, (cudaStream_t)stream)));
+}
+
+int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  JB_HAM_SWITCH(H->ham_id, (launch_jac<HamT>(H, y, M, jac, (cudaStream_t)stream)));
+}
+
+int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre, const double* bim,
+                   double* xre, double* xim, void* stream) {
+  if (M <= 0) return 0;
+  if (!Are || !bre || !xre) return fail(JB200_EINVAL, "null buffer");
+  if (Aim && (!bim || !xim)) return fail(JB200_EINVAL, "complex path needs bim and xim");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n) {
+    case 2: return launch_lu<2>(M, Are, Aim, bre, bim, xre, xim, st);
+    case 3: return launch_lu<3>(M, Are, Aim, bre, bim, xre, xim, st);
+    case 4: return launch_lu<4>(M, Are, Aim, bre, bim, xre, xim, st);
+    default: return fail(JB200_ENOTSUP, "jb200_lu_solve: n must be 2, 3 or 4");
+  }
+}
+
+int jb200_det_pow(const double* x, const double* y, int64_t n, double* out, void* stream) {
+  if (n <= 0) return 0;
+  detpow_kernel<<<(unsigned)std::min<long long>((n + 127) / 128, 148 * 8), 128, 0, (cudaStream_t)stream>>>(x, y, n, out);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int jb200_fp64_peak(int iters, double* tflops) {
+  if (!tflops || iters <= 0) return fail(JB200_EINVAL, "bad argument");
+  int dev = 0, sms = 148;
+  JB_CUDA(cudaGetDevice(&dev));
+  JB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  JB_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  JB_CUDA(cudaEventCreate(&e0));
+  JB_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256;
+  dfma_kernel<<<blocks, threads>>>(iters / 10 + 1, 1.0, sink);  // warm-up
+  JB_CUDA(cudaEventRecord(e0));
+  dfma_kernel<<<blocks, threads>>>(iters, 1.0, sink);
+  JB_CUDA(cudaEventRecord(e1));
+  JB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  JB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+const char* jb200_last_error(void) { return g_err.c_str(); }
+const char* jb200_version(void) { return "janus_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Built-in Hamiltonians and the H -> (dynamics, Jacobian) adaptor.
+//
+// Replaces /root/reference/src/cpp/janus_ode_common.hpp:2161-2217 (evalDyns / evalDynsU) and
+// :2220-2299 (evalJac / evalJacU).  State layout y = [p(0:N), x(N:2N)] (:2167-2169):
+//   ydot = [ sigma * dH/dx ; dH/dp ]      sigma = +1 reference (:2174-2184), -1 canonical
+//   J    = d ydot / d y = [[pppxH, pxpxH], [ppppH, pxppH]] with the sigma on the pdot rows.
+// A supplied control u = control(y) is evaluated on VALUES and held constant under
+// differentiation (evalDynsU/evalJacU semantics, :2188-2217, :2259-2299).
+//
+// A Hamiltonian is a struct with
+//   N, NV = 2N, NPAR, HAS_CONTROL
+//   template <class... V> static auto H(v0, ..., v_{NV-1}, const double* par, double u)
+//        arguments in y-order (p_1..p_N, x_1..x_N), each a D1/D2 number with its own mask
+//   static double control(const double* y, const double* par)          (if HAS_CONTROL)
+// User Hamiltonians compiled at run time (NVRTC) use exactly this interface.
+#pragma once
+#include <utility>
+
+#include "dual.cuh"
+
+namespace jb {
+
+// ids shared with include/janus_b200.h (JB200_HAM_*) and oracle/c/radau_oracle.c (PB_*)
+enum HamId {
+  HAM_HARMONIC = 0,
+  HAM_VDP = 1,
+  HAM_VDP_PMP_SMOOTH = 2,
+  HAM_VDP_PMP_BANG = 3,
+  HAM_VDP_AUG_BANG = 4,
+  HAM_MLP = 5
+};
+
+// C1: H = (p^2 + w^2 x^2)/2    (written with squares like the reference's pow(2))
+struct HamHarmonic {
+  static constexpr int N = 1, NV = 2, NPAR = 1;
+  static constexpr bool HAS_CONTROL = false;
+  template <class P, class X>
+  JB_HD static auto H(const P& p, const X& x, const double* par, double) {
+    const double w = par[0];
+    return (square(p) + (w * w) * square(x)) * 0.5;
+  }
+  JB_HD static double control(const double*, const double*) { return 0.0; }
+};
+
+// C2/C5: H = p1 x2 + p2 (mu (1 - x1^2) x2 - x1)
+struct HamVdp {
+  static constexpr int N = 2, NV = 4, NPAR = 1;
+  static constexpr bool HAS_CONTROL = false;
+  template <class P1, class P2, class X1, class X2>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+                      double) {
+    const double mu = par[0];
+    return p1 * x2 + p2 * (mu * (1.0 - x1 * x1) * x2 - x1);
+  }
+  JB_HD static double control(const double*, const double*) { return 0.0; }
+};
+
+// C3: Hu = p1 x2 + p2 u ((1 - x1^2) x2 - x1) + (W/2) u^2 + 1
+//     (/root/reference/tests/cpp/ode_solver_test.cpp:185-197), u frozen.
+template <bool BANG>
+struct HamVdpPmp {
+  static constexpr int N = 2, NV = 4, NPAR = 3;  // W, umin, umax
+  static constexpr bool HAS_CONTROL = true;
+  template <class P1, class P2, class X1, class X2>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+                      double u) {
+    const double W = par[0];
+    return p1 * x2 + p2 * u * ((1.0 - x1 * x1) * x2 - x1) + ((W / 2) * u * u + 1.0);
+  }
+  JB_HD static double control(const double* y, const double* par) {
+    const double p2 = y[1], x1 = y[2], x2 = y[3];
+    if (BANG)  // examples/cpp/radauted_vdp_aug_example.cpp:30-33
+      return (p2 * (1.0 - x1 * x1) * x2 < 0.0) ? par[2] : par[1];
+    return -p2 * ((1.0 - x1 * x1) * x2 - x1) / par[0];  // tests/cpp/ode_solver_test.cpp:17-24
+  }
+};
+
+// "augmented" vdP of examples/cpp/radauted_vdp_aug_example.cpp:23-46 ==
+// examples/python/aug_vdp_ref_test.py:6-27 :  H = p1 x2 + p2 (u (1 - x1^2) x2 - x1), bang-bang u
+struct HamVdpAugBang {
+  static constexpr int N = 2, NV = 4, NPAR = 2;  // umin, umax
+  static constexpr bool HAS_CONTROL = true;
+  template <class P1, class P2, class X1, class X2>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+                      double u) {
+    return p1 * x2 + p2 * (u * (1.0 - x1 * x1) * x2 - x1);
+  }
+  JB_HD static double control(const double* y, const double* par) {
+    const double p2 = y[1], x1 = y[2], x2 = y[3];
+    return (p2 * (1.0 - x1 * x1) * x2 < 0.0) ? par[1] : par[0];
+  }
+};
+
+// ------------------------------------------------------------------ adaptor
+template <class Ham, size_t... I>
+JB_HD auto ham_eval1(const double* y, const double* par, double u, std::index_sequence<I...>) {
+  return Ham::H(seed1<Ham::NV, (int)I>(y[I])..., par, u);
+}
+template <class Ham, size_t... I>
+JB_HD auto ham_eval2(const double* y, const double* par, double u, std::index_sequence<I...>) {
+  return Ham::H(seed2<Ham::NV, (int)I>(y[I])..., par, u);
+}
+
+// f = [sigma dH/dx ; dH/dp]
+template <class Ham>
+JB_HD void ham_dyns(const double* y, const double* par, double sign, double* f) {
+  constexpr int N = Ham::N, NV = Ham::NV;
+  const double u = Ham::HAS_CONTROL ? Ham::control(y, par) : 0.0;
+  const auto r = ham_eval1<Ham>(y, par, u, std::make_index_sequence<NV>{});
+  using R = decltype(r);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    // pdot_i = sigma dH/dx_i (variable N+i) ; xdot_i = dH/dp_i (variable i)
+    f[i] = JB_BIT(R::gm, N + i) ? sign * r.g[N + i] : 0.0;
+    f[N + i] = JB_BIT(R::gm, i) ? r.g[i] : 0.0;
+  }
+}
+
+// J[r][c] row-major NV x NV
+template <class Ham>
+JB_HD void ham_jac(const double* y, const double* par, double sign, double* J) {
+  constexpr int N = Ham::N, NV = Ham::NV;
+  const double u = Ham::HAS_CONTROL ? Ham::control(y, par) : 0.0;
+  const auto r = ham_eval2<Ham>(y, par, u, std::make_index_sequence<NV>{});
+  using R = decltype(r);
+#pragma unroll
+  for (int rr = 0; rr < NV; rr++) {
+#pragma unroll
+    for (int c = 0; c < NV; c++) {
+      // ydot_rr = d H / d v, v = N+rr (rr<N) or rr-N ; then d/dy_c
+      const int vi = (rr < N) ? (N + rr) : (rr - N);
+      const int a = vi < c ? vi : c, b = vi < c ? c : vi;
+      const int k = hidx(NV, a, b);
+      double val = JB_BIT(R::hm, k) ? r.h[k] : 0.0;
+      J[rr * NV + c] = (rr < N) ? sign * val : val;
+    }
+  }
+}
+
+}  // namespace jb

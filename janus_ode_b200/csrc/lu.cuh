@@ -1,0 +1,194 @@
+// Thread-local small dense LU with partial pivoting, real and complex (the janus-linear /
+// torch::linalg_lu_factor + lu_solve replacement on the Radau path).
+//
+// Reference call sites: /root/reference/src/cpp/radaute_impl.hpp:1558,1611 (lu_factor of
+// gamma/h I - J and (alpha + i beta)/h I - J, complex128) and :1754,1832,1927,1966 (lu_solve).
+// One thread owns one n x n matrix; n is a template parameter so every loop unrolls and the
+// matrix lives in registers (n <= 4) -- no shared-memory traffic, no shuffles.
+//
+// Pivot rule = LAPACK zgetf2 / izamax: first row with the largest |re| + |im| (strict >), rows
+// physically exchanged, multipliers formed by multiplying with the reciprocal of the pivot.
+// The row exchange is a predicated select over the candidate rows (register arrays cannot be
+// indexed dynamically).  The reciprocals of U's diagonal are kept for the solves.
+//
+// ARITHMETIC CONTRACT (mirrored by oracle/c/radau_oracle.c "mirror" mode):
+//   real     r = 1/a_kk ; l = a_ik*r ; a_ij = fma(-l, a_kj, a_ij)
+//   complex  inv = 1/fma(d,d,c*c) ; rr = c*inv ; ri = -d*inv      (pivot c + i d)
+//            lr = fma(-xi, ri, xr*rr) ; li = fma(xi, rr, xr*ri)
+//            ar_ij = fma(li, ui, fma(-lr, ur, ar_ij)) ; ai_ij = fma(-li, ur, fma(-lr, ui, ai_ij))
+//   solve    forward  s = fma(-l_ij, b_j, s)  (complex: sr = fma(li, bi_j, fma(-lr, br_j, sr)),
+//                                                       si = fma(-li, br_j, fma(-lr, bi_j, si)))
+//            backward same with u_ij, then b_i = s * rd_i
+//            (complex: br = fma(-si, ri, sr*rr), bi = fma(si, rr, sr*ri))
+#pragma once
+#include "detmath.cuh"
+
+namespace jb {
+
+template <int N>
+struct RLU {
+  double a[N * N];  // L\U row-major
+  double rd[N];     // 1 / U_kk
+  int piv[N];
+};
+
+template <int N>
+struct ZLU {
+  double re[N * N], im[N * N];
+  double rdre[N], rdim[N];
+  int piv[N];
+};
+
+template <int N>
+JB_HD void rlu_factor(RLU<N>& L) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    int p = k;
+    double best = fabs(L.a[k * N + k]);
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const double v = fabs(L.a[i * N + k]);
+      if (v > best) { best = v; p = i; }
+    }
+    L.piv[k] = p;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (p == i);
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        const double x = L.a[k * N + j], y = L.a[i * N + j];
+        L.a[k * N + j] = sw ? y : x;
+        L.a[i * N + j] = sw ? x : y;
+      }
+    }
+    const double r = 1.0 / L.a[k * N + k];
+    L.rd[k] = r;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const double l = L.a[i * N + k] * r;
+      L.a[i * N + k] = l;
+#pragma unroll
+      for (int j = k + 1; j < N; j++) L.a[i * N + j] = fma(-l, L.a[k * N + j], L.a[i * N + j]);
+    }
+  }
+}
+
+template <int N>
+JB_HD void rlu_solve(const RLU<N>& L, double* b) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (L.piv[k] == i);
+      const double x = b[k], y = b[i];
+      b[k] = sw ? y : x;
+      b[i] = sw ? x : y;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    double s = b[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) s = fma(-L.a[i * N + j], b[j], s);
+    b[i] = s;
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    double s = b[i];
+#pragma unroll
+    for (int j = i + 1; j < N; j++) s = fma(-L.a[i * N + j], b[j], s);
+    b[i] = s * L.rd[i];
+  }
+}
+
+template <int N>
+JB_HD void zlu_factor(ZLU<N>& L) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    int p = k;
+    double best = fabs(L.re[k * N + k]) + fabs(L.im[k * N + k]);
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const double v = fabs(L.re[i * N + k]) + fabs(L.im[i * N + k]);
+      if (v > best) { best = v; p = i; }
+    }
+    L.piv[k] = p;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (p == i);
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        double x = L.re[k * N + j], y = L.re[i * N + j];
+        L.re[k * N + j] = sw ? y : x;
+        L.re[i * N + j] = sw ? x : y;
+        x = L.im[k * N + j];
+        y = L.im[i * N + j];
+        L.im[k * N + j] = sw ? y : x;
+        L.im[i * N + j] = sw ? x : y;
+      }
+    }
+    const double c = L.re[k * N + k], d = L.im[k * N + k];
+    const double inv = 1.0 / fma(d, d, c * c);
+    const double rr = c * inv, ri = -d * inv;
+    L.rdre[k] = rr;
+    L.rdim[k] = ri;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const double xr = L.re[i * N + k], xi = L.im[i * N + k];
+      const double lr = fma(-xi, ri, xr * rr), li = fma(xi, rr, xr * ri);
+      L.re[i * N + k] = lr;
+      L.im[i * N + k] = li;
+#pragma unroll
+      for (int j = k + 1; j < N; j++) {
+        const double ur = L.re[k * N + j], ui = L.im[k * N + j];
+        L.re[i * N + j] = fma(li, ui, fma(-lr, ur, L.re[i * N + j]));
+        L.im[i * N + j] = fma(-li, ur, fma(-lr, ui, L.im[i * N + j]));
+      }
+    }
+  }
+}
+
+template <int N>
+JB_HD void zlu_solve(const ZLU<N>& L, double* br, double* bi) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (L.piv[k] == i);
+      double x = br[k], y = br[i];
+      br[k] = sw ? y : x;
+      br[i] = sw ? x : y;
+      x = bi[k];
+      y = bi[i];
+      bi[k] = sw ? y : x;
+      bi[i] = sw ? x : y;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) {
+      const double lr = L.re[i * N + j], li = L.im[i * N + j];
+      sr = fma(li, bi[j], fma(-lr, br[j], sr));
+      si = fma(-li, br[j], fma(-lr, bi[j], si));
+    }
+    br[i] = sr;
+    bi[i] = si;
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = i + 1; j < N; j++) {
+      const double ur = L.re[i * N + j], ui = L.im[i * N + j];
+      sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+      si = fma(-ui, br[j], fma(-ur, bi[j], si));
+    }
+    const double rr = L.rdre[i], ri = L.rdim[i];
+    br[i] = fma(-si, ri, sr * rr);
+    bi[i] = fma(si, rr, sr * ri);
+  }
+}
+
+}  // namespace jb

@@ -1,0 +1,542 @@
+// Per-trajectory variable-order Radau IIA stepper (1/3/5/7 stages), one thread = one trajectory.
+//
+// B200-native replacement of the reference's masked batch loop
+//   /root/reference/src/cpp/radaute_impl.hpp:537-1345 (RadauTe::solve), :1502-1661 (DecomRC),
+//   :1721-1897 (Solvrad), :1902-1986 (Estrad); scalar truth src/matlab/radau.m:630-1256;
+//   per-trajectory (any()) semantics of src/cpp/radauted_impl.hpp:620-1645.
+// The reference runs ~200 masked libtorch ops + ~100 host syncs per pass over [M,...] tensors.
+// Here the whole state machine of one trajectory -- Hamiltonian derivatives by (hyper-)dual
+// numbers, simplified Newton, real + complex LU, error estimate, step-size / order controller
+// -- runs inside one thread with its state in registers / local memory; HBM is touched once
+// per trajectory (load y0, tspan; store y, t, h, res, stats).
+//
+// Everything here is __host__ __device__ so that tests/hostsim can run the very same code on
+// the CPU for debugging (never part of the product library).
+//
+// Reference deviations kept/dropped: SURVEY.md 8a Q3, Q4, Q6-Q9 (same as oracle/radau_scalar.py).
+// ARITHMETIC CONTRACT: every floating-point operation below is a fixed IEEE sequence (explicit
+// fma() where fused, plain ops otherwise; the translation unit is compiled with -fmad=false so
+// nothing else is contracted).  oracle/c/radau_oracle.c in "mirror" mode follows the same
+// sequence, which gives bit-identical trajectories and counters.
+#pragma once
+#include "hamiltonians.cuh"
+#include "lu.cuh"
+#include "radau_tables_t.cuh"
+
+namespace jb {
+
+constexpr int NYMAX = 16;
+constexpr double EPS = 2.220446049250313e-16;
+
+enum { ST_FCN, ST_JAC, ST_DEC, ST_SOL, ST_STEP, ST_ACC, ST_REJ, ST_NREJ };
+
+// per-solve constants, filled on the host by fill_params() (csrc/capi.cu)
+struct RadauParams {
+  double RelTol1[4][NYMAX];  // 0.1 RelTol^ExpmNs        per stage count (index (s-1)/2)
+  double AbsTol1[4][NYMAX];  // RelTol1 * AbsTol/RelTol
+  double FNewt[4];           // Newton stopping threshold (radau.m:897-900)
+  double inv_sqrt_sn[4];     // 1/sqrt(s*Ny)
+  double inv_sqrt_n;         // 1/sqrt(Ny)
+  double InitialStep, Thet, Safe, Quot1, Quot2, FacL, FacR;  // FacL, FacR already inverted
+  double Vitu, Vitd, hhou, hhod;
+  double sign;
+  long long MaxNbrStep;
+  int Start_Newt, MaxNbrNewton, NbrStg, MinNbrStg, MaxNbrStg, Gustafsson;
+  double ham_par[8];
+};
+
+JB_HD constexpr int nit_of(int s, int MaxNbrNewton) {
+  return s == 1 ? MaxNbrNewton - 3 : s == 3 ? MaxNbrNewton : s == 5 ? MaxNbrNewton + 5 : MaxNbrNewton + 10;
+}
+
+template <int NY, int SM>
+struct Traj {
+  double y[NY], f0[NY], Jac[NY * NY], cont[SM * NY];
+  double t, tfinal, h, h_old, hopt, hacc, erracc, FacConv, Theta, Thetat, PosNeg, hmaxn;
+  int NbrStg, Newt, ChangeNbr;
+  bool Last, First, Reject, Keep, ChangeFlag, UnExpStepRej, UnExpNewtRej, NeedNewJac, NeedNewLU;
+  int res;
+  int st[8];
+  RLU<NY> L0;
+  ZLU<NY> Lc[(SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1];
+};
+
+JB_HD int imin(int a, int b) { return a < b ? a : b; }
+JB_HD int imax(int a, int b) { return a > b ? a : b; }
+JB_HD bool bad(double x) { return !(x - x == 0.0); }  // NaN or Inf
+
+JB_HD double ipow(double x, int n) {
+  double p = 1.0;
+  for (int k = 0; k < n; k++) p = p * x;
+  return p;
+}
+
+template <class Ham, int NY, int SM>
+JB_HD void traj_init(Traj<NY, SM>& T, const RadauParams& P, const double* y0, double t0, double tfinal) {
+  // radau.m:631-696 / radaute_impl.hpp:406-455
+#pragma unroll
+  for (int i = 0; i < NY; i++) T.y[i] = y0[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) T.st[i] = 0;
+#pragma unroll
+  for (int i = 0; i < SM * NY; i++) T.cont[i] = 0.0;
+  T.t = t0;
+  T.tfinal = tfinal;
+  T.PosNeg = (tfinal - t0) >= 0 ? 1.0 : -1.0;
+  T.NbrStg = P.NbrStg;
+  T.UnExpStepRej = T.UnExpNewtRej = T.Keep = T.ChangeFlag = false;
+  T.ChangeNbr = 0;
+  T.Theta = T.Thetat = 0.0;
+  T.hmaxn = fabs(tfinal - t0);
+  double h = P.InitialStep;
+  if (fabs(h) <= 10 * EPS) h = 1e-6;
+  h = T.PosNeg * fmin(fabs(h), T.hmaxn);
+  T.h_old = h;
+  T.hopt = h;
+  if ((T.t + h * 1.0001 - tfinal) * T.PosNeg >= 0) {
+    h = tfinal - T.t;
+    T.Last = true;
+  } else {
+    T.Last = false;
+  }
+  T.h = h;
+  T.FacConv = 1.0;
+  T.Reject = false;
+  T.First = true;
+  ham_dyns<Ham>(T.y, P.ham_par, P.sign, T.f0);
+  T.st[ST_FCN] += 1;
+  T.res = 0;
+#pragma unroll
+  for (int i = 0; i < NY; i++)
+    if (T.f0[i] != T.f0[i]) T.res = 2;
+  T.NeedNewJac = true;
+  T.NeedNewLU = true;
+  T.Newt = 0;
+  T.hacc = 0.0;
+  T.erracc = 0.0;
+}
+
+// gamma/h I - J and (alpha_q + i beta_q)/h I - J, factored (radaute_impl.hpp:1502-1625)
+template <int NY, int S, int SM>
+JB_HD void decomrc(Traj<NY, SM>& T) {
+  using Tab = RadauTab<S>;
+  const double rh = 1.0 / T.h;
+  const double valp0 = Tab::ValP(0) * rh;
+#pragma unroll
+  for (int i = 0; i < NY; i++)
+#pragma unroll
+    for (int j = 0; j < NY; j++) T.L0.a[i * NY + j] = (i == j) ? (valp0 - T.Jac[i * NY + j]) : -T.Jac[i * NY + j];
+  rlu_factor<NY>(T.L0);
+#pragma unroll
+  for (int q = 1; q <= (S - 1) / 2; q++) {
+    const double al = Tab::ValP(2 * q - 1) * rh, be = Tab::ValP(2 * q) * rh;
+    ZLU<NY>& Z = T.Lc[q - 1];
+#pragma unroll
+    for (int i = 0; i < NY; i++)
+#pragma unroll
+      for (int j = 0; j < NY; j++) {
+        Z.re[i * NY + j] = (i == j) ? (al - T.Jac[i * NY + j]) : -T.Jac[i * NY + j];
+        Z.im[i * NY + j] = (i == j) ? be : 0.0;
+      }
+    zlu_factor<NY>(Z);
+  }
+}
+
+// one pass of the outer loop = one attempted step (radau.m:733-1253).
+// returns true when the trajectory is finished (done or failed; T.res holds the code)
+template <class Ham, int NY, int S, int SM>
+JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
+  using Tab = RadauTab<S>;
+  constexpr int si = (S - 1) / 2;
+  const int Nit = nit_of(S, P.MaxNbrNewton);
+  double z[S * NY], w[S * NY];  // [stage][component]
+
+  if (T.NeedNewLU) {  // radau.m:827-844
+    decomrc<NY, S, SM>(T);
+    T.st[ST_DEC] += 1;
+    T.NeedNewLU = false;
+  }
+  const bool Variab = (P.MaxNbrStg - P.MinNbrStg) != 0;
+  if (Variab && T.Keep) {  // radau.m:846-853
+    T.Keep = false;
+    T.ChangeNbr += 1;
+    if (T.ChangeNbr >= 10 && S < P.MaxNbrStg) T.NeedNewJac = false;
+  }
+  if (0.1 * fabs(T.h) <= fabs(T.t) * EPS) {  // radau.m:855
+    T.res = 1;
+    return true;
+  }
+  double rscal[NY];
+#pragma unroll
+  for (int i = 0; i < NY; i++) {
+    const double sc = fma(P.RelTol1[si][i], fabs(T.y[i]), P.AbsTol1[si][i]);  // radau.m:858-862
+    rscal[i] = 1.0 / sc;
+  }
+  if (T.First || P.Start_Newt || T.ChangeFlag) {  // radau.m:872-891
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) {
+      z[k] = 0.0;
+      w[k] = 0.0;
+      T.cont[k] = 0.0;
+    }
+  } else {
+    const double hquot = T.h / T.h_old;
+#pragma unroll
+    for (int q = 0; q < S; q++) {
+      const double cq = Tab::C(q) * hquot;
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        double zq = (cq - Tab::C(0) + 1.0) * T.cont[(S - 1) * NY + i];
+#pragma unroll
+        for (int q1 = 2; q1 <= S; q1++) zq = (zq + T.cont[(S - q1) * NY + i]) * (cq - Tab::C(q1 - 1) + 1.0);
+        z[q * NY + i] = zq;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        double acc = Tab::TI(j, 0) * z[i];
+#pragma unroll
+        for (int q = 1; q < S; q++) acc = fma(Tab::TI(j, q), z[q * NY + i], acc);
+        w[j * NY + i] = acc;
+      }
+  }
+  // ------- simplified Newton (radau.m:897-1018)
+  const double FNewt = P.FNewt[si];
+  T.FacConv = det_pow(fmax(T.FacConv, EPS), 0.8);
+  T.Theta = fabs(P.Thet);
+  T.Newt = 0;
+  const double rh = 1.0 / T.h;
+  double NewNrm = 0.0, OldNrm = 0.0, thqold = 0.0;
+  bool newton_failed = false;
+  for (;;) {
+    T.Reject = false;  // radau.m:913 (quirk Q9)
+    T.Newt += 1;
+    if (T.Newt > Nit) {  // radau.m:915-925
+      T.UnExpStepRej = true;
+      T.st[ST_REJ] += 1;
+      T.st[ST_NREJ] += 1;
+      T.h = T.h * 0.5;
+      T.Reject = true;
+      T.Last = false;
+      T.NeedNewLU = true;
+      newton_failed = true;
+      break;
+    }
+    // stage right-hand sides f(y + z_q), then z = TI f  (radau.m:932-948)
+    {
+      double fq[S * NY];
+      bool nanf = false;
+#pragma unroll
+      for (int q = 0; q < S; q++) {
+        double yq[NY];
+#pragma unroll
+        for (int i = 0; i < NY; i++) yq[i] = T.y[i] + z[q * NY + i];
+        ham_dyns<Ham>(yq, P.ham_par, P.sign, &fq[q * NY]);
+#pragma unroll
+        for (int i = 0; i < NY; i++) nanf = nanf || (fq[q * NY + i] != fq[q * NY + i]);
+      }
+      if (nanf) {
+        T.res = 2;
+        return true;
+      }
+      T.st[ST_FCN] += S;
+#pragma unroll
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          double acc = Tab::TI(j, 0) * fq[i];
+#pragma unroll
+          for (int q = 1; q < S; q++) acc = fma(Tab::TI(j, q), fq[q * NY + i], acc);
+          z[j * NY + i] = acc;
+        }
+    }
+    // Solvrad (radaute_impl.hpp:1721-1868)
+    {
+      const double valp0 = Tab::ValP(0) * rh;
+#pragma unroll
+      for (int i = 0; i < NY; i++) z[i] = fma(-valp0, w[i], z[i]);
+      rlu_solve<NY>(T.L0, &z[0]);
+#pragma unroll
+      for (int q = 1; q <= (S - 1) / 2; q++) {
+        const int q2 = 2 * q - 1, q3 = 2 * q;
+        const double v2 = Tab::ValP(q2) * rh, v3 = Tab::ValP(q3) * rh;
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          const double a = fma(v3, w[q3 * NY + i], fma(-v2, w[q2 * NY + i], z[q2 * NY + i]));
+          const double b = fma(-v2, w[q3 * NY + i], fma(-v3, w[q2 * NY + i], z[q3 * NY + i]));
+          z[q2 * NY + i] = a;
+          z[q3 * NY + i] = b;
+        }
+        zlu_solve<NY>(T.Lc[q - 1], &z[q2 * NY], &z[q3 * NY]);
+      }
+    }
+    T.st[ST_SOL] += 1;
+    NewNrm = 0.0;  // radau.m:955-959
+#pragma unroll
+    for (int q = 0; q < S; q++) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        const double v = z[q * NY + i] * rscal[i];
+        s = fma(v, v, s);
+      }
+      NewNrm += ::sqrt(s);
+    }
+    NewNrm = NewNrm * P.inv_sqrt_sn[si];
+    if (bad(NewNrm)) {
+      T.res = 2;
+      return true;
+    }
+    if (T.Newt > 1 && T.Newt < Nit) {  // radau.m:962-996
+      const double thq = NewNrm / OldNrm;
+      if (T.Newt == 2) T.Theta = thq;
+      else T.Theta = ::sqrt(thq * thqold);
+      thqold = thq;
+      if (T.Theta < 0.99) {
+        T.FacConv = T.Theta / (1.0 - T.Theta);
+        const double dyth = T.FacConv * NewNrm * ipow(T.Theta, Nit - 1 - T.Newt) / FNewt;
+        if (dyth >= 1.0) {
+          const double qNewt = fmax(1.0e-4, fmin(20.0, dyth));
+          const double hhfac = 0.8 * det_pow(qNewt, -1.0 / (4.0 + Nit - 1 - T.Newt));
+          T.h = hhfac * T.h;
+          T.Reject = true;
+          T.Last = false;
+          T.UnExpNewtRej = hhfac <= 0.5;
+          T.st[ST_NREJ] += 1;
+          T.st[ST_REJ] += 1;
+          T.NeedNewLU = true;
+          newton_failed = true;
+          break;
+        }
+      } else {
+        T.h = T.h * 0.5;
+        T.Reject = true;
+        T.Last = false;
+        T.UnExpStepRej = true;
+        T.st[ST_REJ] += 1;
+        T.NeedNewLU = true;
+        newton_failed = true;
+        break;
+      }
+    }
+    OldNrm = fmax(NewNrm, EPS);  // radau.m:1001-1012
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) w[k] = w[k] + z[k];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        double acc = Tab::T(j, 0) * w[i];
+#pragma unroll
+        for (int q = 1; q < S; q++) acc = fma(Tab::T(j, q), w[q * NY + i], acc);
+        z[j * NY + i] = acc;
+      }
+    if (T.FacConv * NewNrm > FNewt) continue;  // radau.m:1014
+    break;
+  }
+  if (newton_failed) return false;  // radau.m:1020-1022
+
+  // ------- Estrad (radaute_impl.hpp:1902-1986)
+  double temp[NY], ev[NY];
+#pragma unroll
+  for (int i = 0; i < NY; i++) {
+    double s = z[i] * (Tab::Dd(0) * rh);
+#pragma unroll
+    for (int q = 1; q < S; q++) s = fma(z[q * NY + i], Tab::Dd(q) * rh, s);
+    temp[i] = s;
+    ev[i] = T.f0[i] + s;
+  }
+  rlu_solve<NY>(T.L0, ev);
+  double err;
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      const double v = ev[i] * rscal[i];
+      s = fma(v, v, s);
+    }
+    err = fmax(::sqrt(s) * P.inv_sqrt_n, 1e-10);
+  }
+  if (err >= 1.0 && (T.First || T.Reject)) {
+    double ya[NY];
+#pragma unroll
+    for (int i = 0; i < NY; i++) ya[i] = T.y[i] + err;  // sic: scalar err (radaute_impl.hpp:1951)
+    ham_dyns<Ham>(ya, P.ham_par, P.sign, ev);
+    T.st[ST_FCN] += 1;
+#pragma unroll
+    for (int i = 0; i < NY; i++) ev[i] = ev[i] + temp[i];
+    rlu_solve<NY>(T.L0, ev);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      const double v = ev[i] * rscal[i];
+      s = fma(v, v, s);
+    }
+    err = fmax(::sqrt(s) * P.inv_sqrt_n, 1e-10);
+  }
+  if (bad(err)) {
+    T.res = 2;
+    return true;
+  }
+  // ------- new step size (radau.m:1038-1050)
+  const double fac = fmin(P.Safe, (2.0 * Nit + 1.0) / (2.0 * Nit + T.Newt));
+  double quot = fmax(P.FacR, fmin(P.FacL, det_pow(err, 1.0 / S + 1.0) / fac));
+  double hnew = T.h / quot;
+  if (err < 1.0) {  // ------- accepted (radau.m:1054-1232)
+    T.First = false;
+    T.st[ST_ACC] += 1;
+    if (P.Gustafsson && !T.ChangeFlag) {
+      if (T.st[ST_ACC] > 1) {
+        const double ratio = err * err / T.erracc;
+        double root;
+        if (S == 1) root = ::sqrt(ratio);
+        else if (S == 3) root = ::sqrt(::sqrt(ratio));
+        else if (S == 7) root = ::sqrt(::sqrt(::sqrt(ratio)));
+        else root = det_pow(ratio, 1.0 / (S + 1.0));
+        double facgus = (T.hacc / T.h) * root / P.Safe;
+        facgus = fmax(P.FacR, fmin(P.FacL, facgus));
+        quot = fmax(quot, facgus);
+        hnew = T.h / quot;
+      }
+      T.hacc = T.h;
+      T.erracc = fmax(1.0e-2, err);
+    }
+    T.h_old = T.h;
+    T.t = T.t + T.h;
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.y[i] = T.y[i] + z[(S - 1) * NY + i];
+    // collocation polynomial (radau.m:1093-1107)
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.cont[(S - 1) * NY + i] = z[i] * (1.0 / Tab::C(0));
+#pragma unroll
+    for (int q = 1; q <= S - 1; q++) {
+      const double Fact = 1.0 / (Tab::C(S - q - 1) - Tab::C(S - q));
+#pragma unroll
+      for (int i = 0; i < NY; i++) T.cont[(q - 1) * NY + i] = (z[(S - q - 1) * NY + i] - z[(S - q) * NY + i]) * Fact;
+    }
+#pragma unroll
+    for (int jj = 2; jj <= S; jj++)
+#pragma unroll
+      for (int k = S; k >= jj; k--) {
+        const double Fact = (S - k == 0) ? 1.0 / (-Tab::C(jj - 1)) : 1.0 / (Tab::C(S - k - 1) - Tab::C(S - k + jj - 1));
+#pragma unroll
+        for (int i = 0; i < NY; i++) T.cont[(k - 1) * NY + i] = (T.cont[(k - 1) * NY + i] - T.cont[(k - 2) * NY + i]) * Fact;
+      }
+    T.NeedNewJac = true;
+    if (T.Last) {  // radau.m:1193-1197
+      T.h = T.hopt;
+      T.st[ST_REJ] += 1;
+      return true;
+    }
+    ham_dyns<Ham>(T.y, P.ham_par, P.sign, T.f0);
+    T.st[ST_FCN] += 1;
+    {
+      bool nanf = false;
+#pragma unroll
+      for (int i = 0; i < NY; i++) nanf = nanf || (T.f0[i] != T.f0[i]);
+      if (nanf) {
+        T.res = 2;
+        return true;
+      }
+    }
+    hnew = T.PosNeg * fmin(fabs(hnew), fabs(T.hmaxn));
+    T.hopt = T.PosNeg * fmin(fabs(T.h), fabs(hnew));
+    if (T.Reject) hnew = T.PosNeg * fmin(fabs(hnew), fabs(T.h));
+    T.Reject = false;
+    if ((T.t + hnew / P.Quot1 - T.tfinal) * T.PosNeg >= 0) {
+      T.h = T.tfinal - T.t;
+      T.Last = true;
+    } else {
+      const double qt = hnew / T.h;
+      if (T.Theta <= P.Thet && qt >= P.Quot1 && qt <= P.Quot2) {
+        T.Keep = true;
+        T.NeedNewJac = false;
+        T.NeedNewLU = false;
+        return false;
+      }
+      T.h = hnew;
+    }
+    T.NeedNewLU = true;
+    if (T.Theta <= P.Thet) T.NeedNewJac = false;
+  } else {  // ------- rejected (radau.m:1234-1253)
+    T.Reject = true;
+    T.Last = false;
+    if (T.First) T.h = T.h / 10.0;
+    else T.h = hnew;
+    if (T.st[ST_ACC] >= 1) T.st[ST_REJ] += 1;
+    T.NeedNewLU = true;
+  }
+  return false;
+}
+
+// head of a pass: Jacobian refresh + order selection (radau.m:733-824); returns false if the
+// trajectory must stop (NaN in the Jacobian)
+template <class Ham, int NY, int SM, bool VAR>
+JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
+  T.st[ST_STEP] += 1;
+  T.FacConv = det_pow(fmax(T.FacConv, EPS), 0.8);
+  if (T.NeedNewJac) {
+    ham_jac<Ham>(T.y, P.ham_par, P.sign, T.Jac);
+    bool nanf = false;
+#pragma unroll
+    for (int k = 0; k < NY * NY; k++) nanf = nanf || (T.Jac[k] != T.Jac[k]);
+    if (nanf) {
+      T.res = 2;
+      return false;
+    }
+    T.st[ST_JAC] += 1;
+    T.NeedNewJac = false;
+    T.NeedNewLU = true;
+  }
+  const bool Variab = (P.MaxNbrStg - P.MinNbrStg) != 0;
+  if (VAR && Variab && !T.Keep) {
+    T.ChangeNbr += 1;
+    int NbrStgNew = T.NbrStg;
+    const double hquot = T.h / T.h_old;
+    T.Thetat = fmin(10.0, fmax(T.Theta, T.Thetat * 0.5));
+    if (T.Newt > 1 && T.Thetat <= P.Vitu && hquot < P.hhou && hquot > P.hhod) NbrStgNew = imin(P.MaxNbrStg, T.NbrStg + 2);
+    if (T.Thetat >= P.Vitd || T.UnExpStepRej) NbrStgNew = imax(P.MinNbrStg, T.NbrStg - 2);
+    if (T.ChangeNbr >= 1 && T.UnExpNewtRej) NbrStgNew = imax(P.MinNbrStg, T.NbrStg - 2);
+    if (T.ChangeNbr <= 10) NbrStgNew = imin(T.NbrStg, NbrStgNew);
+    T.ChangeFlag = T.NbrStg != NbrStgNew;
+    T.UnExpNewtRej = false;
+    T.UnExpStepRej = false;
+    if (T.ChangeFlag) {
+      T.NbrStg = NbrStgNew;
+      T.ChangeNbr = 1;
+      T.NeedNewLU = true;
+    }
+  }
+  return true;
+}
+
+// whole integration of one trajectory.  VAR = false: fixed order S = SM (host guarantees
+// MinNbrStg == MaxNbrStg == NbrStg == SM); VAR = true: orders 1..SM selected at run time.
+template <class Ham, int NY, int SM, bool VAR>
+JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P) {
+  if (!pass_head<Ham, NY, SM, VAR>(T, P)) return true;
+  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P);
+  switch (T.NbrStg) {
+    case 1: return attempt_step<Ham, NY, 1, SM>(T, P);
+    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P);
+    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P);
+    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P);
+  }
+}
+
+JB_HD bool traj_active(double PosNeg, double t, double tfinal, int steps, long long MaxNbrStep) {
+  return steps <= MaxNbrStep && PosNeg * t < PosNeg * tfinal;
+}
+
+template <class Ham, int NY, int SM, bool VAR>
+JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P) {
+  if (T.res != 0) return;
+  while (traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
+    if (one_pass<Ham, NY, SM, VAR>(T, P)) return;
+  }
+  if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;  // MaxNbrStep exceeded
+}
+
+}  // namespace jb

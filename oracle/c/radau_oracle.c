@@ -43,6 +43,79 @@
 #define SMAX 7
 #define EPS 2.220446049250313e-16
 
+/*
+ * Arithmetic modes (same control flow, different roundoff realisation):
+ *   g_mirror = 0  "reference": what the reference's libtorch CPU ops do -- no fused multiply-add,
+ *                 true divisions, libm pow, closed-form derivatives.
+ *   g_mirror = 1  "mirror": the documented ARITHMETIC CONTRACT of the CUDA path
+ *                 (janus_ode_b200/csrc/{dual,lu,radau_core,detmath}.cuh): fma() in the same
+ *                 places, reciprocal-multiplies, deterministic pow/log/exp built from IEEE basic
+ *                 ops, derivatives of H by (dense) dual / hyper-dual arithmetic.  Bit-identical
+ *                 to the GPU.  Needed because the algorithm's accepted-step counts are sensitive
+ *                 to the last bit (tests/test_oracle_sensitivity.py: recompiling THIS file with
+ *                 FMA contraction alone changes >1% of the counts).
+ * Set once before a (parallel) solve; read-only inside.
+ */
+static int g_mirror = 0;
+#define FMA(a, b, c) (g_mirror ? fma((a), (b), (c)) : ((a) * (b) + (c)))
+
+/* ---- deterministic log/exp/pow: same sequence as csrc/detmath.cuh ---- */
+static double det_log(double x) {
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  int64_t b;
+  memcpy(&b, &x, 8);
+  int e = (int)((b >> 52) & 0x7ff) - 1023;
+  int64_t mb = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+  double m;
+  memcpy(&m, &mb, 8);
+  if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+  const double r = (m - 1.0) / (m + 1.0);
+  const double r2 = r * r;
+  double p = 1.0 / 23.0;
+  p = fma(p, r2, 1.0 / 21.0);
+  p = fma(p, r2, 1.0 / 19.0);
+  p = fma(p, r2, 1.0 / 17.0);
+  p = fma(p, r2, 1.0 / 15.0);
+  p = fma(p, r2, 1.0 / 13.0);
+  p = fma(p, r2, 1.0 / 11.0);
+  p = fma(p, r2, 1.0 / 9.0);
+  p = fma(p, r2, 1.0 / 7.0);
+  p = fma(p, r2, 1.0 / 5.0);
+  p = fma(p, r2, 1.0 / 3.0);
+  const double t = r + r;
+  const double logm = fma(t * r2, p, t);
+  const double ed = (double)e;
+  return fma(ed, LN2_HI, fma(ed, LN2_LO, logm));
+}
+static double det_exp(double t) {
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  const double INV_LN2 = 1.44269504088896338700e+00;
+  const double kd = floor(fma(t, INV_LN2, 0.5));
+  double r = fma(-kd, LN2_HI, t);
+  r = fma(-kd, LN2_LO, r);
+  double q = 1.0 / 6227020800.0;
+  q = fma(q, r, 1.0 / 479001600.0);
+  q = fma(q, r, 1.0 / 39916800.0);
+  q = fma(q, r, 1.0 / 3628800.0);
+  q = fma(q, r, 1.0 / 362880.0);
+  q = fma(q, r, 1.0 / 40320.0);
+  q = fma(q, r, 1.0 / 5040.0);
+  q = fma(q, r, 1.0 / 720.0);
+  q = fma(q, r, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const int64_t k = (int64_t)kd;
+  const int64_t sb = (k + 1023) << 52;
+  double scale;
+  memcpy(&scale, &sb, 8);
+  return q * scale;
+}
+static double det_pow(double x, double y) { return det_exp(y * det_log(x)); }
+static double POW(double x, double y) { return g_mirror ? det_pow(x, y) : pow(x, y); }
+
 /* ---- problem ids (shared numbering with include/janus_b200.h JB200_HAM_*) ---- */
 enum {
   PB_HARMONIC = 0,      /* par[0]=omega                      N=1 */
@@ -75,9 +148,145 @@ static double bang(double p2, double x1, double x2, double umin, double umax) {
 
 static void mlp_eval(const problem_t *pb, const double *y, double *f, double *J);
 
+/* ------------------------------------------------------------------ mirror-mode derivatives
+ * Dense dual / hyper-dual arithmetic following the ARITHMETIC CONTRACT of csrc/dual.cuh (the
+ * GPU's compile-time-sparse numbers skip structurally-zero entries; adding / multiplying exact
+ * zeros here gives the same bits).  The Hamiltonians below repeat the expression trees of
+ * csrc/hamiltonians.cuh operation by operation.                                             */
+#define DNV 4
+#define DNH (DNV * (DNV + 1) / 2)
+typedef struct { double v, g[DNV], h[DNH]; } dd_t;
+static int dd_hidx(int nv, int i, int j) { return i * nv - (i * (i - 1)) / 2 + (j - i); }
+
+static dd_t dd_seed(int nv, int i, double v) {
+  dd_t r;
+  memset(&r, 0, sizeof r);
+  (void)nv;
+  r.v = v;
+  r.g[i] = 1.0;
+  return r;
+}
+static dd_t dd_add(int nv, int ord, dd_t a, dd_t b) {
+  dd_t r;
+  r.v = a.v + b.v;
+  for (int i = 0; i < nv; i++) r.g[i] = a.g[i] + b.g[i];
+  if (ord > 1) for (int k = 0; k < nv * (nv + 1) / 2; k++) r.h[k] = a.h[k] + b.h[k];
+  return r;
+}
+static dd_t dd_sub(int nv, int ord, dd_t a, dd_t b) {
+  dd_t r;
+  r.v = a.v - b.v;
+  for (int i = 0; i < nv; i++) r.g[i] = a.g[i] - b.g[i];
+  if (ord > 1) for (int k = 0; k < nv * (nv + 1) / 2; k++) r.h[k] = a.h[k] - b.h[k];
+  return r;
+}
+static dd_t dd_mul(int nv, int ord, dd_t a, dd_t b) {
+  dd_t r;
+  r.v = a.v * b.v;
+  for (int i = 0; i < nv; i++) r.g[i] = fma(a.g[i], b.v, a.v * b.g[i]);
+  if (ord > 1)
+    for (int i = 0; i < nv; i++)
+      for (int j = i; j < nv; j++) {
+        int k = dd_hidx(nv, i, j);
+        double t = a.v * b.h[k];
+        t = fma(a.g[i], b.g[j], t);
+        t = fma(a.g[j], b.g[i], t);
+        t = fma(a.h[k], b.v, t);
+        r.h[k] = t;
+      }
+  return r;
+}
+static dd_t dd_mulc(int nv, int ord, dd_t a, double c) {
+  dd_t r;
+  r.v = a.v * c;
+  for (int i = 0; i < nv; i++) r.g[i] = a.g[i] * c;
+  if (ord > 1) for (int k = 0; k < nv * (nv + 1) / 2; k++) r.h[k] = a.h[k] * c;
+  return r;
+}
+static dd_t dd_csub(int nv, int ord, double c, dd_t a) { /* c - a */
+  dd_t r;
+  r.v = c - a.v;
+  for (int i = 0; i < nv; i++) r.g[i] = -a.g[i];
+  if (ord > 1) for (int k = 0; k < nv * (nv + 1) / 2; k++) r.h[k] = -a.h[k];
+  return r;
+}
+static dd_t dd_addc(dd_t a, double c) { a.v = a.v + c; return a; }
+
+static double control_of(const problem_t *pb, const double *y) {
+  switch (pb->id) {
+    case PB_VDP_PMP_SMOOTH: return -y[1] * ((1.0 - y[2] * y[2]) * y[3] - y[2]) / pb->par[0];
+    case PB_VDP_PMP_BANG: return (y[1] * (1.0 - y[2] * y[2]) * y[3] < 0.0) ? pb->par[2] : pb->par[1];
+    case PB_VDP_AUG_BANG: return (y[1] * (1.0 - y[2] * y[2]) * y[3] < 0.0) ? pb->par[1] : pb->par[0];
+    default: return 0.0;
+  }
+}
+
+/* H evaluated on dual numbers; variables in y-order (p..., x...) */
+static dd_t ham_mirror(const problem_t *pb, const double *y, int ord) {
+  const int nv = pb->Ny;
+  const double u = control_of(pb, y);
+  switch (pb->id) {
+    case PB_HARMONIC: {
+      const double w = pb->par[0];
+      dd_t p = dd_seed(nv, 0, y[0]), x = dd_seed(nv, 1, y[1]);
+      dd_t t1 = dd_mul(nv, ord, p, p), t2 = dd_mul(nv, ord, x, x);
+      return dd_mulc(nv, ord, dd_add(nv, ord, t1, dd_mulc(nv, ord, t2, w * w)), 0.5);
+    }
+    case PB_VDP: {
+      const double mu = pb->par[0];
+      dd_t p1 = dd_seed(nv, 0, y[0]), p2 = dd_seed(nv, 1, y[1]), x1 = dd_seed(nv, 2, y[2]), x2 = dd_seed(nv, 3, y[3]);
+      dd_t a = dd_mul(nv, ord, p1, x2);
+      dd_t c = dd_csub(nv, ord, 1.0, dd_mul(nv, ord, x1, x1));
+      dd_t e = dd_mul(nv, ord, dd_mulc(nv, ord, c, mu), x2);
+      dd_t g = dd_mul(nv, ord, p2, dd_sub(nv, ord, e, x1));
+      return dd_add(nv, ord, a, g);
+    }
+    case PB_VDP_PMP_SMOOTH:
+    case PB_VDP_PMP_BANG: {
+      const double W = pb->par[0];
+      dd_t p1 = dd_seed(nv, 0, y[0]), p2 = dd_seed(nv, 1, y[1]), x1 = dd_seed(nv, 2, y[2]), x2 = dd_seed(nv, 3, y[3]);
+      dd_t a = dd_mul(nv, ord, p1, x2);
+      dd_t pu = dd_mulc(nv, ord, p2, u);
+      dd_t c = dd_csub(nv, ord, 1.0, dd_mul(nv, ord, x1, x1));
+      dd_t f = dd_sub(nv, ord, dd_mul(nv, ord, c, x2), x1);
+      dd_t r = dd_add(nv, ord, a, dd_mul(nv, ord, pu, f));
+      return dd_addc(r, (W / 2) * u * u + 1.0);
+    }
+    default: { /* PB_VDP_AUG_BANG */
+      dd_t p1 = dd_seed(nv, 0, y[0]), p2 = dd_seed(nv, 1, y[1]), x1 = dd_seed(nv, 2, y[2]), x2 = dd_seed(nv, 3, y[3]);
+      dd_t a = dd_mul(nv, ord, p1, x2);
+      dd_t c = dd_csub(nv, ord, 1.0, dd_mul(nv, ord, x1, x1));
+      dd_t e = dd_mul(nv, ord, dd_mulc(nv, ord, c, u), x2);
+      dd_t g = dd_mul(nv, ord, p2, dd_sub(nv, ord, e, x1));
+      return dd_add(nv, ord, a, g);
+    }
+  }
+}
+
+static void rhs_mirror(const problem_t *pb, const double *y, double *f) {
+  const int nv = pb->Ny, N = nv / 2;
+  dd_t r = ham_mirror(pb, y, 1);
+  for (int i = 0; i < N; i++) {
+    f[i] = pb->sign * r.g[N + i];
+    f[N + i] = r.g[i];
+  }
+}
+static void jac_mirror(const problem_t *pb, const double *y, double *J) {
+  const int nv = pb->Ny, N = nv / 2;
+  dd_t r = ham_mirror(pb, y, 2);
+  for (int rr = 0; rr < nv; rr++)
+    for (int c = 0; c < nv; c++) {
+      int vi = (rr < N) ? (N + rr) : (rr - N);
+      int a = vi < c ? vi : c, b = vi < c ? c : vi;
+      double val = r.h[dd_hidx(nv, a, b)];
+      J[rr * nv + c] = (rr < N) ? pb->sign * val : val;
+    }
+}
+
 static void rhs(const problem_t *pb, double t, const double *y, double *f) {
   (void)t;
   const double sg = pb->sign;
+  if (g_mirror && pb->id != PB_MLP) { rhs_mirror(pb, y, f); return; }
   switch (pb->id) {
     case PB_HARMONIC: {
       double w = pb->par[0];
@@ -119,6 +328,7 @@ static void jacobian(const problem_t *pb, double t, const double *y, double *J /
   (void)t;
   const int n = pb->Ny;
   const double sg = pb->sign;
+  if (g_mirror && pb->id != PB_MLP) { jac_mirror(pb, y, J); return; }
   memset(J, 0, sizeof(double) * n * n);
   switch (pb->id) {
     case PB_HARMONIC: {
@@ -260,7 +470,7 @@ static void rlu_factor(int n, rlu_t *L) {
     for (int i = k + 1; i < n; i++) {
       double l = a[i * n + k] * r;
       a[i * n + k] = l;
-      for (int j = k + 1; j < n; j++) a[i * n + j] = a[i * n + j] - l * a[k * n + j];
+      for (int j = k + 1; j < n; j++) a[i * n + j] = FMA(-l, a[k * n + j], a[i * n + j]);
     }
   }
 }
@@ -273,12 +483,12 @@ static void rlu_solve(int n, const rlu_t *L, double *b) {
   }
   for (int i = 1; i < n; i++) {
     double s = b[i];
-    for (int j = 0; j < i; j++) s = s - a[i * n + j] * b[j];
+    for (int j = 0; j < i; j++) s = FMA(-a[i * n + j], b[j], s);
     b[i] = s;
   }
   for (int i = n - 1; i >= 0; i--) {
     double s = b[i];
-    for (int j = i + 1; j < n; j++) s = s - a[i * n + j] * b[j];
+    for (int j = i + 1; j < n; j++) s = FMA(-a[i * n + j], b[j], s);
     b[i] = s * L->rd[i];
   }
 }
@@ -299,17 +509,22 @@ static void zlu_factor(int n, zlu_t *L) {
         tmp = ai[k * n + j]; ai[k * n + j] = ai[p * n + j]; ai[p * n + j] = tmp;
       }
     double c = ar[k * n + k], d = ai[k * n + k];
-    double inv = 1.0 / (c * c + d * d);
+    double inv = 1.0 / FMA(d, d, c * c);
     double rr = c * inv, ri = -d * inv;
     L->rdre[k] = rr; L->rdim[k] = ri;
     for (int i = k + 1; i < n; i++) {
       double xr = ar[i * n + k], xi = ai[i * n + k];
-      double lr = xr * rr - xi * ri, li = xr * ri + xi * rr;
+      double lr = FMA(-xi, ri, xr * rr), li = FMA(xi, rr, xr * ri);
       ar[i * n + k] = lr; ai[i * n + k] = li;
       for (int j = k + 1; j < n; j++) {
         double ur = ar[k * n + j], ui = ai[k * n + j];
-        ar[i * n + j] = ar[i * n + j] - (lr * ur - li * ui);
-        ai[i * n + j] = ai[i * n + j] - (lr * ui + li * ur);
+        if (g_mirror) {
+          ar[i * n + j] = fma(li, ui, fma(-lr, ur, ar[i * n + j]));
+          ai[i * n + j] = fma(-li, ur, fma(-lr, ui, ai[i * n + j]));
+        } else {
+          ar[i * n + j] = ar[i * n + j] - (lr * ur - li * ui);
+          ai[i * n + j] = ai[i * n + j] - (lr * ui + li * ur);
+        }
       }
     }
   }
@@ -328,8 +543,13 @@ static void zlu_solve(int n, const zlu_t *L, double *br, double *bi) {
     double sr = br[i], si = bi[i];
     for (int j = 0; j < i; j++) {
       double lr = ar[i * n + j], li = ai[i * n + j];
-      sr = sr - (lr * br[j] - li * bi[j]);
-      si = si - (lr * bi[j] + li * br[j]);
+      if (g_mirror) {
+        sr = fma(li, bi[j], fma(-lr, br[j], sr));
+        si = fma(-li, br[j], fma(-lr, bi[j], si));
+      } else {
+        sr = sr - (lr * br[j] - li * bi[j]);
+        si = si - (lr * bi[j] + li * br[j]);
+      }
     }
     br[i] = sr; bi[i] = si;
   }
@@ -337,12 +557,17 @@ static void zlu_solve(int n, const zlu_t *L, double *br, double *bi) {
     double sr = br[i], si = bi[i];
     for (int j = i + 1; j < n; j++) {
       double ur = ar[i * n + j], ui = ai[i * n + j];
-      sr = sr - (ur * br[j] - ui * bi[j]);
-      si = si - (ur * bi[j] + ui * br[j]);
+      if (g_mirror) {
+        sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+        si = fma(-ui, br[j], fma(-ur, bi[j], si));
+      } else {
+        sr = sr - (ur * br[j] - ui * bi[j]);
+        si = si - (ur * bi[j] + ui * br[j]);
+      }
     }
     double rr = L->rdre[i], ri = L->rdim[i];
-    br[i] = sr * rr - si * ri;
-    bi[i] = sr * ri + si * rr;
+    br[i] = FMA(-si, ri, sr * rr);
+    bi[i] = FMA(si, rr, sr * ri);
   }
 }
 
@@ -421,14 +646,14 @@ static void solvrad(int n, const tab_t *tb, double h, const lus_t *lu, double z[
   double rh = 1.0 / h;
   double valp[SMAX];
   for (int q = 0; q < tb->s; q++) valp[q] = tb->ValP[q] * rh;
-  for (int i = 0; i < n; i++) z[0][i] = z[0][i] - valp[0] * w[0][i];
+  for (int i = 0; i < n; i++) z[0][i] = FMA(-valp[0], w[0][i], z[0][i]);
   rlu_solve(n, &lu->L0, z[0]);
   for (int q = 1; q <= (tb->s - 1) / 2; q++) {
     int q2 = 2 * q - 1, q3 = 2 * q;
     double z2[NYMAX], z3[NYMAX];
     for (int i = 0; i < n; i++) {
-      z2[i] = z[q2][i] - valp[q2] * w[q2][i] + valp[q3] * w[q3][i];
-      z3[i] = z[q3][i] - valp[q3] * w[q2][i] - valp[q2] * w[q3][i];
+      z2[i] = FMA(valp[q3], w[q3][i], FMA(-valp[q2], w[q2][i], z[q2][i]));
+      z3[i] = FMA(-valp[q2], w[q3][i], FMA(-valp[q3], w[q2][i], z[q3][i]));
     }
     zlu_solve(n, &lu->Lc[q - 1], z2, z3);
     for (int i = 0; i < n; i++) { z[q2][i] = z2[i]; z[q3][i] = z3[i]; }
@@ -437,7 +662,7 @@ static void solvrad(int n, const tab_t *tb, double h, const lus_t *lu, double z[
 
 static double scaled_norm(int n, const double *v, const double *Scal) {
   double s = 0.0;
-  for (int i = 0; i < n; i++) { double q = v[i] / Scal[i]; s += q * q; }
+  for (int i = 0; i < n; i++) { double q = g_mirror ? v[i] * (1.0 / Scal[i]) : v[i] / Scal[i]; s = FMA(q, q, s); }
   return sqrt(s);
 }
 
@@ -448,13 +673,13 @@ static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t
   double rh = 1.0 / h, temp[NYMAX], ev[NYMAX];
   for (int i = 0; i < n; i++) {
     double s = 0.0;
-    for (int q = 0; q < tb->s; q++) s += z[q][i] * (tb->Dd[q] * rh);
+    for (int q = 0; q < tb->s; q++) s = FMA(z[q][i], tb->Dd[q] * rh, s);
     temp[i] = s;
     ev[i] = f0[i] + s;
   }
   rlu_solve(n, &lu->L0, ev);
   double err = scaled_norm(n, ev, Scal);
-  err = fmax(err / sqrt((double)n), 1e-10);
+  err = g_mirror ? fmax(err * (1.0 / sqrt((double)n)), 1e-10) : fmax(err / sqrt((double)n), 1e-10);
   if (err >= 1.0 && (First || Reject)) {
     double ya[NYMAX];
     for (int i = 0; i < n; i++) ya[i] = y[i] + err;
@@ -463,7 +688,7 @@ static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t
     for (int i = 0; i < n; i++) ev[i] = ev[i] + temp[i];
     rlu_solve(n, &lu->L0, ev);
     err = scaled_norm(n, ev, Scal);
-    err = fmax(err / sqrt((double)n), 1e-10);
+    err = g_mirror ? fmax(err * (1.0 / sqrt((double)n)), 1e-10) : fmax(err / sqrt((double)n), 1e-10);
   }
   return err;
 }
@@ -506,7 +731,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
     QuotTol[i] = op->AbsTol[i] / op->RelTol[i];
     RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
     AbsTol1[i] = RelTol1[i] * QuotTol[i];
-    Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+    Scal[i] = FMA(RelTol1[i], fabs(y[i]), AbsTol1[i]);
   }
   rhs(pb, t, y, f0);
   st[ST_FCN] += 1;
@@ -518,7 +743,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
 
   while (st[ST_STEP] <= op->MaxNbrStep && PosNeg * t < PosNeg * tfinal) {
     st[ST_STEP] += 1;
-    FacConv = pow(fmax(FacConv, EPS), 0.8);
+    FacConv = POW(fmax(FacConv, EPS), 0.8);
     if (NeedNewJac) {
       jacobian(pb, t, y, Jac);
       if (any_nan(Jac, n * n)) { res = 2; break; }
@@ -545,7 +770,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
         for (int i = 0; i < n; i++) {
           RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
           AbsTol1[i] = RelTol1[i] * QuotTol[i];
-          Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+          Scal[i] = FMA(RelTol1[i], fabs(y[i]), AbsTol1[i]);
         }
         NeedNewLU = 1;
         SqrtStgNy = sqrt((double)(NbrStg * n));
@@ -569,7 +794,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       QuotTol[i] = op->AbsTol[i] / op->RelTol[i];
       RelTol1[i] = 0.1 * pow(op->RelTol[i], ExpmNs);
       AbsTol1[i] = RelTol1[i] * QuotTol[i];
-      Scal[i] = AbsTol1[i] + RelTol1[i] * fabs(y[i]);
+      Scal[i] = FMA(RelTol1[i], fabs(y[i]), AbsTol1[i]);
       mrt = fmin(mrt, RelTol1[i]);
     }
     const int s = NbrStg;
@@ -588,13 +813,13 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       for (int j = 0; j < s; j++)
         for (int i = 0; i < n; i++) {
           double acc = tb.TI[j][0] * z[0][i];
-          for (int q = 1; q < s; q++) acc = acc + tb.TI[j][q] * z[q][i];
+          for (int q = 1; q < s; q++) acc = FMA(tb.TI[j][q], z[q][i], acc);
           w[j][i] = acc;
         }
     }
     double FNewt = fmax(10 * EPS / mrt, fmin(0.03, pow(mrt, 1.0 / ExpmNs - 1.0)));
     if (s == 1) FNewt = fmax(10 * EPS / mrt, 0.03);
-    FacConv = pow(fmax(FacConv, EPS), 0.8);
+    FacConv = POW(fmax(FacConv, EPS), 0.8);
     Theta = fabs(Thet);
     Newt = 0;
     int newton_failed = 0, nan_fail = 0;
@@ -620,14 +845,14 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       for (int j = 0; j < s; j++)
         for (int i = 0; i < n; i++) {
           double acc = tb.TI[j][0] * fq[0][i];
-          for (int q = 1; q < s; q++) acc = acc + tb.TI[j][q] * fq[q][i];
+          for (int q = 1; q < s; q++) acc = FMA(tb.TI[j][q], fq[q][i], acc);
           z[j][i] = acc;
         }
       solvrad(n, &tb, h, &lu, z, w);
       st[ST_SOL] += 1;
       NewNrm = 0.0;
       for (int q = 0; q < s; q++) NewNrm += scaled_norm(n, z[q], Scal);
-      NewNrm = NewNrm / SqrtStgNy;
+      NewNrm = g_mirror ? NewNrm * (1.0 / SqrtStgNy) : NewNrm / SqrtStgNy;
       if (!isfinite(NewNrm)) { nan_fail = 1; break; }
       if (Newt > 1 && Newt < tb.Nit) {
         double thq = NewNrm / OldNrm;
@@ -635,10 +860,13 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
         thqold = thq;
         if (Theta < 0.99) {
           FacConv = Theta / (1.0 - Theta);
-          double dyth = FacConv * NewNrm * pow(Theta, (double)(tb.Nit - 1 - Newt)) / FNewt;
+          double thp;
+          if (g_mirror) { thp = 1.0; for (int k = 0; k < tb.Nit - 1 - Newt; k++) thp = thp * Theta; }
+          else thp = pow(Theta, (double)(tb.Nit - 1 - Newt));
+          double dyth = FacConv * NewNrm * thp / FNewt;
           if (dyth >= 1.0) {
             double qNewt = fmax(1.0e-4, fmin(20.0, dyth));
-            double hhfac = 0.8 * pow(qNewt, -1.0 / (4.0 + tb.Nit - 1 - Newt));
+            double hhfac = 0.8 * POW(qNewt, -1.0 / (4.0 + tb.Nit - 1 - Newt));
             h = hhfac * h;
             Reject = 1; Last = 0;
             UnExpNewtRej = hhfac <= 0.5;
@@ -659,7 +887,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       for (int j = 0; j < s; j++)
         for (int i = 0; i < n; i++) {
           double acc = tb.T[j][0] * w[0][i];
-          for (int q = 1; q < s; q++) acc = acc + tb.T[j][q] * w[q][i];
+          for (int q = 1; q < s; q++) acc = FMA(tb.T[j][q], w[q][i], acc);
           z[j][i] = acc;
         }
       if (FacConv * NewNrm > FNewt) continue;
@@ -672,14 +900,20 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
     if (!isfinite(err)) { res = 2; break; }
     double fac = fmin(Safe, (2.0 * tb.Nit + 1.0) / (2.0 * tb.Nit + Newt));
     double exponent = 1.0 / s + 1.0;
-    double quot = fmax(FacR, fmin(FacL, pow(err, exponent) / fac));
+    double quot = fmax(FacR, fmin(FacL, POW(err, exponent) / fac));
     double hnew = h / quot;
     if (err < 1.0) {
       First = 0;
       st[ST_ACC] += 1;
       if (op->Gustafsson && !ChangeFlag) {
         if (st[ST_ACC] > 1) {
-          double facgus = (hacc / h) * pow(err * err / erracc, 1.0 / (s + 1.0)) / Safe;
+          double ratio = err * err / erracc, root;
+          if (!g_mirror) root = pow(ratio, 1.0 / (s + 1.0));
+          else if (s == 1) root = sqrt(ratio);
+          else if (s == 3) root = sqrt(sqrt(ratio));
+          else if (s == 7) root = sqrt(sqrt(sqrt(ratio)));
+          else root = det_pow(ratio, 1.0 / (s + 1.0));
+          double facgus = (hacc / h) * root / Safe;
           facgus = fmax(FacR, fmin(FacL, facgus));
           quot = fmax(quot, facgus);
           hnew = h / quot;
@@ -690,7 +924,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       h_old = h;
       t = t + h;
       for (int i = 0; i < n; i++) y[i] = y[i] + z[s - 1][i];
-      for (int i = 0; i < n; i++) cont[s - 1][i] = z[0][i] / tb.C[0];
+      for (int i = 0; i < n; i++) cont[s - 1][i] = g_mirror ? z[0][i] * (1.0 / tb.C[0]) : z[0][i] / tb.C[0];
       for (int q = 1; q <= s - 1; q++) {
         double Fact = 1.0 / (tb.C[s - q - 1] - tb.C[s - q]);
         for (int i = 0; i < n; i++) cont[q - 1][i] = (z[s - q - 1][i] - z[s - q][i]) * Fact;
@@ -746,6 +980,9 @@ done:
 /* ------------------------------------------------------------------ public entry points */
 /* y0 [M][Ny] row-major, tspan [M][2]; outputs y_out [M][Ny], t_out[M], h_out[M], res[M],
  * stats [M][8], nstg[M].  nthreads <= 0 -> all.  Returns 0.                               */
+void oracle_set_arith(int mirror) { g_mirror = mirror ? 1 : 0; }
+int oracle_get_arith(void) { return g_mirror; }
+
 int oracle_radau_solve(int problem, const double *par, int sign, int Ny, long long M, const double *y0,
                        const double *tspan, const oracle_opts *op, double *y_out, double *t_out, double *h_out,
                        int *res, long long *stats, int *nstg, int nthreads) {
@@ -824,4 +1061,9 @@ int oracle_max_threads(void) {
 #else
   return 1;
 #endif
+}
+
+/* deterministic pow (mirror of csrc/detmath.cuh) exposed for the bitwise test */
+void oracle_det_pow(const double *x, const double *y, long long n, double *out) {
+  for (long long i = 0; i < n; i++) out[i] = det_pow(x[i], y[i]);
 }

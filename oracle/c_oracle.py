@@ -73,8 +73,24 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve(problem, par, sign, y0, tspan, opts, nthreads=0):
+def set_arith(mode):
+    """'reference' (no FMA, libm pow, closed-form derivatives) or 'mirror' (the CUDA path's
+    arithmetic contract, bit-identical to the GPU)."""
+    assert mode in ("reference", "mirror")
+    lib().oracle_set_arith(C.c_int(1 if mode == "mirror" else 0))
+
+
+def det_pow(x, y):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().oracle_det_pow(_dp(x), _dp(y), C.c_longlong(x.size), _dp(out))
+    return out
+
+
+def solve(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
     """y0 [M,Ny], tspan [M,2] -> dict(y, t, h, res, stats[M,8], nstg)."""
+    set_arith(arith)
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
@@ -95,8 +111,9 @@ def solve(problem, par, sign, y0, tspan, opts, nthreads=0):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)
 
 
-def trace(problem, par, sign, y0, tspan, opts, cap=100000):
+def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     """one trajectory, with the accepted step sizes."""
+    set_arith(arith)
     y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
     par = np.ascontiguousarray(par, dtype=np.float64)
@@ -114,7 +131,8 @@ def trace(problem, par, sign, y0, tspan, opts, cap=100000):
     return dict(y=y, t=t.value, res=res, stats=stats, h_accept=rec[:n.value].copy())
 
 
-def eval_dyns(problem, par, sign, y):
+def eval_dyns(problem, par, sign, y, arith="reference"):
+    set_arith(arith)
     y = np.ascontiguousarray(y, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
     M, Ny = y.shape
@@ -124,7 +142,8 @@ def eval_dyns(problem, par, sign, y):
     return f
 
 
-def eval_jac(problem, par, sign, y):
+def eval_jac(problem, par, sign, y, arith="reference"):
+    set_arith(arith)
     y = np.ascontiguousarray(y, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
     M, Ny = y.shape
@@ -134,8 +153,9 @@ def eval_jac(problem, par, sign, y):
     return J
 
 
-def lu_solve(A, b):
+def lu_solve(A, b, arith="reference"):
     """A [M,n,n] real or complex, b [M,n] -> x (zgetf2-rule LU with reciprocal pivots)."""
+    set_arith(arith)
     A = np.asarray(A)
     b = np.asarray(b)
     M, n, _ = A.shape

@@ -14,7 +14,7 @@ inv(A) for the Radau IIA Butcher matrix A built from C) and then writes
 
   oracle/radau_tables.py                     (python, for oracle/*.py)
   oracle/c/radau_tables.h                    (plain C, for oracle/c/radau_oracle.c)
-  janus_ode_b200/csrc/radau_tables.cuh       (device constants for the kernels)
+  janus_ode_b200/csrc/radau_tables_t.cuh     (constexpr accessors RadauTab<S> for the kernels)
 
 Storage convention in all outputs: Hairer's orientation, i.e.
   z_j = sum_q T[j][q] * w_q ,   w_j = sum_q TI[j][q] * z_q .
@@ -190,6 +190,32 @@ def emit_c(tabs, path, device):
         f.write(f"#endif  // {guard}\n")
 
 
+def emit_cuh(tabs, path):
+    with open(path, "w") as f:
+        f.write("// Radau IIA tables -- GENERATED by oracle/tools/gen_tables.py, do not edit.\n")
+        f.write("// Numbers: Hairer & Wanner RADAU constants as kept in the reference at\n")
+        f.write("// src/matlab/radau.m:1621-2000 == src/cpp/radaute_impl.hpp:2187-2644.\n")
+        f.write("// Orientation: z_j = sum_q T(j,q) w_q ; w_j = sum_q TI(j,q) z_q (Hairer's).\n")
+        f.write("// ValP = [gamma, alpha1, beta1, ...] (inverted eigenvalues of A).\n")
+        f.write("// constexpr accessors: with unrolled loops every use folds to an immediate/constant-bank operand.\n")
+        f.write("#pragma once\n#include \"detmath.cuh\"\n\nnamespace jb {\n\ntemplate <int S>\nstruct RadauTab;\n\n")
+        for s in (1, 3, 5, 7):
+            t = tabs[s]
+            f.write(f"template <>\nstruct RadauTab<{s}> {{\n")
+            for name in ("C", "Dd", "ValP"):
+                f.write(f"  JB_HD static constexpr double {name}(int i) {{\n")
+                f.write(f"    constexpr double v[{s}] = {{" + ", ".join(r17(v) for v in t[name]) + "};\n")
+                f.write("    return v[i];\n  }\n")
+            for name in ("T", "TI"):
+                f.write(f"  JB_HD static constexpr double {name}(int i, int j) {{\n")
+                f.write(f"    constexpr double v[{s}][{s}] = {{\n")
+                for row in t[name]:
+                    f.write("        {" + ", ".join(r17(v) for v in row) + "},\n")
+                f.write("    };\n    return v[i][j];\n  }\n")
+            f.write("};\n\n")
+        f.write("}  // namespace jb\n")
+
+
 def main():
     tabs = build_tables()
     crosscheck_cpp(tabs)
@@ -197,7 +223,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "oracle", "c"), exist_ok=True)
     emit_python(tabs, os.path.join(ROOT, "oracle", "radau_tables.py"))
     emit_c(tabs, os.path.join(ROOT, "oracle", "c", "radau_tables.h"), device=False)
-    emit_c(tabs, os.path.join(ROOT, "janus_ode_b200", "csrc", "radau_tables.cuh"), device=True)
+    emit_cuh(tabs, os.path.join(ROOT, "janus_ode_b200", "csrc", "radau_tables_t.cuh"))
     print("tables written")
 
 

@@ -1,0 +1,81 @@
+// TEST TOOL ONLY: runs the integrator core (janus_ode_b200/csrc/radau_core.cuh) on the CPU.
+// The product library (libjanus_b200.so) never contains this; it exists so that the
+// arithmetic contract (GPU core == oracle "mirror" mode, bit for bit) can be checked in the
+// GPU-less container.  Built by tests/hostsim/build.sh with g++ -ffp-contract=off.
+#include <cmath>
+#include <cstring>
+
+#include "../../janus_ode_b200/csrc/radau_core.cuh"
+
+using namespace jb;
+
+template <class Ham, int SM, bool VAR>
+static void run(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out,
+                double* t_out, double* h_out, int* res, long long* stats, int* nstg) {
+  constexpr int NY = Ham::NV;
+  for (long long m = 0; m < M; m++) {
+    Traj<NY, SM> T;
+    traj_init<Ham, NY, SM>(T, P, y0 + m * NY, tspan[2 * m], tspan[2 * m + 1]);
+    integrate<Ham, NY, SM, VAR>(T, P);
+    for (int i = 0; i < NY; i++) y_out[m * NY + i] = T.y[i];
+    t_out[m] = T.t;
+    h_out[m] = T.h;
+    res[m] = T.res;
+    for (int k = 0; k < 8; k++) stats[m * 8 + k] = T.st[k];
+    nstg[m] = T.NbrStg;
+  }
+}
+
+template <class Ham>
+static void dispatch(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out,
+                     double* t_out, double* h_out, int* res, long long* stats, int* nstg) {
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3) run<Ham, 3, false>(P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg);
+  else if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1) run<Ham, 1, false>(P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg);
+  else if (P.MaxNbrStg <= 3) run<Ham, 3, true>(P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg);
+  else run<Ham, 7, true>(P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg);
+}
+
+extern "C" {
+// P is passed as raw bytes of jb::RadauParams (filled by the caller, see tests/hostsim.py)
+int hostsim_params_size() { return (int)sizeof(RadauParams); }
+
+void hostsim_fill_params(RadauParams* P, const double* RelTol, const double* AbsTol, int ny, double InitialStep,
+                         double Thet, double Safe, double Quot1, double Quot2, double FacL, double FacR, double Vitu,
+                         double Vitd, double hhou, double hhod, int sign, long long MaxNbrStep, int Start_Newt,
+                         int MaxNbrNewton, int NbrStg, int MinNbrStg, int MaxNbrStg, int Gustafsson, const double* hp,
+                         int nhp) {
+  std::memset(P, 0, sizeof *P);
+  for (int k = 0; k < 4; k++) {
+    const int s = 2 * k + 1;
+    const double ExpmNs = (s + 1.0) / (2.0 * s);
+    double mrt = INFINITY;
+    for (int i = 0; i < ny; i++) {
+      const double quot = AbsTol[i] / RelTol[i];
+      P->RelTol1[k][i] = 0.1 * std::pow(RelTol[i], ExpmNs);
+      P->AbsTol1[k][i] = P->RelTol1[k][i] * quot;
+      mrt = std::fmin(mrt, P->RelTol1[k][i]);
+    }
+    P->FNewt[k] = std::fmax(10 * EPS / mrt, std::fmin(0.03, std::pow(mrt, 1.0 / ExpmNs - 1.0)));
+    if (s == 1) P->FNewt[k] = std::fmax(10 * EPS / mrt, 0.03);
+    P->inv_sqrt_sn[k] = 1.0 / std::sqrt((double)(s * ny));
+  }
+  P->inv_sqrt_n = 1.0 / std::sqrt((double)ny);
+  P->InitialStep = InitialStep; P->Thet = Thet; P->Safe = Safe; P->Quot1 = Quot1; P->Quot2 = Quot2;
+  P->FacL = 1.0 / FacL; P->FacR = 1.0 / FacR; P->Vitu = Vitu; P->Vitd = Vitd; P->hhou = hhou; P->hhod = hhod;
+  P->sign = (double)sign; P->MaxNbrStep = MaxNbrStep; P->Start_Newt = Start_Newt; P->MaxNbrNewton = MaxNbrNewton;
+  P->NbrStg = NbrStg; P->MinNbrStg = MinNbrStg; P->MaxNbrStg = MaxNbrStg; P->Gustafsson = Gustafsson;
+  for (int i = 0; i < nhp && i < 8; i++) P->ham_par[i] = hp[i];
+}
+
+int hostsim_solve(int ham_id, const RadauParams* P, const double* y0, const double* tspan, long long M, double* y_out,
+                  double* t_out, double* h_out, int* res, long long* stats, int* nstg) {
+  switch (ham_id) {
+    case HAM_HARMONIC: dispatch<HamHarmonic>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg); return 0;
+    case HAM_VDP: dispatch<HamVdp>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg); return 0;
+    case HAM_VDP_PMP_SMOOTH: dispatch<HamVdpPmp<false>>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg); return 0;
+    case HAM_VDP_PMP_BANG: dispatch<HamVdpPmp<true>>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg); return 0;
+    case HAM_VDP_AUG_BANG: dispatch<HamVdpAugBang>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg); return 0;
+  }
+  return -1;
+}
+}

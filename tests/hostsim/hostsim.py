@@ -1,0 +1,55 @@
+"""ctypes driver of tests/hostsim/libhostsim.so -- TEST TOOL ONLY (CPU run of the CUDA core)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhostsim.so")
+HAM = dict(harmonic=0, vdp=1, vdp_pmp_smooth=2, vdp_pmp_bang=3, vdp_aug_bang=4)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "hostsim.cpp")
+    core = os.path.join(_HERE, "..", "..", "janus_ode_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(core, f)) for f in os.listdir(core) if f.endswith(".cuh"))
+    newest = max(newest, os.path.getmtime(src))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-shared",
+                               "-x", "c++", "-o", _SO, src])
+    return _SO
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def solve(ham, par, sign, y0, tspan, opts):
+    build()
+    lib = C.CDLL(_SO)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, ny = y0.shape
+    P = (C.c_char * lib.hostsim_params_size())()
+    rt = np.ascontiguousarray(np.broadcast_to(np.asarray(opts.RelTol, dtype=np.float64), (ny,)))
+    at = np.ascontiguousarray(np.broadcast_to(np.asarray(opts.AbsTol, dtype=np.float64), (ny,)))
+    d = C.c_double
+    lib.hostsim_fill_params(P, _dp(rt), _dp(at), C.c_int(ny), d(opts.InitialStep), d(opts.JacRecompute),
+                            d(opts.Safe), d(opts.Quot1), d(opts.Quot2), d(opts.FacL), d(opts.FacR), d(opts.Vitu),
+                            d(opts.Vitd), d(opts.hhou), d(opts.hhod), C.c_int(sign), C.c_longlong(opts.MaxNbrStep),
+                            C.c_int(int(opts.Start_Newt)), C.c_int(opts.MaxNbrNewton), C.c_int(opts.NbrStg),
+                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(int(opts.Gustafsson)),
+                            _dp(par), C.c_int(par.size))
+    y = np.empty_like(y0)
+    t = np.empty(M)
+    h = np.empty(M)
+    res = np.empty(M, dtype=np.int32)
+    stats = np.empty((M, 8), dtype=np.int64)
+    nstg = np.empty(M, dtype=np.int32)
+    rc = lib.hostsim_solve(C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
+                           res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+                           nstg.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)
