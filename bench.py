@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""Benchmark of the accelerated path: trajectory-steps/s (fp64) of the batched Hamiltonian Radau
+solve on the BASELINE.json headline workload (config 2: stiff van der Pol, mu = 1000, 1M
+trajectories per GPU, reference-default variable order 3/5/7).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--M rows-per-gpu]
+                  [--fixed-order]
+  N > 1: launched by torchrun, one rank per GPU; trajectories are independent, so each rank
+  integrates its interleaved shard (rows r, r+N, ... of the seeded global batch of N*M rows) with
+  no data-path collective; NCCL only reduces the counters / times ("scaling": "weak").
+
+A "step" = one solve of the whole per-GPU batch.  `value` = accepted trajectory-steps of all
+ranks / max-over-ranks device time with inputs resident in HBM; `e2e` = the same through the
+public API with pinned HOST tensors (jb200_solve_host: H2D + solve + D2H inside the timed call).
+`roofline` = algorithmic FLOPs (SURVEY.md 8d model, counted per trajectory inside the kernel) over
+the CUDA-event kernel time, against the FP64 DFMA peak measured on this GPU in the same run
+(MEASURED_PEAKS.json has no FP64 figure).  `cpu_baseline` / `--impl reference` = the C restatement
+of the reference algorithm (oracle/c, reference arithmetic, all host threads) on a bounded sample
+of the same rows -- the reference itself cannot be built in this environment.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "trajectory-steps/sec (fp64)"
+UNIT = "trajectory-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--M", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--fixed-order", action="store_true", help="fixed 3 stages instead of the default 3/5/7")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    order = "fixed s=3" if a.fixed_order else "variable order 3/5/7 (reference default)"
+    return (f"config 2: stiff van der Pol Hamiltonian form mu=1000, {a.M} trajectories/GPU fp64, "
+            f"RelTol 1e-6 AbsTol 1e-9, t in [0,(3-2ln2)mu], {order}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(a, rows, threads=0):
+    """C restatement of the reference algorithm on `rows` rows of the workload (reference arithmetic)."""
+    import numpy as np
+    from janus_ode_b200 import configs
+    from oracle import c_oracle
+    cfg = configs.c2_vdp(M=a.M * a.gpus, fixed_order=a.fixed_order, lo=0, hi=rows)
+    y0, ts = cfg["y0"].numpy(), cfg["tspan"].numpy()
+    cores = c_oracle.max_threads() if threads <= 0 else threads
+    t0 = time.perf_counter()
+    o = c_oracle.solve("vdp", list(cfg["ham"].params), cfg["sign"], y0, ts, cfg["options"], nthreads=cores,
+                       arith="reference")
+    dt = time.perf_counter() - t0
+    acc = int(o["stats"][:, 5].sum())
+    assert (o["res"] == 0).all()
+    return acc / dt, dt, acc, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    c_oracle.build()
+    rows = a.cpu_sample or 65536
+    rate0, dt0, _, cores = cpu_reference_run(a, 8192)               # size the sample: ~10 s per step
+    rows = a.cpu_sample or int(min(a.M * a.gpus, max(8192, 8192 * 10.0 / max(dt0, 1e-3))))
+    for _ in range(a.warmup and 1):
+        cpu_reference_run(a, min(rows, 8192))
+    rates, times = [], []
+    for _ in range(a.steps):
+        r, dt, acc, cores = cpu_reference_run(a, rows)
+        rates.append(r)
+        times.append(dt)
+    value = sum(rates) / len(rates)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(a), "sample": f"first {rows} rows of the same seeded batch"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"first {rows} rows of the workload, C restatement of the reference algorithm "
+                                      f"(oracle/c, no-FMA reference arithmetic, OpenMP over trajectories); the "
+                                      f"reference itself cannot be built here (SURVEY.md 8c)"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import janus_ode_b200 as jb
+    from janus_ode_b200 import configs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun --nproc-per-node N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # shard: rows rank, rank+world, ... of the seeded global batch
+    Mg = a.M * world
+    cfg = configs.c2_vdp(M=Mg, fixed_order=a.fixed_order)
+    idx = configs.shard_rows(Mg, rank, world)
+    y0_h = cfg["y0"][idx].contiguous().pin_memory()
+    ts_h = cfg["tspan"][idx].contiguous().pin_memory()
+    y0_d, ts_d = y0_h.to(dev), ts_h.to(dev)
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_device_step():
+        r = jb.RadauTe(dyn, dyn.jacobian, ts_d, y0_d, cfg["options"])
+        flush.zero_()                                   # evict L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.solve()
+        e1.record()
+        return r, e0, e1
+
+    for _ in range(max(a.warmup, 3)):
+        r, _, _ = one_device_step()
+    peak = jb.fp64_peak_tflops(20000) if rank == 0 else None       # FP64 DFMA probe (roofline denominator)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs, launches = [], 0
+    barrier()
+    for _ in range(a.steps):
+        r, e0, e1 = one_device_step()
+        evs.append((e0, e1))
+        launches += r.gpu_launches
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    t_dev = sum(ms) * 1e-3
+    assert bool((r.res == 0).all()), "some trajectories failed"
+    acc = int(r.stats.AccptNbr.sum().item())
+    att = int(r.stats.StepNbr.sum().item())
+    sol = int(r.stats.SolveNbr.sum().item())
+    dec = int(r.stats.DecompNbr.sum().item())
+    jac = int(r.stats.JacNbr.sum().item())
+    flops = int(r.work.sum().item())
+
+    # ---- e2e: public API with pinned host tensors, H2D + D2H inside the timed call
+    for _ in range(2):
+        rh = jb.RadauTe(dyn, dyn.jacobian, ts_h, y0_h, cfg["options"])
+        rh.solve()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        rh = jb.RadauTe(dyn, dyn.jacobian, ts_h, y0_h, cfg["options"])
+        rh.solve()
+        launches_e2e = rh.gpu_launches
+    t_e2e = time.perf_counter() - t0
+    acc_e2e = int(rh.stats.AccptNbr.sum().item())
+    ny = cfg["ham"].Ny
+    h2d = a.M * (ny + 2) * 8
+    d2h = a.M * (ny * 8 + 8 + 8 + 4 + 64 + 4 + 8)
+
+    tens = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    sums = torch.tensor([acc, att, sol, dec, jac, flops, acc_e2e, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tens, op=dist.ReduceOp.MAX)     # time = max over ranks
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)     # work = sum over ranks
+    t_dev, t_e2e = tens.tolist()
+    acc, att, sol, dec, jac, flops, acc_e2e, launches = [int(v) for v in sums.tolist()]
+
+    if rank == 0:
+        value = acc * a.steps / t_dev
+        kernel_s = t_dev / a.steps                       # the solve is ONE kernel: event time == kernel time
+        achieved = (flops / world) / kernel_s / 1e12     # per GPU
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+               "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(a), "rows_total": Mg, "parallelism": f"batch-sharded x{world}",
+                          "l2": "256 MiB buffer written between timed iterations",
+                          "accepted_steps": acc, "attempted_steps": att, "newton_iterations": sol,
+                          "lu_factorisations": dec, "jacobians": jac},
+               "e2e": {"value": acc_e2e * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                       "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * t_e2e / a.steps,
+                       "api": "RadauTe(dyn, dyn.jacobian, tspan_cpu_pinned, y0_cpu_pinned, opts).solve() -> jb200_solve_host"},
+               "gpu_launches": launches,
+               "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "peak_source": "DFMA probe jb200_fp64_peak on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                            "algorithmic_flops_per_launch": flops / world,
+                            "flops_per_accepted_step": flops / max(acc, 1),
+                            "hbm_bytes_per_launch": h2d + d2h,
+                            "hbm_frac_of_measured": ((h2d + d2h) / kernel_s / 1e9) / _hbm_peak()},
+               "clocks": clocks}
+        if not a.no_cpu_baseline:
+            from oracle import c_oracle
+            c_oracle.build()
+            rate0, dt0, _, cores = cpu_reference_run(a, 8192)
+            rows = a.cpu_sample or int(min(Mg, max(8192, 8192 * 12.0 / max(dt0, 1e-3))))
+            rate, dt, _, cores = cpu_reference_run(a, rows)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"first {rows} rows of the workload, {dt:.1f} s; C restatement of the "
+                                             f"reference algorithm (oracle/c, reference arithmetic, OpenMP)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0      # fallback of /opt/skills/guides/B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -96,15 +96,17 @@ int jb200_ny(void* handle);
 
 /* Integrate M trajectories.  All pointers are DEVICE pointers; stream is a cudaStream_t.
  * y0 [M,Ny], tspan [M,2] -> y_out [M,Ny], t_out [M], h_out [M], res [M], stats [M,8] (int64),
- * nstg [M] (final stage count; may be NULL).  Asynchronous on `stream`.                   */
+ * nstg [M] (final stage count; may be NULL), work [M] (algorithmic FLOPs per trajectory by the
+ * SURVEY 8d model, for roofline accounting; may be NULL).  Asynchronous on `stream`.       */
 int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
                 double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
-                void* stream);
+                int64_t* work, void* stream);
 
 /* Same with HOST pointers (what a reference caller holds: CPU tensors).  Copies in, solves,
  * copies out and synchronises; the device workspace lives in the handle.                   */
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
-                     double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg);
+                     double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
+                     int64_t* work);
 
 /* kernels launched by the last jb200_solve* call on this handle */
 int jb200_last_launches(void* handle);

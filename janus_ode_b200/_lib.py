@@ -1,0 +1,72 @@
+"""ctypes loader of the C-ABI library (include/janus_b200.h).  No CPU fallback: if the CUDA
+library is missing or there is no GPU, calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjanus_b200.so")
+
+NYMAX = 16
+NSTATS = 8
+
+
+class jb200_opts(C.Structure):
+    """struct jb200_opts (include/janus_b200.h) == OptionsTe, src/cpp/radaute.hpp:52-96."""
+    _fields_ = [("RelTol", C.c_double * NYMAX), ("AbsTol", C.c_double * NYMAX), ("n_tol", C.c_int),
+                ("InitialStep", C.c_double), ("MaxStep", C.c_double), ("JacRecompute", C.c_double),
+                ("Start_Newt", C.c_int), ("MaxNbrNewton", C.c_int), ("NbrStg", C.c_int),
+                ("MinNbrStg", C.c_int), ("MaxNbrStg", C.c_int), ("MaxNbrStep", C.c_int64),
+                ("Safe", C.c_double), ("Quot1", C.c_double), ("Quot2", C.c_double), ("FacL", C.c_double),
+                ("FacR", C.c_double), ("Vitu", C.c_double), ("Vitd", C.c_double), ("hhou", C.c_double),
+                ("hhod", C.c_double), ("Gustafsson", C.c_int), ("costate_sign", C.c_int)]
+
+
+class JanusB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/janus_b200.h declares
+SYMBOLS = ("jb200_opts_default", "jb200_create", "jb200_destroy", "jb200_ny", "jb200_solve",
+           "jb200_solve_host", "jb200_last_launches", "jb200_eval_dyns", "jb200_eval_jac", "jb200_lu_solve",
+           "jb200_det_pow", "jb200_fp64_peak", "jb200_last_error", "jb200_version")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JanusB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(janus_ode_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, i64 = C.c_void_p, C.c_void_p, C.c_int64
+        L.jb200_opts_default.argtypes = [C.POINTER(jb200_opts)]
+        L.jb200_create.argtypes = [C.POINTER(jb200_opts), C.c_int, C.POINTER(C.c_double), C.c_int,
+                                   C.POINTER(C.c_void_p)]
+        L.jb200_destroy.argtypes = [vp]
+        L.jb200_destroy.restype = None
+        L.jb200_ny.argtypes = [vp]
+        L.jb200_solve.argtypes = [vp, dp, dp, i64, dp, dp, dp, dp, dp, dp, dp, vp]
+        L.jb200_solve_host.argtypes = [vp, dp, dp, i64, dp, dp, dp, dp, dp, dp, dp]
+        L.jb200_last_launches.argtypes = [vp]
+        L.jb200_eval_dyns.argtypes = [vp, dp, i64, dp, vp]
+        L.jb200_eval_jac.argtypes = [vp, dp, i64, dp, vp]
+        L.jb200_lu_solve.argtypes = [C.c_int, i64, dp, dp, dp, dp, dp, dp, vp]
+        L.jb200_det_pow.argtypes = [dp, dp, i64, dp, vp]
+        L.jb200_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.jb200_last_error.restype = C.c_char_p
+        L.jb200_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().jb200_last_error().decode()
+        if rc == -1:
+            raise ValueError(msg)
+        raise JanusB200Error(f"janus_b200 error {rc}: {msg}")

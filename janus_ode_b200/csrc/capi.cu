@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(128) radau_kernel(const __grid_constant__ Rada
                                                     double* __restrict__ y_out, double* __restrict__ t_out,
                                                     double* __restrict__ h_out, int* __restrict__ res,
                                                     long long* __restrict__ stats, int* __restrict__ nstg,
+                                                    long long* __restrict__ work,
                                                     unsigned long long* __restrict__ counter) {
   constexpr int NY = Ham::NV;
   Traj<NY, SM> T;
@@ -85,10 +86,14 @@ __global__ void __launch_bounds__(128) radau_kernel(const __grid_constant__ Rada
       traj_init<Ham, NY, SM>(T, P, y, ts.x, ts.y);
       have = true;
     }
-    bool done = (T.res != 0) || !traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep);
-    if (!done) done = one_pass<Ham, NY, SM, VAR>(T, P);
-    if (done) {
+    bool done;
+    if (T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
+      done = one_pass<Ham, NY, SM, VAR>(T, P);
+    } else {  // failed at init, or the step cap ended the loop (radau.m:1287)
       if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
+      done = true;
+    }
+    if (done) {
       store_row<NY>(y_out, m, T.y);
       t_out[m] = T.t;
       h_out[m] = T.h;
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(128) radau_kernel(const __grid_constant__ Rada
 #pragma unroll
       for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
       if (nstg) nstg[m] = T.NbrStg;
+      if (work) work[m] = T.work;
       have = false;
     }
   }
@@ -200,6 +206,7 @@ struct Handle {
   double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
   int *d_res = nullptr, *d_nstg = nullptr;
   long long* d_stats = nullptr;
+  long long* d_work = nullptr;
   cudaStream_t own_stream = nullptr;
 };
 
@@ -298,7 +305,7 @@ static void fill_params(RadauParams& P, const jb200_opts* o, int ny, const doubl
 
 template <class Ham, int SM, bool VAR>
 static int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                        double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+                        double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
   auto kern = radau_kernel<Ham, SM, VAR>;
   int bps = 0;
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 128, 0));
@@ -308,7 +315,7 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
-  kern<<<(unsigned)blocks, 128, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, H->d_counter);
+  kern<<<(unsigned)blocks, 128, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, H->d_counter);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
@@ -316,15 +323,15 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
 
 template <class Ham>
 static int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                          double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+                          double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
   const RadauParams& P = H->P;
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
-    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
-    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
   if (P.MaxNbrStg <= 3)
-    return launch_radau<Ham, 3, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
-  return launch_radau<Ham, 7, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st);
+    return launch_radau<Ham, 3, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+  return launch_radau<Ham, 7, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
 }
 
 #define JB_HAM_SWITCH(ID, CALL)                                              \
@@ -338,12 +345,12 @@ static int dispatch_order(Handle* H, const double* y0, const double* tspan, long
   }
 
 static int solve_dev(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, cudaStream_t st) {
+                     double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
   if (M <= 0) {
     H->launches = 0;
     return 0;
   }
-  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, st)));
+  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st)));
 }
 
 template <class Ham>
@@ -376,7 +383,7 @@ static int launch_lu(long long M, const double* Are, const double* Aim, const do
 static int ensure_workspace(Handle* H, long long M) {
   if (M <= H->cap) return 0;
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
-  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
   H->cap = 0;
   const int ny = H->ny;
   JB_CUDA(cudaMalloc(&H->d_y0, sizeof(double) * M * ny));
@@ -387,6 +394,7 @@ static int ensure_workspace(Handle* H, long long M) {
   JB_CUDA(cudaMalloc(&H->d_res, sizeof(int) * M));
   JB_CUDA(cudaMalloc(&H->d_nstg, sizeof(int) * M));
   JB_CUDA(cudaMalloc(&H->d_stats, sizeof(long long) * M * 8));
+  JB_CUDA(cudaMalloc(&H->d_work, sizeof(long long) * M));
   H->cap = M;
   return 0;
 }
@@ -458,7 +466,7 @@ void jb200_destroy(void* handle) {
   if (!H) return;
   cudaFree(H->d_counter);
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
-  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
   delete H;
 }
@@ -466,17 +474,17 @@ void jb200_destroy(void* handle) {
 int jb200_ny(void* handle) { return handle ? ((Handle*)handle)->ny : JB200_EINVAL; }
 
 int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
-                double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, void* stream) {
+                double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M < 0) return fail(JB200_EINVAL, "M < 0");
   if (M > 0 && (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats)) return fail(JB200_EINVAL, "null buffer");
   return solve_dev(H, y0, tspan, (long long)M, y_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
-                   (cudaStream_t)stream);
+                   (long long*)work, (cudaStream_t)stream);
 }
 
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
-                     double* h_out, int32_t* res, int64_t* stats, int32_t* nstg) {
+                     double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work) {
   Handle* H = (Handle*)handle;
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M < 0) return fail(JB200_EINVAL, "M < 0");
@@ -494,7 +502,7 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   const int ny = H->ny;
   JB_CUDA(cudaMemcpyAsync(H->d_y0, y0, sizeof(double) * M * ny, cudaMemcpyHostToDevice, st));
   JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
-  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, st);
+  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, H->d_work, st);
   if (rc) return rc;
   JB_CUDA(cudaMemcpyAsync(y_out, H->d_y, sizeof(double) * M * ny, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaMemcpyAsync(t_out, H->d_t, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
@@ -502,6 +510,7 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   JB_CUDA(cudaMemcpyAsync(res, H->d_res, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaMemcpyAsync(stats, H->d_stats, sizeof(long long) * M * 8, cudaMemcpyDeviceToHost, st));
   if (nstg) JB_CUDA(cudaMemcpyAsync(nstg, H->d_nstg, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+  if (work) JB_CUDA(cudaMemcpyAsync(work, H->d_work, sizeof(long long) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -12,6 +12,8 @@
 //   template <class... V> static auto H(v0, ..., v_{NV-1}, const double* par, double u)
 //        arguments in y-order (p_1..p_N, x_1..x_N), each a D1/D2 number with its own mask
 //   static double control(const double* y, const double* par)          (if HAS_CONTROL)
+//   FLOPS_F, FLOPS_J   FP64 instructions of one dynamics / Jacobian evaluation, counted from the
+//                      SASS of dyns_kernel / jac_kernel (roofline accounting only)
 // User Hamiltonians compiled at run time (NVRTC) use exactly this interface.
 #pragma once
 #include <utility>
@@ -33,6 +35,7 @@ enum HamId {
 // C1: H = (p^2 + w^2 x^2)/2    (written with squares like the reference's pow(2))
 struct HamHarmonic {
   static constexpr int N = 1, NV = 2, NPAR = 1;
+  static constexpr int FLOPS_F = 4, FLOPS_J = 2;
   static constexpr bool HAS_CONTROL = false;
   template <class P, class X>
   JB_HD static auto H(const P& p, const X& x, const double* par, double) {
@@ -45,6 +48,7 @@ struct HamHarmonic {
 // C2/C5: H = p1 x2 + p2 (mu (1 - x1^2) x2 - x1)
 struct HamVdp {
   static constexpr int N = 2, NV = 4, NPAR = 1;
+  static constexpr int FLOPS_F = 14, FLOPS_J = 16;
   static constexpr bool HAS_CONTROL = false;
   template <class P1, class P2, class X1, class X2>
   JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
@@ -60,6 +64,7 @@ struct HamVdp {
 template <bool BANG>
 struct HamVdpPmp {
   static constexpr int N = 2, NV = 4, NPAR = 3;  // W, umin, umax
+  static constexpr int FLOPS_F = BANG ? 16 : 34, FLOPS_J = BANG ? 18 : 38;
   static constexpr bool HAS_CONTROL = true;
   template <class P1, class P2, class X1, class X2>
   JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
@@ -79,6 +84,7 @@ struct HamVdpPmp {
 // examples/python/aug_vdp_ref_test.py:6-27 :  H = p1 x2 + p2 (u (1 - x1^2) x2 - x1), bang-bang u
 struct HamVdpAugBang {
   static constexpr int N = 2, NV = 4, NPAR = 2;  // umin, umax
+  static constexpr int FLOPS_F = 16, FLOPS_J = 18;
   static constexpr bool HAS_CONTROL = true;
   template <class P1, class P2, class X1, class X2>
   JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,

@@ -45,6 +45,20 @@ struct RadauParams {
   double ham_par[8];
 };
 
+// Algorithmic FLOP model of SURVEY.md 8(d) (mul, add, div, sqrt, pow = 1; complex mul = 6, add = 2),
+// n = Ny, s stages, F / Jf = FP64 instructions of one dynamics / Jacobian evaluation counted from
+// this library's own SASS (Ham::FLOPS_F, Ham::FLOPS_J).  Accumulated per trajectory in Traj::work.
+JB_HD constexpr long long W_newt(int s, int n, int F) {  // one simplified-Newton iteration
+  return (long long)s * F + 2LL * s * s * n + 2LL * s * s * n + (long long)s * n + (2LL * n + 8LL * n * ((s - 1) / 2)) +
+         (2LL * n * n + 8LL * n * n * ((s - 1) / 2)) + 3LL * s * n;
+}
+JB_HD constexpr long long W_lu(int s, int n) {  // real + (s-1)/2 complex LU factorisations
+  return (2LL * n * n * n + 8LL * n * n * n * ((s - 1) / 2)) / 3;
+}
+JB_HD constexpr long long W_tail(int s, int n, int F) {  // Estrad + f0 + controller
+  return (long long)F + 2LL * s * n + 2LL * n * n + 3LL * n + 60;
+}
+
 JB_HD constexpr int nit_of(int s, int MaxNbrNewton) {
   return s == 1 ? MaxNbrNewton - 3 : s == 3 ? MaxNbrNewton : s == 5 ? MaxNbrNewton + 5 : MaxNbrNewton + 10;
 }
@@ -57,6 +71,7 @@ struct Traj {
   bool Last, First, Reject, Keep, ChangeFlag, UnExpStepRej, UnExpNewtRej, NeedNewJac, NeedNewLU;
   int res;
   int st[8];
+  long long work;  // algorithmic FLOPs spent on this trajectory (SURVEY.md 8d formula, see W_* below)
   RLU<NY> L0;
   ZLU<NY> Lc[(SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1];
 };
@@ -105,6 +120,7 @@ JB_HD void traj_init(Traj<NY, SM>& T, const RadauParams& P, const double* y0, do
   T.First = true;
   ham_dyns<Ham>(T.y, P.ham_par, P.sign, T.f0);
   T.st[ST_FCN] += 1;
+  T.work = Ham::FLOPS_F;
   T.res = 0;
 #pragma unroll
   for (int i = 0; i < NY; i++)
@@ -154,6 +170,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
   if (T.NeedNewLU) {  // radau.m:827-844
     decomrc<NY, S, SM>(T);
     T.st[ST_DEC] += 1;
+    T.work += W_lu(S, NY);
     T.NeedNewLU = false;
   }
   const bool Variab = (P.MaxNbrStg - P.MinNbrStg) != 0;
@@ -273,6 +290,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
       }
     }
     T.st[ST_SOL] += 1;
+    T.work += W_newt(S, NY, Ham::FLOPS_F);
     NewNrm = 0.0;  // radau.m:955-959
 #pragma unroll
     for (int q = 0; q < S; q++) {
@@ -339,6 +357,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
   if (newton_failed) return false;  // radau.m:1020-1022
 
   // ------- Estrad (radaute_impl.hpp:1902-1986)
+  T.work += W_tail(S, NY, Ham::FLOPS_F);
   double temp[NY], ev[NY];
 #pragma unroll
   for (int i = 0; i < NY; i++) {
@@ -365,6 +384,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
     for (int i = 0; i < NY; i++) ya[i] = T.y[i] + err;  // sic: scalar err (radaute_impl.hpp:1951)
     ham_dyns<Ham>(ya, P.ham_par, P.sign, ev);
     T.st[ST_FCN] += 1;
+    T.work += Ham::FLOPS_F + 2LL * NY * NY + 3LL * NY;
 #pragma unroll
     for (int i = 0; i < NY; i++) ev[i] = ev[i] + temp[i];
     rlu_solve<NY>(T.L0, ev);
@@ -487,6 +507,7 @@ JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
       return false;
     }
     T.st[ST_JAC] += 1;
+    T.work += Ham::FLOPS_J;
     T.NeedNewJac = false;
     T.NeedNewLU = true;
   }

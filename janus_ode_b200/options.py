@@ -1,0 +1,103 @@
+"""OptionsTe / StatsTe mirrors (reference: /root/reference/src/cpp/radaute.hpp:52-108)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import NYMAX, jb200_opts
+
+STAT_NAMES = ("FcnNbr", "JacNbr", "DecompNbr", "SolveNbr", "StepNbr", "AccptNbr", "StepRejNbr",
+              "NewtRejNbr")
+
+
+@dataclass
+class OptionsTe:
+    """Same field names and defaults as the reference's OptionsTe (solver knobs).
+
+    MaxStep is accepted and ignored exactly like the reference (hmax = tfinal - t0,
+    src/cpp/radaute_impl.hpp:227).  MassFcn / EventsFcn / OutputFcn / Complex / Refine > 1 are
+    outside the accelerated path and raise if set.
+    """
+    RelTol: object = 1.0e-3
+    AbsTol: object = 1.0e-6
+    InitialStep: float = 1.0e-2
+    MaxStep: float = 1.0
+    JacRecompute: float = 1.0e-3
+    Start_Newt: bool = False
+    MaxNbrNewton: int = 7
+    NbrStg: int = 3
+    MinNbrStg: int = 3
+    MaxNbrStg: int = 7
+    MaxNbrStep: int = 10000
+    Safe: float = 0.9
+    Quot1: float = 1.0
+    Quot2: float = 1.2
+    FacL: float = 0.2
+    FacR: float = 8.0
+    Vitu: float = 0.002
+    Vitd: float = 0.8
+    hhou: float = 1.2
+    hhod: float = 0.8
+    Gustafsson: bool = True
+    Complex: bool = False
+    Refine: int = 1
+    MassFcn: object = None
+    EventsFcn: object = None
+    OutputFcn: object = None
+
+    def to_c(self, ny: int, costate_sign: int) -> jb200_opts:
+        for nm in ("MassFcn", "EventsFcn", "OutputFcn"):
+            if getattr(self, nm) is not None:
+                raise NotImplementedError(f"{nm} is outside the accelerated Radau path")
+        if self.Complex or self.Refine > 1:
+            raise NotImplementedError("Complex=true tables / Refine>1 are outside the accelerated path")
+        o = jb200_opts()
+        rt = np.atleast_1d(np.asarray(_to_np(self.RelTol), dtype=np.float64)).ravel()
+        at = np.atleast_1d(np.asarray(_to_np(self.AbsTol), dtype=np.float64)).ravel()
+        for name, v in (("RelTol", rt), ("AbsTol", at)):
+            if v.size not in (1, ny):
+                raise ValueError(f"{name} vector of length 1 or {ny}")
+        n_tol = max(rt.size, at.size)
+        rt = np.broadcast_to(rt, (n_tol,))
+        at = np.broadcast_to(at, (n_tol,))
+        if n_tol > NYMAX:
+            raise ValueError("too many tolerance components")
+        for i in range(n_tol):
+            o.RelTol[i] = rt[i]
+            o.AbsTol[i] = at[i]
+        o.n_tol = n_tol
+        for k in ("InitialStep", "MaxStep", "JacRecompute", "Safe", "Quot1", "Quot2", "FacL", "FacR", "Vitu",
+                  "Vitd", "hhou", "hhod"):
+            setattr(o, k, float(_to_np(getattr(self, k))))
+        for k in ("MaxNbrNewton", "NbrStg", "MinNbrStg", "MaxNbrStg", "MaxNbrStep"):
+            setattr(o, k, int(_to_np(getattr(self, k))))
+        o.Start_Newt = int(bool(self.Start_Newt))
+        o.Gustafsson = int(bool(self.Gustafsson))
+        o.costate_sign = int(costate_sign)
+        return o
+
+
+def _to_np(v):
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    a = np.asarray(v)
+    return a if a.ndim else a.item()
+
+
+@dataclass
+class StatsTe:
+    """Per-trajectory int64 counters, one tensor per field (src/cpp/radaute.hpp:98-108)."""
+    FcnNbr: object = None
+    JacNbr: object = None
+    DecompNbr: object = None
+    SolveNbr: object = None
+    StepNbr: object = None
+    AccptNbr: object = None
+    StepRejNbr: object = None
+    NewtRejNbr: object = None
+    raw: object = field(default=None, repr=False)   # [M, 8]
+
+    @classmethod
+    def from_tensor(cls, st):
+        return cls(*[st[:, i] for i in range(8)], raw=st)

@@ -1,0 +1,211 @@
+"""Python host side of the accelerated path: the reference's solver API shape over the C ABI.
+
+Mirrors
+  RadauTe(OdeFcn, JacFn, tspan, y0, Op, params).solve() -> res, public fields y, t, h, stats
+      (/root/reference/src/cpp/radaute.hpp:243-483, impl src/cpp/radaute_impl.hpp:5-1345)
+  the `dyns(t, y, params)` / `dyns.jacobian(t, y, params)` protocol of the Python steppers
+      (/root/reference/src/python/seulex_dual_example_vdp.py:26-67)
+PyTorch is only the owner of device memory and streams here; all arithmetic happens in
+libjanus_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .hamiltonians import Hamiltonian
+from .options import OptionsTe, StatsTe
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class _Handle:
+    def __init__(self, ham: Hamiltonian, options: OptionsTe, costate_sign: int):
+        L = _lib.lib()
+        o = options.to_c(ham.Ny, costate_sign)
+        par = (C.c_double * max(1, len(ham.params)))(*ham.params)
+        h = C.c_void_p()
+        _lib.check(L.jb200_create(C.byref(o), ham.ham_id, par, len(ham.params), C.byref(h)))
+        self.h = h
+        self.L = L
+
+    def close(self):
+        if self.h:
+            self.L.jb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HamiltonianSystem:
+    """`dyns` object of the reference protocol: dyns(t, y[, params]) -> ydot [M,Ny] and
+    dyns.jacobian(t, y[, params]) -> J [M,Ny,Ny], evaluated by the dual / hyper-dual kernels
+    (evalDyns / evalJac, src/cpp/janus_ode_common.hpp:2161-2299).
+    costate_sign +1 = reference (pdot = +dH/dx), -1 = canonical."""
+
+    def __init__(self, hamiltonian: Hamiltonian, costate_sign: int = +1):
+        if not isinstance(hamiltonian, Hamiltonian):
+            raise TypeError("the accelerated path needs a janus_ode_b200.Hamiltonian descriptor; a Python "
+                            "callable cannot run inside a CUDA kernel")
+        if costate_sign not in (1, -1):
+            raise ValueError("costate_sign must be +1 or -1")
+        self.hamiltonian = hamiltonian
+        self.costate_sign = costate_sign
+        self._handle = None
+
+    def _h(self):
+        if self._handle is None:
+            self._handle = _Handle(self.hamiltonian, OptionsTe(), self.costate_sign)
+        return self._handle
+
+    def _check(self, y):
+        if y.dim() != 2 or y.shape[1] != self.hamiltonian.Ny:
+            raise ValueError(f"y must be [M,{self.hamiltonian.Ny}]")
+        if y.dtype != torch.float64:
+            raise TypeError("y must be float64")
+        if not y.is_cuda:
+            raise _lib.JanusB200Error("stage evaluation runs on CUDA tensors only (no CPU fallback)")
+        return y.contiguous()
+
+    def __call__(self, t, y, params=None):
+        y = self._check(y)
+        out = torch.empty_like(y)
+        H = self._h()
+        _lib.check(H.L.jb200_eval_dyns(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
+        return out
+
+    def jacobian(self, t, y, params=None):
+        y = self._check(y)
+        ny = self.hamiltonian.Ny
+        out = torch.empty(y.shape[0], ny, ny, dtype=torch.float64, device=y.device)
+        H = self._h()
+        _lib.check(H.L.jb200_eval_jac(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
+        return out
+
+
+class RadauTe:
+    """Batched variable-order Radau IIA for a Hamiltonian system, one adaptive step per trajectory.
+
+    RadauTe(dyns, jac, tspan[M,2], y0[M,Ny], options, params=None), like the reference; `dyns`
+    must be a HamiltonianSystem (jac is implied by it and may be None or dyns.jacobian).
+    solve() returns res[M] (float64 codes 0/1/2/3 like the reference) and fills the public
+    fields y, t, h, stats, nstg, count.  CUDA tensors are integrated in place on their device
+    and stream; CPU tensors go through jb200_solve_host (copy in, solve, copy out) -- the
+    drop-in for a reference caller, who holds CPU tensors.
+    """
+
+    def __init__(self, dyns, jac, tspan, y0, options: OptionsTe | None = None, params=None):
+        if not isinstance(dyns, HamiltonianSystem):
+            raise TypeError("dyns must be a janus_ode_b200.HamiltonianSystem")
+        if jac is not None and getattr(jac, "__self__", None) is not dyns and jac is not dyns:
+            raise TypeError("jac must be None or dyns.jacobian (the Jacobian is the Hessian of H)")
+        self.dyns = dyns
+        self.options = options or OptionsTe()
+        ham = dyns.hamiltonian
+        if tspan.dim() != y0.dim():
+            raise ValueError("tspan must be a tensor")          # radaute_impl.hpp:10-14
+        if y0.dim() != 2:
+            raise ValueError("Initial conditions argument must be a valid vector")
+        if y0.shape[1] != ham.Ny:
+            raise ValueError(f"y0 must be [M,{ham.Ny}] for Hamiltonian '{ham.name}'")
+        if tspan.shape[0] != y0.shape[0] or tspan.shape[1] < 2:
+            raise ValueError("tspan must be [M,>=2]")
+        if tspan.shape[1] > 2:
+            raise NotImplementedError("tspan with interior output points (OutFlag 3) is outside the "
+                                      "accelerated path; pass [t0, tfinal]")
+        if y0.dtype != torch.float64 or tspan.dtype != torch.float64:
+            raise TypeError("y0 and tspan must be float64")
+        if y0.device != tspan.device:
+            raise ValueError("y0 and tspan must live on the same device")
+        t0, tf = tspan[:, 0], tspan[:, -1]
+        if bool(((tf - t0) == 0).any()):
+            raise ValueError("Time vector must be strictly monotonic")   # radaute_impl.hpp:54-59
+        self._handle = _Handle(ham, self.options, dyns.costate_sign)      # validates the options
+        self.M, self.Ny = y0.shape
+        self.device = y0.device
+        self.tspan = tspan[:, [0, -1]].contiguous()
+        self.y = y0.contiguous()          # never written: solve() replaces it with the result tensor
+        self.t = t0.clone()
+        self.h = torch.zeros(self.M, dtype=torch.float64, device=self.device)
+        self.stats = None
+        self.nstg = None
+        self.count = 0
+        self.res = None
+
+    def solve(self):
+        H = self._handle
+        M, ny, dev = self.M, self.Ny, self.device
+        # host path: page-locked result buffers so the D2H copies of jb200_solve_host are direct DMA
+        kw = dict(device=dev) if self.y.is_cuda else dict(device=dev, pin_memory=True)
+        y_out = torch.empty(M, ny, dtype=torch.float64, **kw)
+        t_out = torch.empty(M, dtype=torch.float64, **kw)
+        h_out = torch.empty(M, dtype=torch.float64, **kw)
+        res = torch.empty(M, dtype=torch.int32, **kw)
+        stats = torch.empty(M, 8, dtype=torch.int64, **kw)
+        nstg = torch.empty(M, dtype=torch.int32, **kw)
+        work = torch.empty(M, dtype=torch.int64, **kw)
+        if self.y.is_cuda:
+            with torch.cuda.device(dev):
+                _lib.check(H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
+                                           _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work), _stream_ptr(dev)))
+        else:
+            _lib.check(H.L.jb200_solve_host(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
+                                            _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work)))
+        self.y, self.t, self.h = y_out, t_out, h_out
+        self.stats = StatsTe.from_tensor(stats)
+        self.nstg = nstg
+        self.work = work           # algorithmic FLOPs per trajectory (roofline accounting)
+        self.res = res.to(torch.float64)
+        self.gpu_launches = int(H.L.jb200_last_launches(H.h))
+        self.count = int(stats[:, 4].max().item()) if M > 0 else 0   # passes of the reference's loop
+        return self.res
+
+
+def lu_solve(A, b):
+    """Batched small dense LU factor + solve on CUDA tensors, A [M,n,n], b [M,n], n in {2,3,4};
+    real float64 or complex128 (the torch::linalg_lu_factor / lu_solve role on the Radau path,
+    src/cpp/radaute_impl.hpp:1558,1754)."""
+    if not A.is_cuda:
+        raise _lib.JanusB200Error("lu_solve runs on CUDA tensors only (no CPU fallback)")
+    M, n, _ = A.shape
+    L = _lib.lib()
+    st = _stream_ptr(A.device)
+    if A.is_complex() or b.is_complex():
+        A = A.to(torch.complex128)
+        b = b.to(torch.complex128)
+        Ar, Ai = A.real.contiguous(), A.imag.contiguous()
+        br, bi = b.real.contiguous(), b.imag.contiguous()
+        xr, xi = torch.empty_like(br), torch.empty_like(bi)
+        _lib.check(L.jb200_lu_solve(n, M, _ptr(Ar), _ptr(Ai), _ptr(br), _ptr(bi), _ptr(xr), _ptr(xi), st))
+        return torch.complex(xr, xi)
+    A = A.contiguous()
+    b = b.contiguous()
+    x = torch.empty_like(b)
+    _lib.check(L.jb200_lu_solve(n, M, _ptr(A), None, _ptr(b), None, _ptr(x), None, st))
+    return x
+
+
+def det_pow(x, y):
+    """deterministic pow of the controller (test hook)."""
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().jb200_det_pow(_ptr(x.contiguous()), _ptr(y.contiguous()), x.numel(), _ptr(out),
+                                        _stream_ptr(x.device)))
+    return out
+
+
+def fp64_peak_tflops(iters=20000):
+    v = C.c_double()
+    _lib.check(_lib.lib().jb200_fp64_peak(int(iters), C.byref(v)))
+    return v.value

@@ -736,7 +736,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
   rhs(pb, t, y, f0);
   st[ST_FCN] += 1;
   if (any_nan(f0, n)) { res = 2; goto done; }
-  int NeedNewJac = 1, NeedNewLU = 1, Newt = 0;
+  int NeedNewJac = 1, NeedNewLU = 1, Newt = 0, finished = 0;
   double SqrtStgNy = sqrt((double)(NbrStg * n));
   double hacc = 0.0, erracc = 0.0, thqold = 0.0, OldNrm = 0.0;
   if (rec_n) *rec_n = 0;
@@ -939,6 +939,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       if (Last) {
         h = hopt;
         st[ST_REJ] += 1;
+        finished = 1;
         break;
       }
       rhs(pb, t, y, f0);
@@ -968,7 +969,8 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       NeedNewLU = 1;
     }
   }
-  if (res == 0 && PosNeg * t < PosNeg * tfinal) res = 3;
+  /* radau.m:1287: only the step cap ends the loop early (t + (tfinal - t) may round below tfinal) */
+  if (res == 0 && !finished && PosNeg * t < PosNeg * tfinal) res = 3;
 done:
   for (int i = 0; i < n; i++) y_out[i] = y[i];
   *t_out = t;

@@ -183,7 +183,7 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
     Returns RadauResult; res: 0 ok, 1 step too small, 2 NaN/inf, 3 MaxNbrStep exceeded.
     """
     op = opts or RadauOptions()
-    op.validate()
+    getattr(op, "validate", lambda: None)()   # any object with OptionsTe's field names works
     y = np.array(y0, dtype=np.float64).copy()
     Ny = y.shape[0]
     t = float(t0)
@@ -247,6 +247,7 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
     hacc = erracc = 0.0
     thqold = OldNrm = 0.0
     err = 0.0
+    finished = False
 
     # ------- MAIN LOOP  radau.m:712
     while stats["StepNbr"] <= op.MaxNbrStep and PosNeg * t < PosNeg * tfinal:
@@ -458,6 +459,7 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
             if Last:                                # :1193-1197
                 h = hopt
                 stats["StepRejNbr"] += 1
+                finished = True
                 break
             f0 = np.asarray(f(t, y), dtype=np.float64)      # :1198-1206
             stats["FcnNbr"] += 1
@@ -494,7 +496,7 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
                 stats["StepRejNbr"] += 1
             NeedNewLU = True
 
-    if out.res == 0 and PosNeg * t < PosNeg * tfinal:
+    if out.res == 0 and not finished and PosNeg * t < PosNeg * tfinal:
         out.res = 3                                 # MaxNbrStep exceeded (radau.m:1287)
     out.y, out.t, out.h, out.nstg = y, t, h, NbrStg
     return out
