@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjanus_b200.so")
+LIB_PATH = os.environ.get("JB200_LIB", os.path.join(_HERE, "libjanus_b200.so"))   # override: developer A/B builds
 
 NYMAX = 16
 NSTATS = 8

