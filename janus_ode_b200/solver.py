@@ -27,6 +27,28 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_HANDLE_CACHE = {}
+
+
+def _get_handle(ham: Hamiltonian, options: OptionsTe, costate_sign: int, device):
+    """Solver objects are one-shot like the reference's (construct per solve), but the native handle
+    behind them -- device workspace of the host-buffer and variable-order paths -- is reused for the
+    same (Hamiltonian, options, device)."""
+    import numpy as np
+    key = (ham, costate_sign, str(device),
+           tuple((k, tuple(np.atleast_1d(np.asarray(v, dtype=float)).tolist()) if k in ("RelTol", "AbsTol") else v)
+                 for k, v in sorted(vars(options).items())))
+    try:
+        h = _HANDLE_CACHE.get(key)
+    except TypeError:
+        return _Handle(ham, options, costate_sign)
+    if h is None:
+        if len(_HANDLE_CACHE) >= 8:
+            _HANDLE_CACHE.pop(next(iter(_HANDLE_CACHE))).close()
+        h = _HANDLE_CACHE[key] = _Handle(ham, options, costate_sign)
+    return h
+
+
 class _Handle:
     def __init__(self, ham: Hamiltonian, options: OptionsTe, costate_sign: int):
         L = _lib.lib()
@@ -132,7 +154,12 @@ class RadauTe:
         t0, tf = tspan[:, 0], tspan[:, -1]
         if bool(((tf - t0) == 0).any()):
             raise ValueError("Time vector must be strictly monotonic")   # radaute_impl.hpp:54-59
-        self._handle = _Handle(ham, self.options, dyns.costate_sign)      # validates the options
+        dev_key = y0.device if y0.is_cuda else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "none"
+        if y0.is_cuda:
+            with torch.cuda.device(y0.device):
+                self._handle = _get_handle(ham, self.options, dyns.costate_sign, dev_key)   # validates the options
+        else:
+            self._handle = _get_handle(ham, self.options, dyns.costate_sign, dev_key)
         self.M, self.Ny = y0.shape
         self.device = y0.device
         self.tspan = tspan[:, [0, -1]].contiguous()

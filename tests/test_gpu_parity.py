@@ -124,7 +124,7 @@ def test_golden_files(name, mk, tag):
     g = np.load(os.path.join(GOLD, f"{name}_{tag}.npz"))
     cfg = mk(M=g["y0"].shape[0], fixed_order=(tag == "s3"))
     a = gpu_solve(cfg)
-    assert a["launches"] == 1
+    assert a["launches"] == 1 if tag == "s3" else a["launches"] > 1   # fused kernel vs epochs
     assert np.array_equal(a["y"], g["mir_y"]) and np.array_equal(a["stats"], g["mir_stats"])
     assert np.array_equal(a["res"], g["mir_res"]) and np.array_equal(a["t"], g["mir_t"])
     assert np.array_equal(a["nstg"], g["mir_nstg"]) and np.array_equal(a["h"], g["mir_h"])
