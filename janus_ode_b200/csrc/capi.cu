@@ -151,8 +151,20 @@ __global__ void partition_kernel(const unsigned char* __restrict__ tag, long lon
   }
 }
 
+#ifndef JB_MINB_HI
+#define JB_MINB_HI 2      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
+#endif
+#ifndef JB_THREADS_HI
+#define JB_THREADS_HI 128
+#endif
+template <int S>
+struct EpochCfg {
+  static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
+  static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_FIXED;
+};
+
 template <class Ham, int S>
-__global__ void __launch_bounds__(JB_THREADS, JB_MINB_FIXED)
+__global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     epoch_kernel(const __grid_constant__ RadauParams P, Parked<Ham::NV>* __restrict__ st, const int* __restrict__ list,
                  int count, int max_passes, unsigned long long* __restrict__ counter, unsigned char* __restrict__ tag,
                  double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
@@ -283,6 +295,8 @@ struct Handle {
   unsigned char* d_tag = nullptr;
   int* d_lists = nullptr;
   int* d_counts = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   int epoch_passes = 24;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
   // workspace of jb200_solve_host
   long long cap = 0;
@@ -406,19 +420,32 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
 
 template <class Ham, int S>
 static int launch_epoch(Handle* H, int k, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
-                        long long* stats, int* nstg, long long* work, cudaStream_t st) {
+                        long long* stats, int* nstg, long long* work, cudaStream_t main_st, int& used) {
+  // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
+  cudaStream_t st = main_st;
+  if (used > 0) {
+    st = H->aux[used - 1];
+    JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
+  }
   auto kern = epoch_kernel<Ham, S>;
+  constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
   if (bps < 1) bps = 1;
+  if (S >= 5 && bps > EpochCfg<S>::minb) bps = EpochCfg<S>::minb;
   long long blocks = (long long)H->sm_count * bps;
-  const long long need = ((long long)count + JB_THREADS - 1) / JB_THREADS;
+  const long long need = ((long long)count + TH - 1) / TH;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + (long long)k * M, count,
+  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + (long long)k * M, count,
                                                H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
                                                stats, nstg, work);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;
+  if (used > 0) {
+    JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
+    JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
+  }
+  used += 1;
   return 0;
 }
 
@@ -452,11 +479,13 @@ static int solve_var(Handle* H, const double* y0, const double* tspan, long long
     JB_CUDA(cudaMemcpyAsync(cnt, H->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
     if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) break;
-    int rc = 0;
-    if (cnt[0]) rc = launch_epoch<Ham, 1>(H, 0, cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, st);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3>(H, 1, cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, st);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5>(H, 2, cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, st);
-    if (!rc && cnt[3]) rc = launch_epoch<Ham, 7>(H, 3, cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    int rc = 0, used = 0;
+    JB_CUDA(cudaEventRecord(H->ev_fork, st));
+    // largest stage count first: its kernel is the longest-running per trajectory
+    if (cnt[3]) rc = launch_epoch<Ham, 7>(H, 3, cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5>(H, 2, cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3>(H, 1, cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1>(H, 0, cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
     if (rc) return rc;
   }
   return 0;
@@ -604,6 +633,11 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&H->sm_count, cudaDevAttrMultiProcessorCount, H->device);
   if (e == cudaSuccess) e = cudaMalloc(&H->d_counter, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+    e = cudaStreamCreateWithFlags(&H->aux[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete H;
     return fail(JB200_ECUDA, std::string("jb200_create: ") + cudaGetErrorString(e));
@@ -621,6 +655,11 @@ void jb200_destroy(void* handle) {
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
   cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
+  for (int i = 0; i < 3; i++) {
+    if (H->aux[i]) cudaStreamDestroy(H->aux[i]);
+    if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]);
+  }
+  if (H->ev_fork) cudaEventDestroy(H->ev_fork);
   delete H;
 }
 
