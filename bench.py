@@ -106,7 +106,8 @@ def cpu_reference_run(a, rows, threads=0):
     from oracle import c_oracle
     cfg = configs.c2_vdp(M=a.M * a.gpus, fixed_order=a.fixed_order, lo=0, hi=rows)
     y0, ts = cfg["y0"].numpy(), cfg["tspan"].numpy()
-    cores = c_oracle.max_threads() if threads <= 0 else threads
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: do not inherit that)
+    cores = len(os.sched_getaffinity(0)) if threads <= 0 else threads
     t0 = time.perf_counter()
     o = c_oracle.solve("vdp", list(cfg["ham"].params), cfg["sign"], y0, ts, cfg["options"], nthreads=cores,
                        arith="reference")
@@ -260,7 +261,7 @@ def run_ours(a):
                             "hbm_bytes_per_launch": h2d + d2h,
                             "hbm_frac_of_measured": ((h2d + d2h) / kernel_s / 1e9) / _hbm_peak()},
                "clocks": clocks}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:
             from oracle import c_oracle
             c_oracle.build()
             rate0, dt0, _, cores = cpu_reference_run(a, 8192)

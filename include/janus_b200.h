@@ -51,6 +51,8 @@ extern "C" {
                                                                    u=-p2((1-x1^2)x2-x1)/W frozen         */
 #define JB200_HAM_VDP_PMP_BANG 3    /* N=2 par: W,umin,umax        same Hu, u=umax if p2(1-x1^2)x2<0 else umin */
 #define JB200_HAM_VDP_AUG_BANG 4    /* N=2 par: umin,umax          H=p1x2+p2(u(1-x1^2)x2-x1), bang-bang u */
+#define JB200_HAM_USER 100          /* plugin libraries only: the user-supplied Hamiltonian the plugin was
+                                       compiled around (janus_ode_b200/user.py; same ABI, N <= 2)          */
 
 /* result codes per trajectory (res[]) -- src/cpp/radaute_impl.hpp:711-719,873-877,1245-1255 */
 #define JB200_RES_OK 0

@@ -3,8 +3,9 @@ optstat/janus-ode behind its solver API).  See DESIGN.md / INTEGRATION.md."""
 from ._lib import JanusB200Error, LIB_PATH
 from .hamiltonians import Hamiltonian, Harmonic, VanDerPol, VdpAug, VdpPmp
 from .options import STAT_NAMES, OptionsTe, StatsTe
+from .user import compile_hamiltonian
 from .solver import HamiltonianSystem, RadauTe, det_pow, fp64_peak_tflops, lu_solve
 
 __all__ = ["JanusB200Error", "LIB_PATH", "Hamiltonian", "Harmonic", "VanDerPol", "VdpAug", "VdpPmp",
            "STAT_NAMES", "OptionsTe", "StatsTe", "HamiltonianSystem", "RadauTe", "det_pow",
-           "fp64_peak_tflops", "lu_solve"]
+           "fp64_peak_tflops", "lu_solve", "compile_hamiltonian"]

@@ -28,6 +28,7 @@ class JanusB200Error(RuntimeError):
 
 
 _lib = None
+_plugins = {}
 
 # every symbol include/janus_b200.h declares
 SYMBOLS = ("jb200_opts_default", "jb200_create", "jb200_destroy", "jb200_ny", "jb200_solve",
@@ -35,14 +36,25 @@ SYMBOLS = ("jb200_opts_default", "jb200_create", "jb200_destroy", "jb200_ny", "j
            "jb200_det_pow", "jb200_fp64_peak", "jb200_last_error", "jb200_version")
 
 
-def lib():
+def lib(path=None):
+    """the C-ABI library; `path` selects a plugin build around a user Hamiltonian (same ABI)."""
     global _lib
+    if path is not None:
+        if path not in _plugins:
+            _plugins[path] = _load(path)
+        return _plugins[path]
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        _lib = _load(LIB_PATH)
+    return _lib
+
+
+def _load(path):
+    if True:
+        if not os.path.exists(path):
             raise JanusB200Error(
-                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(janus_ode_b200 has no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         vp, dp, i64 = C.c_void_p, C.c_void_p, C.c_int64
         L.jb200_opts_default.argtypes = [C.POINTER(jb200_opts)]
         L.jb200_create.argtypes = [C.POINTER(jb200_opts), C.c_int, C.POINTER(C.c_double), C.c_int,
@@ -60,13 +72,16 @@ def lib():
         L.jb200_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.jb200_last_error.restype = C.c_char_p
         L.jb200_version.restype = C.c_char_p
-        _lib = L
-    return _lib
+        return L
 
 
-def check(rc):
+def check(rc, L=None):
     if rc != 0:
-        msg = lib().jb200_last_error().decode()
+        msg = (L or lib()).jb200_last_error().decode()
         if rc == -1:
             raise ValueError(msg)
         raise JanusB200Error(f"janus_b200 error {rc}: {msg}")
+
+
+def check_h(handle, rc):
+    check(rc, handle.L)

@@ -24,6 +24,11 @@
 
 #include "../../include/janus_b200.h"
 #include "radau_core.cuh"
+#ifdef JB_USER_HAM_HEADER
+// Plugin build (janus_ode_b200/user.py): the same library compiled around ONE user-supplied
+// Hamiltonian struct `jb::UserHam` (interface: csrc/hamiltonians.cuh), exposed as JB200_HAM_USER.
+#include JB_USER_HAM_HEADER
+#endif
 
 namespace jb {
 
@@ -308,6 +313,9 @@ struct Handle {
 };
 
 static int ham_ny(int ham_id) {
+#ifdef JB_USER_HAM_HEADER
+  if (ham_id == JB200_HAM_USER) return UserHam::NV;
+#endif
   switch (ham_id) {
     case JB200_HAM_HARMONIC: return 2;
     case JB200_HAM_VDP:
@@ -318,6 +326,9 @@ static int ham_ny(int ham_id) {
   }
 }
 static int ham_npar(int ham_id) {
+#ifdef JB_USER_HAM_HEADER
+  if (ham_id == JB200_HAM_USER) return UserHam::NPAR;
+#endif
   switch (ham_id) {
     case JB200_HAM_HARMONIC: return 1;
     case JB200_HAM_VDP: return 1;
@@ -506,7 +517,13 @@ static int dispatch_order(Handle* H, const double* y0, const double* tspan, long
   return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
 }
 
-#ifdef JB_FAST_BUILD   /* developer builds: van der Pol only (5x faster to compile) */
+#if defined(JB_USER_HAM_HEADER)
+#define JB_HAM_SWITCH(ID, CALL)                                              \
+  switch (ID) {                                                              \
+    case JB200_HAM_USER: { using HamT = UserHam; return CALL; }              \
+    default: return fail(JB200_ENOTSUP, "plugin library: JB200_HAM_USER only"); \
+  }
+#elif defined(JB_FAST_BUILD)   /* developer builds: van der Pol only (5x faster to compile) */
 #define JB_HAM_SWITCH(ID, CALL)                                              \
   switch (ID) {                                                              \
     case JB200_HAM_VDP: { using HamT = HamVdp; return CALL; }                \

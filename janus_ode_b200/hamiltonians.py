@@ -15,6 +15,7 @@ class Hamiltonian:
     ham_id: int
     N: int
     params: tuple
+    lib_path: str | None = None     # plugin library of a user Hamiltonian (janus_ode_b200/user.py)
 
     @property
     def Ny(self):

@@ -51,11 +51,11 @@ def _get_handle(ham: Hamiltonian, options: OptionsTe, costate_sign: int, device)
 
 class _Handle:
     def __init__(self, ham: Hamiltonian, options: OptionsTe, costate_sign: int):
-        L = _lib.lib()
+        L = _lib.lib(ham.lib_path)
         o = options.to_c(ham.Ny, costate_sign)
         par = (C.c_double * max(1, len(ham.params)))(*ham.params)
         h = C.c_void_p()
-        _lib.check(L.jb200_create(C.byref(o), ham.ham_id, par, len(ham.params), C.byref(h)))
+        _lib.check(L.jb200_create(C.byref(o), ham.ham_id, par, len(ham.params), C.byref(h)), L)
         self.h = h
         self.L = L
 
@@ -105,7 +105,7 @@ class HamiltonianSystem:
         y = self._check(y)
         out = torch.empty_like(y)
         H = self._h()
-        _lib.check(H.L.jb200_eval_dyns(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
+        _lib.check_h(H, H.L.jb200_eval_dyns(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
         return out
 
     def jacobian(self, t, y, params=None):
@@ -113,7 +113,7 @@ class HamiltonianSystem:
         ny = self.hamiltonian.Ny
         out = torch.empty(y.shape[0], ny, ny, dtype=torch.float64, device=y.device)
         H = self._h()
-        _lib.check(H.L.jb200_eval_jac(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
+        _lib.check_h(H, H.L.jb200_eval_jac(H.h, _ptr(y), y.shape[0], _ptr(out), _stream_ptr(y.device)))
         return out
 
 
@@ -185,10 +185,10 @@ class RadauTe:
         work = torch.empty(M, dtype=torch.int64, **kw)
         if self.y.is_cuda:
             with torch.cuda.device(dev):
-                _lib.check(H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
+                _lib.check_h(H, H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
                                            _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work), _stream_ptr(dev)))
         else:
-            _lib.check(H.L.jb200_solve_host(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
+            _lib.check_h(H, H.L.jb200_solve_host(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
                                             _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work)))
         self.y, self.t, self.h = y_out, t_out, h_out
         self.stats = StatsTe.from_tensor(stats)
