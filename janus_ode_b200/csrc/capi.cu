@@ -5,7 +5,7 @@
 //                              lanes refill from a global work counter when their trajectory ends
 //                              (active-set maintenance: finished trajectories stop costing work)
 //   init/partition/epoch_kernel<Ham,S>  variable order: trajectories are regrouped by stage count
-//                              between epochs of <= 24 attempted steps, so every warp runs one
+//                              between epochs of <= 12 attempted steps, index lists counting-sorted by a regime key, so every warp runs one
 //                              attempt_step<S> instantiation (order-homogeneous warps); between
 //                              epochs a trajectory is a 568-byte Parked record in HBM
 //   dyns_kernel / jac_kernel   stage evaluation only (dual / hyper-dual), for the dyns /
@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/janus_b200.h"
 #include "radau_core.cuh"
@@ -128,10 +129,24 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED)
 }
 
 // ---- variable-order path: order-homogeneous epochs over parked trajectories (radau_core.cuh) ----
+// Regime key of a parked trajectory: stage count (2 bits) x step-size octave (6 bits) x Newton
+// iterations of its last attempt (2 bits).  Trajectories with the same key behave alike (same number
+// of Newton iterations, same accept/reject pattern), so warps built from key-sorted lists diverge
+// less.  0 = finished.  Purely a scheduling hint: results do not depend on it.
+constexpr int NKEYS = 4 * 256;
+__device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int Newt) {
+  const int k = (NbrStg - 1) >> 1;
+  int e = (int)((__double_as_longlong(h) >> 52) & 0x7ff) - 1023 + 44;   // |h| in [2^-44, 2^20) -> 0..63
+  e = e < 0 ? 0 : (e > 63 ? 63 : e);
+  int nw = Newt - 1;
+  nw = nw < 0 ? 0 : (nw > 3 ? 3 : nw);
+  return (unsigned short)(1 + k * 256 + e * 4 + nw);
+}
+
 template <class Ham>
 __global__ void init_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
                             const double* __restrict__ tspan, long long M, Parked<Ham::NV>* __restrict__ st,
-                            unsigned char* __restrict__ tag) {
+                            unsigned short* __restrict__ tag) {
   constexpr int NY = Ham::NV;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     double y[NY];
@@ -140,19 +155,29 @@ __global__ void init_kernel(const __grid_constant__ RadauParams P, const double*
     Traj<NY, 7> T;
     traj_init<Ham, NY, 7>(T, P, y, ts.x, ts.y);
     park<NY, 7>(T, ts.x, false, false, st[m]);
-    tag[m] = (unsigned char)T.NbrStg;
+    tag[m] = regime_key(T.NbrStg, T.h, T.Newt);
   }
 }
 
-__global__ void partition_kernel(const unsigned char* __restrict__ tag, long long M, int* __restrict__ lists,
-                                 int* __restrict__ counts) {
+__global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ counts) {
+  __shared__ int sh[NKEYS];
+  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     const int t = tag[m];
-    if (t) {
-      const int k = (t - 1) >> 1;
-      const int pos = atomicAdd(&counts[k], 1);
-      lists[(long long)k * M + pos] = (int)m;
-    }
+    if (t) atomicAdd(&sh[t - 1], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&counts[i], sh[i]);
+}
+
+// counting-sort scatter: cursor[key] starts at the exclusive prefix sum of the histogram
+__global__ void scatter_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ cursor,
+                               int* __restrict__ list) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const int t = tag[m];
+    if (t) list[atomicAdd(&cursor[t - 1], 1)] = (int)m;
   }
 }
 
@@ -168,10 +193,10 @@ struct EpochCfg {
   static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_FIXED;
 };
 
-template <class Ham, int S>
+template <class Ham, int S, bool VAR>
 __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     epoch_kernel(const __grid_constant__ RadauParams P, Parked<Ham::NV>* __restrict__ st, const int* __restrict__ list,
-                 int count, int max_passes, unsigned long long* __restrict__ counter, unsigned char* __restrict__ tag,
+                 int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
                  double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
                  int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
                  long long* __restrict__ work) {
@@ -184,9 +209,9 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     double t0;
     bool head_done;
     unpark<NY, S>(st[m], T, t0, head_done);
-    const bool fin = run_epoch<Ham, NY, S>(T, P, head_done, max_passes);
+    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes);
     park<NY, S>(T, t0, head_done, fin, st[m]);
-    tag[m] = fin ? (unsigned char)0 : (unsigned char)T.NbrStg;
+    tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
     if (fin) {
       store_row<NY>(y_out, m, T.y);
       t_out[m] = T.t;
@@ -297,12 +322,13 @@ struct Handle {
   // variable-order epoch workspace
   long long vcap = 0;
   void* d_parked = nullptr;
-  unsigned char* d_tag = nullptr;
+  unsigned short* d_tag = nullptr;
   int* d_lists = nullptr;
   int* d_counts = nullptr;
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-  int epoch_passes = 24;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
+  bool fixed_epochs = false;
+  int epoch_passes = 12;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
   // workspace of jb200_solve_host
   long long cap = 0;
   double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
@@ -429,8 +455,8 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
   return 0;
 }
 
-template <class Ham, int S>
-static int launch_epoch(Handle* H, int k, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
+template <class Ham, int S, bool VAR>
+static int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
                         long long* stats, int* nstg, long long* work, cudaStream_t main_st, int& used) {
   // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
   cudaStream_t st = main_st;
@@ -438,7 +464,7 @@ static int launch_epoch(Handle* H, int k, int count, long long M, double* y_out,
     st = H->aux[used - 1];
     JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
   }
-  auto kern = epoch_kernel<Ham, S>;
+  auto kern = epoch_kernel<Ham, S, VAR>;
   constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
@@ -447,7 +473,7 @@ static int launch_epoch(Handle* H, int k, int count, long long M, double* y_out,
   long long blocks = (long long)H->sm_count * bps;
   const long long need = ((long long)count + TH - 1) / TH;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + (long long)k * M, count,
+  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + base, count,
                                                H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
                                                stats, nstg, work);
   JB_CUDA(cudaGetLastError());
@@ -462,7 +488,7 @@ static int launch_epoch(Handle* H, int k, int count, long long M, double* y_out,
 
 // variable order: init -> { partition by stage count ; one order-homogeneous epoch kernel per
 // non-empty bucket } until no trajectory is left.  Synchronises the stream once per epoch (4 ints).
-template <class Ham>
+template <class Ham, bool VAR = true>
 static int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                      double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
   constexpr int NY = Ham::NV;
@@ -471,32 +497,44 @@ static int solve_var(Handle* H, const double* y0, const double* tspan, long long
     cudaFree(H->d_parked); cudaFree(H->d_tag); cudaFree(H->d_lists); cudaFree(H->d_counts);
     H->vcap = 0;
     JB_CUDA(cudaMalloc(&H->d_parked, sizeof(Parked<NY>) * M));
-    JB_CUDA(cudaMalloc(&H->d_tag, M));
-    JB_CUDA(cudaMalloc(&H->d_lists, sizeof(int) * 4 * M));
-    JB_CUDA(cudaMalloc(&H->d_counts, sizeof(int) * 4));
+    JB_CUDA(cudaMalloc(&H->d_tag, sizeof(unsigned short) * M));
+    JB_CUDA(cudaMalloc(&H->d_lists, sizeof(int) * M));
+    JB_CUDA(cudaMalloc(&H->d_counts, sizeof(int) * NKEYS));
     H->vcap = M;
   }
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
   init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
+  std::vector<int> hist(NKEYS);
   for (long long epoch = 0;; epoch++) {
-    int cnt[4];
-    JB_CUDA(cudaMemsetAsync(H->d_counts, 0, sizeof(int) * 4, st));
+    // counting sort of the live trajectories by regime key -> one contiguous index list, order-major
+    JB_CUDA(cudaMemsetAsync(H->d_counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
-    partition_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_lists, H->d_counts);
+    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts);
     JB_CUDA(cudaGetLastError());
-    H->launches += 1;
-    JB_CUDA(cudaMemcpyAsync(cnt, H->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaMemcpyAsync(hist.data(), H->d_counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
-    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) break;
+    int cnt[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, run = 0;
+    for (int i = 0; i < NKEYS; i++) {
+      const int c = hist[i];
+      hist[i] = run;           // exclusive prefix sum = scatter cursor
+      if ((i & 255) == 0) base[i >> 8] = run;
+      cnt[i >> 8] += c;
+      run += c;
+    }
+    if (run == 0) break;
+    JB_CUDA(cudaMemcpyAsync(H->d_counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
+    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts, H->d_lists);
+    JB_CUDA(cudaGetLastError());
+    H->launches += 2;
     int rc = 0, used = 0;
     JB_CUDA(cudaEventRecord(H->ev_fork, st));
     // largest stage count first: its kernel is the longest-running per trajectory
-    if (cnt[3]) rc = launch_epoch<Ham, 7>(H, 3, cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5>(H, 2, cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3>(H, 1, cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1>(H, 0, cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
     if (rc) return rc;
   }
   return 0;
@@ -506,6 +544,8 @@ template <class Ham>
 static int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                           double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
   const RadauParams& P = H->P;
+  if (P.MinNbrStg == P.MaxNbrStg && H->fixed_epochs)   // fixed order through the regime-sorted epochs
+    return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
     return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
@@ -660,6 +700,7 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
     return fail(JB200_ECUDA, std::string("jb200_create: ") + cudaGetErrorString(e));
   }
   if (const char* ep = std::getenv("JB200_EPOCH_PASSES")) H->epoch_passes = std::max(1, atoi(ep));
+  if (const char* fe = std::getenv("JB200_FIXED_EPOCHS")) H->fixed_epochs = atoi(fe) != 0;
   *handle = H;
   return 0;
 }

@@ -628,7 +628,7 @@ JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_d
 // Run one parked trajectory at stage count S for at most max_passes attempted steps.
 // Returns true when the trajectory is finished; otherwise it must be re-parked (epoch budget
 // used up, or its order changed -> head_done tells the next owner to skip pass_head).
-template <class Ham, int NY, int S>
+template <class Ham, int NY, int S, bool VAR = true>
 JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes) {
   if (!T.NeedNewLU) decomrc<NY, S, S>(T);  // rebuild the factors this trajectory was parked with
   for (int passes = 0;;) {
@@ -637,7 +637,7 @@ JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int 
       return true;
     }
     if (!head_done) {
-      if (!pass_head<Ham, NY, S, true>(T, P)) return true;
+      if (!pass_head<Ham, NY, S, VAR>(T, P)) return true;
     }
     if (T.NbrStg != S) {
       head_done = true;
