@@ -104,6 +104,18 @@ int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, 
                 double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                 int64_t* work, void* stream);
 
+/* Output at interior points of tspan (OutFlag 3 of the reference's MATLAB twin,
+ * src/matlab/radau.m:1150-1168, ntrprad :1291-1308 == src/cpp/radaute_impl.hpp:1413-1440; the
+ * C++ RadauTe leaves this case as a TODO, :1206-1207).  tspan [M,ntspan] with ntspan >= 2 (first
+ * column t0, last tfinal); after every accepted step the requested times it covers are evaluated
+ * on the collocation polynomial: tout [M,ntspan], yout [M,ntspan,Ny], nout [M] (points written;
+ * the last written point is overwritten with the final (t, y) like radau.m:1267-1269).  Rows
+ * beyond nout are left untouched.  Device pointers.                                        */
+int jb200_solve_dense(void* handle, const double* y0, const double* tspan, int ntspan, int64_t M,
+                      double* y_out, double* t_out, double* h_out, int32_t* res, int64_t* stats,
+                      int32_t* nstg, int64_t* work, double* tout, double* yout, int32_t* nout,
+                      void* stream);
+
 /* Same with HOST pointers (what a reference caller holds: CPU tensors).  Copies in, solves,
  * copies out and synchronises; the device workspace lives in the handle.                   */
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,

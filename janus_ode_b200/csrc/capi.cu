@@ -84,6 +84,14 @@ __device__ __forceinline__ void store_row(double* __restrict__ dst, long long m,
 #define JB_THREADS 128
 #endif
 
+// optional dense output (tspan with interior points): device arrays, nullptr when unused
+struct DenseArgs {
+  int ntspan;      // columns of tspan (>= 2)
+  double* tout;    // [M, ntspan] or nullptr
+  double* yout;    // [M, ntspan, NY]
+  int* nout;       // [M]
+};
+
 template <class Ham, int SM, bool VAR>
 __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED) radau_kernel(const __grid_constant__ RadauParams P,
                                                     const double* __restrict__ y0,
@@ -91,25 +99,28 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED)
                                                     double* __restrict__ y_out, double* __restrict__ t_out,
                                                     double* __restrict__ h_out, int* __restrict__ res,
                                                     long long* __restrict__ stats, int* __restrict__ nstg,
-                                                    long long* __restrict__ work,
+                                                    long long* __restrict__ work, const DenseArgs dense,
                                                     unsigned long long* __restrict__ counter) {
   constexpr int NY = Ham::NV;
   Traj<NY, SM> T;
   long long m = -1;
   bool have = false;
+  const int nts = dense.ntspan;
   for (;;) {
     if (!have) {
       m = (long long)atomicAdd(counter, 1ull);
       if (m >= M) break;
       double y[NY];
       load_row<NY>(y0, m, y);
-      const double2 ts = __ldg(reinterpret_cast<const double2*>(tspan) + m);
-      traj_init<Ham, NY, SM>(T, P, y, ts.x, ts.y);
+      traj_init<Ham, NY, SM>(T, P, y, __ldg(tspan + m * nts), __ldg(tspan + m * nts + nts - 1));
       have = true;
     }
+    const DenseOut dout{tspan + m * nts, nts, dense.tout ? dense.tout + m * nts : nullptr,
+                        dense.yout ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut* dp = dense.tout ? &dout : nullptr;
     bool done;
     if (T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
-      done = one_pass<Ham, NY, SM, VAR>(T, P);
+      done = one_pass<Ham, NY, SM, VAR>(T, P, dp);
     } else {  // failed at init, or the step cap ended the loop (radau.m:1287)
       if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
       done = true;
@@ -123,6 +134,10 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED)
       for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
       if (nstg) nstg[m] = T.NbrStg;
       if (work) work[m] = T.work;
+      if (dp) {
+        dense_finish<NY, SM>(T, dout);
+        dense.nout[m] = T.nout;
+      }
       have = false;
     }
   }
@@ -145,16 +160,16 @@ __device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int N
 
 template <class Ham>
 __global__ void init_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
-                            const double* __restrict__ tspan, long long M, Parked<Ham::NV>* __restrict__ st,
-                            unsigned short* __restrict__ tag) {
+                            const double* __restrict__ tspan, int nts, long long M,
+                            Parked<Ham::NV>* __restrict__ st, unsigned short* __restrict__ tag) {
   constexpr int NY = Ham::NV;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     double y[NY];
     load_row<NY>(y0, m, y);
-    const double2 ts = __ldg(reinterpret_cast<const double2*>(tspan) + m);
+    const double t0 = __ldg(tspan + m * nts);
     Traj<NY, 7> T;
-    traj_init<Ham, NY, 7>(T, P, y, ts.x, ts.y);
-    park<NY, 7>(T, ts.x, false, false, st[m]);
+    traj_init<Ham, NY, 7>(T, P, y, t0, __ldg(tspan + m * nts + nts - 1));
+    park<NY, 7>(T, t0, false, false, st[m]);
     tag[m] = regime_key(T.NbrStg, T.h, T.Newt);
   }
 }
@@ -172,12 +187,23 @@ __global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M,
     if (sh[i]) atomicAdd(&counts[i], sh[i]);
 }
 
-// counting-sort scatter: cursor[key] starts at the exclusive prefix sum of the histogram
+// counting-sort scatter: cursor[key] starts at the exclusive prefix sum of the histogram.
+// Warp-aggregated: lanes holding the same key are matched and claim their slots with ONE atomic
+// (the live keys are few, so per-lane atomics serialise on a handful of addresses).
 __global__ void scatter_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ cursor,
                                int* __restrict__ list) {
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    const int t = tag[m];
-    if (t) list[atomicAdd(&cursor[t - 1], 1)] = (int)m;
+  const int lane = threadIdx.x & 31;
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
+    const long long m = base + threadIdx.x;
+    const int t = (m < M) ? (int)tag[m] : 0;
+    const unsigned peers = __match_any_sync(0xffffffffu, t);
+    if (t) {
+      const int leader = __ffs(peers) - 1;
+      int pos = 0;
+      if (lane == leader) pos = atomicAdd(&cursor[t - 1], __popc(peers));
+      pos = __shfl_sync(peers, pos, leader);
+      list[pos + __popc(peers & ((1u << lane) - 1u))] = (int)m;
+    }
   }
 }
 
@@ -199,8 +225,9 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
                  int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
                  double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
                  int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
-                 long long* __restrict__ work) {
+                 long long* __restrict__ work, const double* __restrict__ tspan, const DenseArgs dense) {
   constexpr int NY = Ham::NV;
+  const int nts = dense.ntspan;
   for (;;) {
     const long long i = (long long)atomicAdd(counter, 1ull);
     if (i >= count) break;
@@ -209,7 +236,10 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     double t0;
     bool head_done;
     unpark<NY, S>(st[m], T, t0, head_done);
-    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes);
+    const DenseOut dout{tspan + m * nts, nts, dense.tout ? dense.tout + m * nts : nullptr,
+                        dense.yout ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut* dp = dense.tout ? &dout : nullptr;
+    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp);
     park<NY, S>(T, t0, head_done, fin, st[m]);
     tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
     if (fin) {
@@ -221,6 +251,10 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
       for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
       if (nstg) nstg[m] = T.NbrStg;
       if (work) work[m] = T.work;
+      if (dp) {
+        dense_finish<NY, S>(T, dout);
+        dense.nout[m] = T.nout;
+      }
     }
   }
 }
@@ -439,7 +473,7 @@ static void fill_params(RadauParams& P, const jb200_opts* o, int ny, const doubl
 
 template <class Ham, int SM, bool VAR>
 static int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                        double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
+                        double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
   auto kern = radau_kernel<Ham, SM, VAR>;
   int bps = 0;
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
@@ -449,7 +483,7 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
-  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, H->d_counter);
+  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
@@ -457,7 +491,7 @@ static int launch_radau(Handle* H, const double* y0, const double* tspan, long l
 
 template <class Ham, int S, bool VAR>
 static int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
-                        long long* stats, int* nstg, long long* work, cudaStream_t main_st, int& used) {
+                        long long* stats, int* nstg, long long* work, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
   // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
   cudaStream_t st = main_st;
   if (used > 0) {
@@ -475,7 +509,7 @@ static int launch_epoch(Handle* H, int k, int base, int count, long long M, doub
   if (blocks > need) blocks = need;
   kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + base, count,
                                                H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
-                                               stats, nstg, work);
+                                               stats, nstg, work, tspan, dense);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;
   if (used > 0) {
@@ -490,7 +524,7 @@ static int launch_epoch(Handle* H, int k, int base, int count, long long M, doub
 // non-empty bucket } until no trajectory is left.  Synchronises the stream once per epoch (4 ints).
 template <class Ham, bool VAR = true>
 static int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
+                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
   constexpr int NY = Ham::NV;
   if (M > 2000000000LL) return fail(JB200_EINVAL, "M too large for the variable-order path");
   if (M > H->vcap) {
@@ -503,7 +537,7 @@ static int solve_var(Handle* H, const double* y0, const double* tspan, long long
     H->vcap = M;
   }
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
-  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
+  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, dense.ntspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   std::vector<int> hist(NKEYS);
@@ -531,10 +565,10 @@ static int solve_var(Handle* H, const double* y0, const double* tspan, long long
     int rc = 0, used = 0;
     JB_CUDA(cudaEventRecord(H->ev_fork, st));
     // largest stage count first: its kernel is the longest-running per trajectory
-    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
-    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, st, used);
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
     if (rc) return rc;
   }
   return 0;
@@ -542,19 +576,19 @@ static int solve_var(Handle* H, const double* y0, const double* tspan, long long
 
 template <class Ham>
 static int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                          double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
+                          double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
   const RadauParams& P = H->P;
   if (P.MinNbrStg == P.MaxNbrStg && H->fixed_epochs)   // fixed order through the regime-sorted epochs
-    return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
-    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
-    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 5)
-    return launch_radau<Ham, 5, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    return launch_radau<Ham, 5, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 7)
-    return launch_radau<Ham, 7, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
-  return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st);
+    return launch_radau<Ham, 7, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
 }
 
 #if defined(JB_USER_HAM_HEADER)
@@ -582,12 +616,12 @@ static int dispatch_order(Handle* H, const double* y0, const double* tspan, long
 #endif
 
 static int solve_dev(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, long long* work, cudaStream_t st) {
+                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
   if (M <= 0) {
     H->launches = 0;
     return 0;
   }
-  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, st)));
+  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st)));
 }
 
 template <class Ham>
@@ -729,8 +763,23 @@ int jb200_solve(void* handle, const double* y0, const double* tspan, int64_t M, 
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M < 0) return fail(JB200_EINVAL, "M < 0");
   if (M > 0 && (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats)) return fail(JB200_EINVAL, "null buffer");
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
   return solve_dev(H, y0, tspan, (long long)M, y_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
-                   (long long*)work, (cudaStream_t)stream);
+                   (long long*)work, none, (cudaStream_t)stream);
+}
+
+int jb200_solve_dense(void* handle, const double* y0, const double* tspan, int ntspan, int64_t M, double* y_out,
+                      double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work,
+                      double* tout, double* yout, int32_t* nout, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (ntspan < 2) return fail(JB200_EINVAL, "tspan needs at least [t0, tfinal]");
+  if (M > 0 && (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats || !tout || !yout || !nout))
+    return fail(JB200_EINVAL, "null buffer");
+  const DenseArgs dense{ntspan, tout, yout, (int*)nout};
+  return solve_dev(H, y0, tspan, (long long)M, y_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
+                   (long long*)work, dense, (cudaStream_t)stream);
 }
 
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
@@ -752,7 +801,8 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   const int ny = H->ny;
   JB_CUDA(cudaMemcpyAsync(H->d_y0, y0, sizeof(double) * M * ny, cudaMemcpyHostToDevice, st));
   JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
-  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, H->d_work, st);
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
+  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, H->d_work, none, st);
   if (rc) return rc;
   JB_CUDA(cudaMemcpyAsync(y_out, H->d_y, sizeof(double) * M * ny, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaMemcpyAsync(t_out, H->d_t, sizeof(double) * M, cudaMemcpyDeviceToHost, st));

@@ -63,11 +63,21 @@ JB_HD constexpr int nit_of(int s, int MaxNbrNewton) {
   return s == 1 ? MaxNbrNewton - 3 : s == 3 ? MaxNbrNewton : s == 5 ? MaxNbrNewton + 5 : MaxNbrNewton + 10;
 }
 
+// Output at the interior points of tspan (OutFlag 3, /root/reference/src/matlab/radau.m:1150-1168;
+// the C++ reference leaves this case as a TODO, src/cpp/radaute_impl.hpp:1206-1207): rows of ONE
+// trajectory.  tspan == nullptr: final state only.
+struct DenseOut {
+  const double* tspan;  // [ntspan] requested output times (first = t0, last = tfinal)
+  int ntspan;
+  double* tout;         // [ntspan]
+  double* yout;         // [ntspan][NY]
+};
+
 template <int NY, int SM>
 struct Traj {
   double y[NY], f0[NY], Jac[NY * NY], cont[SM * NY];
   double t, tfinal, h, h_old, hopt, hacc, erracc, FacConv, Theta, Thetat, PosNeg, hmaxn;
-  int NbrStg, Newt, ChangeNbr;
+  int NbrStg, Newt, ChangeNbr, nout;
   bool Last, First, Reject, Keep, ChangeFlag, UnExpStepRej, UnExpNewtRej, NeedNewJac, NeedNewLU;
   int res;
   int st[8];
@@ -99,6 +109,7 @@ JB_HD void traj_init(Traj<NY, SM>& T, const RadauParams& P, const double* y0, do
   T.tfinal = tfinal;
   T.PosNeg = (tfinal - t0) >= 0 ? 1.0 : -1.0;
   T.NbrStg = P.NbrStg;
+  T.nout = 0;
   T.UnExpStepRej = T.UnExpNewtRej = T.Keep = T.ChangeFlag = false;
   T.ChangeNbr = 0;
   T.Theta = T.Thetat = 0.0;
@@ -160,8 +171,46 @@ JB_HD void decomrc(Traj<NY, SM>& T) {
 
 // one pass of the outer loop = one attempted step (radau.m:733-1253).
 // returns true when the trajectory is finished (done or failed; T.res holds the code)
+// dense output after an accepted step: every requested time in (t - h, t] is evaluated on the
+// collocation polynomial (ntrprad, src/cpp/radaute_impl.hpp:1413-1440 == radau.m:1291-1308)
+template <int NY, int S, int SM>
+JB_HD void dense_output(Traj<NY, SM>& T, const DenseOut& out) {
+  using Tab = RadauTab<S>;
+  while (T.nout < out.ntspan) {
+    const double tn = out.tspan[T.nout];
+    if (T.PosNeg * (T.t - tn) < 0) break;
+    if (T.t == tn) {
+      out.tout[T.nout] = T.t;
+#pragma unroll
+      for (int i = 0; i < NY; i++) out.yout[T.nout * NY + i] = T.y[i];
+      T.nout += 1;
+      break;
+    }
+    const double s = (tn - T.t) / T.h_old;  // h_old = the step just taken
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      double yi = (s - (Tab::C(0) - 1.0)) * T.cont[(S - 1) * NY + i];
+#pragma unroll
+      for (int q = 1; q < S; q++) yi = (s - (Tab::C(q) - 1.0)) * (yi + T.cont[(S - 1 - q) * NY + i]);
+      out.yout[T.nout * NY + i] = yi + T.y[i];
+    }
+    out.tout[T.nout] = tn;
+    T.nout += 1;
+  }
+}
+
+// radau.m:1267-1269: the last recorded point is overwritten with the final (t, y)
+template <int NY, int SM>
+JB_HD void dense_finish(const Traj<NY, SM>& T, const DenseOut& out) {
+  if (T.nout >= 1) {
+    out.tout[T.nout - 1] = T.t;
+#pragma unroll
+    for (int i = 0; i < NY; i++) out.yout[(T.nout - 1) * NY + i] = T.y[i];
+  }
+}
+
 template <class Ham, int NY, int S, int SM>
-JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
+JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
   using Tab = RadauTab<S>;
   constexpr int si = (S - 1) / 2;
   const int Nit = nit_of(S, P.MaxNbrNewton);
@@ -444,6 +493,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P) {
 #pragma unroll
         for (int i = 0; i < NY; i++) T.cont[(k - 1) * NY + i] = (T.cont[(k - 1) * NY + i] - T.cont[(k - 2) * NY + i]) * Fact;
       }
+    if (out) dense_output<NY, S, SM>(T, *out);  // radau.m:1150-1168
     T.NeedNewJac = true;
     if (T.Last) {  // radau.m:1193-1197
       T.h = T.hopt;
@@ -536,14 +586,14 @@ JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
 // whole integration of one trajectory.  VAR = false: fixed order S = SM (host guarantees
 // MinNbrStg == MaxNbrStg == NbrStg == SM); VAR = true: orders 1..SM selected at run time.
 template <class Ham, int NY, int SM, bool VAR>
-JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P) {
+JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
   if (!pass_head<Ham, NY, SM, VAR>(T, P)) return true;
-  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P);
+  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P, out);
   switch (T.NbrStg) {
-    case 1: return attempt_step<Ham, NY, 1, SM>(T, P);
-    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P);
-    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P);
-    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P);
+    case 1: return attempt_step<Ham, NY, 1, SM>(T, P, out);
+    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P, out);
+    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P, out);
+    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P, out);
   }
 }
 
@@ -552,10 +602,10 @@ JB_HD bool traj_active(double PosNeg, double t, double tfinal, int steps, long l
 }
 
 template <class Ham, int NY, int SM, bool VAR>
-JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P) {
+JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
   if (T.res != 0) return;
   while (traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
-    if (one_pass<Ham, NY, SM, VAR>(T, P)) return;
+    if (one_pass<Ham, NY, SM, VAR>(T, P, out)) return;
   }
   if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;  // MaxNbrStep exceeded
 }
@@ -579,7 +629,8 @@ struct alignas(16) Parked {
   long long work;
   int st[8];
   int NbrStg, Newt, ChangeNbr, res;
-  unsigned flags, pad;
+  unsigned flags;
+  int nout;
 };
 
 template <int NY, int SM>
@@ -600,7 +651,7 @@ JB_HD void park(const Traj<NY, SM>& T, double t0, bool head_done, bool finished,
             (T.Keep ? PF_KEEP : 0u) | (T.ChangeFlag ? PF_CHANGE : 0u) | (T.UnExpStepRej ? PF_UNEXP_STEP : 0u) |
             (T.UnExpNewtRej ? PF_UNEXP_NEWT : 0u) | (T.NeedNewJac ? PF_NEED_JAC : 0u) |
             (T.NeedNewLU ? PF_NEED_LU : 0u) | (head_done ? PF_HEAD_DONE : 0u) | (finished ? PF_FINISHED : 0u);
-  p.pad = 0u;
+  p.nout = T.nout;
 }
 
 template <int NY, int SM>
@@ -623,13 +674,15 @@ JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_d
   T.Keep = p.flags & PF_KEEP; T.ChangeFlag = p.flags & PF_CHANGE; T.UnExpStepRej = p.flags & PF_UNEXP_STEP;
   T.UnExpNewtRej = p.flags & PF_UNEXP_NEWT; T.NeedNewJac = p.flags & PF_NEED_JAC; T.NeedNewLU = p.flags & PF_NEED_LU;
   head_done = p.flags & PF_HEAD_DONE;
+  T.nout = p.nout;
 }
 
 // Run one parked trajectory at stage count S for at most max_passes attempted steps.
 // Returns true when the trajectory is finished; otherwise it must be re-parked (epoch budget
 // used up, or its order changed -> head_done tells the next owner to skip pass_head).
 template <class Ham, int NY, int S, bool VAR = true>
-JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes) {
+JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes,
+                     const DenseOut* out = nullptr) {
   if (!T.NeedNewLU) decomrc<NY, S, S>(T);  // rebuild the factors this trajectory was parked with
   for (int passes = 0;;) {
     if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
@@ -644,7 +697,7 @@ JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int 
       return false;
     }
     head_done = false;
-    if (attempt_step<Ham, NY, S, S>(T, P)) return true;
+    if (attempt_step<Ham, NY, S, S>(T, P, out)) return true;
     if (++passes >= max_passes) return false;
   }
 }

@@ -144,9 +144,11 @@ class RadauTe:
             raise ValueError(f"y0 must be [M,{ham.Ny}] for Hamiltonian '{ham.name}'")
         if tspan.shape[0] != y0.shape[0] or tspan.shape[1] < 2:
             raise ValueError("tspan must be [M,>=2]")
-        if tspan.shape[1] > 2:
-            raise NotImplementedError("tspan with interior output points (OutFlag 3) is outside the "
-                                      "accelerated path; pass [t0, tfinal]")
+        if tspan.shape[1] > 2 and not y0.is_cuda:
+            raise NotImplementedError("dense output (tspan with interior points) takes CUDA tensors")
+        d = tspan[:, 1:] - tspan[:, :-1]
+        if tspan.shape[1] > 2 and not (bool((d > 0).all()) or bool((d < 0).all())):
+            raise ValueError("Time vector must be strictly monotonic")
         if y0.dtype != torch.float64 or tspan.dtype != torch.float64:
             raise TypeError("y0 and tspan must be float64")
         if y0.device != tspan.device:
@@ -162,7 +164,9 @@ class RadauTe:
             self._handle = _get_handle(ham, self.options, dyns.costate_sign, dev_key)
         self.M, self.Ny = y0.shape
         self.device = y0.device
-        self.tspan = tspan[:, [0, -1]].contiguous()
+        self.tspan = tspan.contiguous()
+        self.ntspan = tspan.shape[1]
+        self.tout = self.yout = self.nout = None
         self.y = y0.contiguous()          # never written: solve() replaces it with the result tensor
         self.t = t0.clone()
         self.h = torch.zeros(self.M, dtype=torch.float64, device=self.device)
@@ -183,7 +187,17 @@ class RadauTe:
         stats = torch.empty(M, 8, dtype=torch.int64, **kw)
         nstg = torch.empty(M, dtype=torch.int32, **kw)
         work = torch.empty(M, dtype=torch.int64, **kw)
-        if self.y.is_cuda:
+        if self.y.is_cuda and self.ntspan > 2:
+            # output at the requested tspan points (radau.m OutFlag 3): tout, yout, nout like the reference
+            self.tout = torch.zeros(M, self.ntspan, dtype=torch.float64, **kw)
+            self.yout = torch.zeros(M, self.ntspan, ny, dtype=torch.float64, **kw)
+            self.nout = torch.zeros(M, dtype=torch.int32, **kw)
+            with torch.cuda.device(dev):
+                _lib.check_h(H, H.L.jb200_solve_dense(H.h, _ptr(self.y), _ptr(self.tspan), self.ntspan, M, _ptr(y_out),
+                                                     _ptr(t_out), _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg),
+                                                     _ptr(work), _ptr(self.tout), _ptr(self.yout), _ptr(self.nout),
+                                                     _stream_ptr(dev)))
+        elif self.y.is_cuda:
             with torch.cuda.device(dev):
                 _lib.check_h(H, H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
                                            _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work), _stream_ptr(dev)))

@@ -694,9 +694,12 @@ static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t
 }
 
 /* one trajectory; returns res code */
+/* dense output rows of one trajectory (radau.m:1150-1168 OutFlag 3); tsp == NULL: final state only */
+typedef struct { const double *tsp; int ntspan; double *tout, *yout; int nout; } dense_t;
+
 static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, double tfinal, const double *y0,
                      double *y_out, double *t_out, double *h_out, long long *st, int *nstg_out,
-                     double *rec_h, int rec_cap, int *rec_n) {
+                     double *rec_h, int rec_cap, int *rec_n, dense_t *dn) {
   const int n = pb->Ny;
   double y[NYMAX], f0[NYMAX], Scal[NYMAX], RelTol1[NYMAX], AbsTol1[NYMAX], QuotTol[NYMAX];
   double Jac[NYMAX * NYMAX];
@@ -935,6 +938,26 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
           for (int i = 0; i < n; i++) cont[k - 1][i] = (cont[k - 1][i] - cont[k - 2][i]) * Fact;
         }
       if (rec_h && rec_n && *rec_n < rec_cap) rec_h[(*rec_n)++] = h;
+      if (dn && dn->tsp) { /* radau.m:1150-1168 + ntrprad :1291-1308 (h_old = the step just taken) */
+        while (dn->nout < dn->ntspan) {
+          const double tn = dn->tsp[dn->nout];
+          if (PosNeg * (t - tn) < 0) break;
+          if (t == tn) {
+            dn->tout[dn->nout] = t;
+            for (int i = 0; i < n; i++) dn->yout[dn->nout * n + i] = y[i];
+            dn->nout += 1;
+            break;
+          }
+          const double sfr = (tn - t) / h_old;
+          for (int i = 0; i < n; i++) {
+            double yi = (sfr - (tb.C[0] - 1.0)) * cont[s - 1][i];
+            for (int q = 1; q < s; q++) yi = (sfr - (tb.C[q] - 1.0)) * (yi + cont[s - 1 - q][i]);
+            dn->yout[dn->nout * n + i] = yi + y[i];
+          }
+          dn->tout[dn->nout] = tn;
+          dn->nout += 1;
+        }
+      }
       NeedNewJac = 1;
       if (Last) {
         h = hopt;
@@ -972,6 +995,10 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
   /* radau.m:1287: only the step cap ends the loop early (t + (tfinal - t) may round below tfinal) */
   if (res == 0 && !finished && PosNeg * t < PosNeg * tfinal) res = 3;
 done:
+  if (dn && dn->tsp && dn->nout >= 1) { /* radau.m:1267-1269 */
+    dn->tout[dn->nout - 1] = t;
+    for (int i = 0; i < n; i++) dn->yout[(dn->nout - 1) * n + i] = y[i];
+  }
   for (int i = 0; i < n; i++) y_out[i] = y[i];
   *t_out = t;
   *h_out = h;
@@ -997,7 +1024,30 @@ int oracle_radau_solve(int problem, const double *par, int sign, int Ny, long lo
 #pragma omp parallel for schedule(dynamic, 16)
   for (long long m = 0; m < M; m++) {
     res[m] = radau_one(&pb, op, tspan[2 * m], tspan[2 * m + 1], y0 + m * Ny, y_out + m * Ny, t_out + m,
-                       h_out + m, stats + 8 * m, nstg + m, NULL, 0, NULL);
+                       h_out + m, stats + 8 * m, nstg + m, NULL, 0, NULL, NULL);
+  }
+  return 0;
+}
+
+/* same with output at the interior points of tspan [M][ntspan]: tout [M][ntspan], yout [M][ntspan][Ny], nout [M] */
+int oracle_radau_solve_dense(int problem, const double *par, int sign, int Ny, long long M, const double *y0,
+                             const double *tspan, int ntspan, const oracle_opts *op, double *y_out, double *t_out,
+                             double *h_out, int *res, long long *stats, int *nstg, double *tout, double *yout,
+                             int *nout, int nthreads) {
+  problem_t pb;
+  pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+  if (Ny > NYMAX) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+  for (long long m = 0; m < M; m++) {
+    dense_t dn;
+    dn.tsp = tspan + m * ntspan; dn.ntspan = ntspan; dn.tout = tout + m * ntspan;
+    dn.yout = yout + m * ntspan * Ny; dn.nout = 0;
+    res[m] = radau_one(&pb, op, tspan[m * ntspan], tspan[m * ntspan + ntspan - 1], y0 + m * Ny, y_out + m * Ny,
+                       t_out + m, h_out + m, stats + 8 * m, nstg + m, NULL, 0, NULL, &dn);
+    nout[m] = dn.nout;
   }
   return 0;
 }
@@ -1009,7 +1059,7 @@ int oracle_radau_trace(int problem, const double *par, int sign, int Ny, const d
   problem_t pb;
   pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
   double h_out; int nstg;
-  return radau_one(&pb, op, tspan[0], tspan[1], y0, y_out, t_out, &h_out, stats, &nstg, rec_h, rec_cap, rec_n);
+  return radau_one(&pb, op, tspan[0], tspan[1], y0, y_out, t_out, &h_out, stats, &nstg, rec_h, rec_cap, rec_n, NULL);
 }
 
 /* batched dynamics / Jacobian (checks the stage-eval kernel) */

@@ -111,6 +111,34 @@ def solve(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)
 
 
+def solve_dense(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
+    """tspan [M, ntspan] with interior output points -> additionally tout [M,ntspan], yout [M,ntspan,Ny], nout."""
+    set_arith(arith)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, Ny = y0.shape
+    nts = tspan.shape[1]
+    y = np.empty_like(y0)
+    t = np.empty(M)
+    h = np.empty(M)
+    res = np.empty(M, dtype=np.int32)
+    stats = np.empty((M, 8), dtype=np.int64)
+    nstg = np.empty(M, dtype=np.int32)
+    tout = np.zeros((M, nts))
+    yout = np.zeros((M, nts, Ny))
+    nout = np.zeros(M, dtype=np.int32)
+    o = _opts(opts, Ny)
+    ip = C.POINTER(C.c_int)
+    rc = lib().oracle_radau_solve_dense(
+        C.c_int(PB[problem]), _dp(par), C.c_int(sign), C.c_int(Ny), C.c_longlong(M), _dp(y0), _dp(tspan),
+        C.c_int(nts), C.byref(o), _dp(y), _dp(t), _dp(h), res.ctypes.data_as(ip),
+        stats.ctypes.data_as(C.POINTER(C.c_longlong)), nstg.ctypes.data_as(ip), _dp(tout), _dp(yout),
+        nout.ctypes.data_as(ip), C.c_int(nthreads))
+    assert rc == 0
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, tout=tout, yout=yout, nout=nout)
+
+
 def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     """one trajectory, with the accepted step sizes."""
     set_arith(arith)

@@ -10,14 +10,24 @@
 
 using namespace jb;
 
+// dense output request for the whole batch (tout == nullptr: none); tspan is [M][g_nts]
+static int g_nts = 2;
+static double *g_tout = nullptr, *g_yout = nullptr;
+static int* g_nout = nullptr;
+
 template <class Ham, int SM, bool VAR>
 static void run(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out,
                 double* t_out, double* h_out, int* res, long long* stats, int* nstg) {
   constexpr int NY = Ham::NV;
   for (long long m = 0; m < M; m++) {
     Traj<NY, SM> T;
-    traj_init<Ham, NY, SM>(T, P, y0 + m * NY, tspan[2 * m], tspan[2 * m + 1]);
-    integrate<Ham, NY, SM, VAR>(T, P);
+    traj_init<Ham, NY, SM>(T, P, y0 + m * NY, tspan[g_nts * m], tspan[g_nts * m + g_nts - 1]);
+    DenseOut d{tspan + m * g_nts, g_nts, g_tout ? g_tout + m * g_nts : nullptr, g_yout ? g_yout + m * g_nts * NY : nullptr};
+    integrate<Ham, NY, SM, VAR>(T, P, g_tout ? &d : nullptr);
+    if (g_tout) {
+      dense_finish<NY, SM>(T, d);
+      g_nout[m] = T.nout;
+    }
     for (int i = 0; i < NY; i++) y_out[m * NY + i] = T.y[i];
     t_out[m] = T.t;
     h_out[m] = T.h;
@@ -37,6 +47,9 @@ static void dispatch(const RadauParams& P, const double* y0, const double* tspan
 }
 
 extern "C" {
+void hostsim_set_dense(int nts, double* tout, double* yout, int* nout) {
+  g_nts = nts; g_tout = tout; g_yout = yout; g_nout = nout;
+}
 // P is passed as raw bytes of jb::RadauParams (filled by the caller, see tests/hostsim.py)
 int hostsim_params_size() { return (int)sizeof(RadauParams); }
 

@@ -49,9 +49,17 @@ def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
     res = np.empty(M, dtype=np.int32)
     stats = np.empty((M, 8), dtype=np.int64)
     nstg = np.empty(M, dtype=np.int32)
+    nts = tspan.shape[1]
+    out = {}
+    if nts > 2:
+        assert epochs_K == 0
+        out = dict(tout=np.zeros((M, nts)), yout=np.zeros((M, nts, ny)), nout=np.zeros(M, dtype=np.int32))
+        lib.hostsim_set_dense(C.c_int(nts), _dp(out["tout"]), _dp(out["yout"]), out["nout"].ctypes.data_as(C.POINTER(C.c_int)))
+    else:
+        lib.hostsim_set_dense(C.c_int(2), None, None, None)
     args = [C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
             res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
             nstg.ctypes.data_as(C.POINTER(C.c_int))]
     rc = lib.hostsim_solve_epochs(*args, C.c_int(epochs_K)) if epochs_K > 0 else lib.hostsim_solve(*args)
     assert rc == 0
-    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg)
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, **out)
