@@ -1,33 +1,15 @@
-// C ABI (include/janus_b200.h) + the CUDA kernels of the Hamiltonian Radau path, sm_100a.
+// C ABI (include/janus_b200.h) of the Hamiltonian Radau path, sm_100a: option validation, per-solve
+// constants, handle / workspace management and dispatch to the per-Hamiltonian entry points
+// (solver_impl.cuh, one translation unit per Hamiltonian: tu_ham.cu), plus the Hamiltonian-independent
+// kernels: lu_kernel (batched small dense LU factor+solve, real / complex), detpow_kernel (test hook),
+// dfma_kernel (FP64 roofline probe).
 //
-// Kernels:
-//   radau_kernel<Ham,S,false>  fixed order: persistent fused integrator, one thread = one trajectory,
-//                              lanes refill from a global work counter when their trajectory ends
-//                              (active-set maintenance: finished trajectories stop costing work)
-//   init/partition/epoch_kernel<Ham,S>  variable order: trajectories are regrouped by stage count
-//                              between epochs of <= 12 attempted steps, index lists counting-sorted by a regime key, so every warp runs one
-//                              attempt_step<S> instantiation (order-homogeneous warps); between
-//                              epochs a trajectory is a 568-byte Parked record in HBM
-//   dyns_kernel / jac_kernel   stage evaluation only (dual / hyper-dual), for the dyns /
-//                              dyns.jacobian surface of the API and for parity tests
-//   lu_kernel                  batched small dense LU factor+solve, real / complex
-//   detpow_kernel, dfma_kernel test hook and FP64 roofline probe
-// Compiled with -fmad=false: every fused multiply-add is an explicit fma() (arithmetic contract,
-// see radau_core.cuh).
-#include <cuda_runtime.h>
-
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/janus_b200.h"
-#include "radau_core.cuh"
+// Build modes:  default      -- capi.cu + 5 x tu_ham.cu, linked (see __graft_entry__.build())
+//               -DJB_USER_HAM_HEADER="file"  monolithic plugin around ONE user Hamiltonian
+//                                            `jb::UserHam` (janus_ode_b200/user.py) = JB200_HAM_USER
+//               -DJB_FAST_BUILD               monolithic, van der Pol only (developer A/B builds)
+#include "solver_impl.cuh"
 #ifdef JB_USER_HAM_HEADER
-// Plugin build (janus_ode_b200/user.py): the same library compiled around ONE user-supplied
-// Hamiltonian struct `jb::UserHam` (interface: csrc/hamiltonians.cuh), exposed as JB200_HAM_USER.
 #include JB_USER_HAM_HEADER
 #endif
 
@@ -35,255 +17,12 @@ namespace jb {
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string& msg) {
+int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-#define JB_CUDA(call)                                                                   \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return fail(JB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
-  } while (0)
 
-// ------------------------------------------------------------------ kernels
-template <int NY>
-__device__ __forceinline__ void load_row(const double* __restrict__ src, long long m, double* dst) {
-  if (NY % 2 == 0) {
-    const double2* s2 = reinterpret_cast<const double2*>(src + m * NY);
-#pragma unroll
-    for (int i = 0; i < NY / 2; i++) {
-      const double2 v = __ldg(s2 + i);
-      dst[2 * i] = v.x;
-      dst[2 * i + 1] = v.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < NY; i++) dst[i] = __ldg(src + m * NY + i);
-  }
-}
-template <int NY>
-__device__ __forceinline__ void store_row(double* __restrict__ dst, long long m, const double* src) {
-  if (NY % 2 == 0) {
-    double2* d2 = reinterpret_cast<double2*>(dst + m * NY);
-#pragma unroll
-    for (int i = 0; i < NY / 2; i++) d2[i] = make_double2(src[2 * i], src[2 * i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < NY; i++) dst[m * NY + i] = src[i];
-  }
-}
-
-#ifndef JB_MINB_FIXED
-#define JB_MINB_FIXED 2   // resident CTAs/SM targeted for the fixed-order kernels (register budget)
-#endif
-#ifndef JB_MINB_VAR
-#define JB_MINB_VAR 2
-#endif
-#ifndef JB_THREADS
-#define JB_THREADS 128
-#endif
-
-// optional dense output (tspan with interior points): device arrays, nullptr when unused
-struct DenseArgs {
-  int ntspan;      // columns of tspan (>= 2)
-  double* tout;    // [M, ntspan] or nullptr
-  double* yout;    // [M, ntspan, NY]
-  int* nout;       // [M]
-};
-
-template <class Ham, int SM, bool VAR>
-__global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED) radau_kernel(const __grid_constant__ RadauParams P,
-                                                    const double* __restrict__ y0,
-                                                    const double* __restrict__ tspan, long long M,
-                                                    double* __restrict__ y_out, double* __restrict__ t_out,
-                                                    double* __restrict__ h_out, int* __restrict__ res,
-                                                    long long* __restrict__ stats, int* __restrict__ nstg,
-                                                    long long* __restrict__ work, const DenseArgs dense,
-                                                    unsigned long long* __restrict__ counter) {
-  constexpr int NY = Ham::NV;
-  Traj<NY, SM> T;
-  long long m = -1;
-  bool have = false;
-  const int nts = dense.ntspan;
-  for (;;) {
-    if (!have) {
-      m = (long long)atomicAdd(counter, 1ull);
-      if (m >= M) break;
-      double y[NY];
-      load_row<NY>(y0, m, y);
-      traj_init<Ham, NY, SM>(T, P, y, __ldg(tspan + m * nts), __ldg(tspan + m * nts + nts - 1));
-      have = true;
-    }
-    const DenseOut dout{tspan + m * nts, nts, dense.tout ? dense.tout + m * nts : nullptr,
-                        dense.yout ? dense.yout + m * nts * NY : nullptr};
-    const DenseOut* dp = dense.tout ? &dout : nullptr;
-    bool done;
-    if (T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
-      done = one_pass<Ham, NY, SM, VAR>(T, P, dp);
-    } else {  // failed at init, or the step cap ended the loop (radau.m:1287)
-      if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
-      done = true;
-    }
-    if (done) {
-      store_row<NY>(y_out, m, T.y);
-      t_out[m] = T.t;
-      h_out[m] = T.h;
-      res[m] = T.res;
-#pragma unroll
-      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
-      if (nstg) nstg[m] = T.NbrStg;
-      if (work) work[m] = T.work;
-      if (dp) {
-        dense_finish<NY, SM>(T, dout);
-        dense.nout[m] = T.nout;
-      }
-      have = false;
-    }
-  }
-}
-
-// ---- variable-order path: order-homogeneous epochs over parked trajectories (radau_core.cuh) ----
-// Regime key of a parked trajectory: stage count (2 bits) x step-size octave (6 bits) x Newton
-// iterations of its last attempt (2 bits).  Trajectories with the same key behave alike (same number
-// of Newton iterations, same accept/reject pattern), so warps built from key-sorted lists diverge
-// less.  0 = finished.  Purely a scheduling hint: results do not depend on it.
-constexpr int NKEYS = 4 * 256;
-__device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int Newt) {
-  const int k = (NbrStg - 1) >> 1;
-  int e = (int)((__double_as_longlong(h) >> 52) & 0x7ff) - 1023 + 44;   // |h| in [2^-44, 2^20) -> 0..63
-  e = e < 0 ? 0 : (e > 63 ? 63 : e);
-  int nw = Newt - 1;
-  nw = nw < 0 ? 0 : (nw > 3 ? 3 : nw);
-  return (unsigned short)(1 + k * 256 + e * 4 + nw);
-}
-
-template <class Ham>
-__global__ void init_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
-                            const double* __restrict__ tspan, int nts, long long M,
-                            Parked<Ham::NV>* __restrict__ st, unsigned short* __restrict__ tag) {
-  constexpr int NY = Ham::NV;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    double y[NY];
-    load_row<NY>(y0, m, y);
-    const double t0 = __ldg(tspan + m * nts);
-    Traj<NY, 7> T;
-    traj_init<Ham, NY, 7>(T, P, y, t0, __ldg(tspan + m * nts + nts - 1));
-    park<NY, 7>(T, t0, false, false, st[m]);
-    tag[m] = regime_key(T.NbrStg, T.h, T.Newt);
-  }
-}
-
-__global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ counts) {
-  __shared__ int sh[NKEYS];
-  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    const int t = tag[m];
-    if (t) atomicAdd(&sh[t - 1], 1);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x)
-    if (sh[i]) atomicAdd(&counts[i], sh[i]);
-}
-
-// counting-sort scatter: cursor[key] starts at the exclusive prefix sum of the histogram.
-// Warp-aggregated: lanes holding the same key are matched and claim their slots with ONE atomic
-// (the live keys are few, so per-lane atomics serialise on a handful of addresses).
-__global__ void scatter_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ cursor,
-                               int* __restrict__ list) {
-  const int lane = threadIdx.x & 31;
-  for (long long base = blockIdx.x * (long long)blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
-    const long long m = base + threadIdx.x;
-    const int t = (m < M) ? (int)tag[m] : 0;
-    const unsigned peers = __match_any_sync(0xffffffffu, t);
-    if (t) {
-      const int leader = __ffs(peers) - 1;
-      int pos = 0;
-      if (lane == leader) pos = atomicAdd(&cursor[t - 1], __popc(peers));
-      pos = __shfl_sync(peers, pos, leader);
-      list[pos + __popc(peers & ((1u << lane) - 1u))] = (int)m;
-    }
-  }
-}
-
-#ifndef JB_MINB_HI
-#define JB_MINB_HI 2      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
-#endif
-#ifndef JB_THREADS_HI
-#define JB_THREADS_HI 128
-#endif
-template <int S>
-struct EpochCfg {
-  static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
-  static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_FIXED;
-};
-
-template <class Ham, int S, bool VAR>
-__global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
-    epoch_kernel(const __grid_constant__ RadauParams P, Parked<Ham::NV>* __restrict__ st, const int* __restrict__ list,
-                 int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
-                 double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
-                 int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
-                 long long* __restrict__ work, const double* __restrict__ tspan, const DenseArgs dense) {
-  constexpr int NY = Ham::NV;
-  const int nts = dense.ntspan;
-  for (;;) {
-    const long long i = (long long)atomicAdd(counter, 1ull);
-    if (i >= count) break;
-    const long long m = list[i];
-    Traj<NY, S> T;
-    double t0;
-    bool head_done;
-    unpark<NY, S>(st[m], T, t0, head_done);
-    const DenseOut dout{tspan + m * nts, nts, dense.tout ? dense.tout + m * nts : nullptr,
-                        dense.yout ? dense.yout + m * nts * NY : nullptr};
-    const DenseOut* dp = dense.tout ? &dout : nullptr;
-    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp);
-    park<NY, S>(T, t0, head_done, fin, st[m]);
-    tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
-    if (fin) {
-      store_row<NY>(y_out, m, T.y);
-      t_out[m] = T.t;
-      h_out[m] = T.h;
-      res[m] = T.res;
-#pragma unroll
-      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
-      if (nstg) nstg[m] = T.NbrStg;
-      if (work) work[m] = T.work;
-      if (dp) {
-        dense_finish<NY, S>(T, dout);
-        dense.nout[m] = T.nout;
-      }
-    }
-  }
-}
-
-template <class Ham>
-__global__ void dyns_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
-                            double* __restrict__ f) {
-  constexpr int NY = Ham::NV;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    double yy[NY], ff[NY];
-    load_row<NY>(y, m, yy);
-    ham_dyns<Ham>(yy, P.ham_par, P.sign, ff);
-    store_row<NY>(f, m, ff);
-  }
-}
-
-template <class Ham>
-__global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
-                           double* __restrict__ J) {
-  constexpr int NY = Ham::NV;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    double yy[NY], JJ[NY * NY];
-    load_row<NY>(y, m, yy);
-    ham_jac<Ham>(yy, P.ham_par, P.sign, JJ);
-#pragma unroll
-    for (int r = 0; r < NY; r++) store_row<NY>(J, m * NY + r, &JJ[r * NY]);
-  }
-}
-
+// ------------------------------------------------------------------ Hamiltonian-independent kernels
 template <int N, bool CPLX>
 __global__ void lu_kernel(long long M, const double* __restrict__ Are, const double* __restrict__ Aim,
                           const double* __restrict__ bre, const double* __restrict__ bim, double* __restrict__ xre,
@@ -345,61 +84,27 @@ __global__ void dfma_kernel(int iters, double seed, double* sink) {
   if (s == 123.456) sink[0] = s;
 }
 
-// ------------------------------------------------------------------ host side
-struct Handle {
-  int ham_id = 0, ny = 0, device = 0, sm_count = 148;
-  RadauParams P;
-  int kernel_sm = 3;     // SM template value in use
-  bool kernel_var = false;
-  unsigned long long* d_counter = nullptr;   // [4] work-fetch counters (one per stage count)
-  int launches = 0;
-  // variable-order epoch workspace
-  long long vcap = 0;
-  void* d_parked = nullptr;
-  unsigned short* d_tag = nullptr;
-  int* d_lists = nullptr;
-  int* d_counts = nullptr;
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-  bool fixed_epochs = false;
-  int epoch_passes = 12;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
-  // workspace of jb200_solve_host
-  long long cap = 0;
-  double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
-  int *d_res = nullptr, *d_nstg = nullptr;
-  long long* d_stats = nullptr;
-  long long* d_work = nullptr;
-  cudaStream_t own_stream = nullptr;
-};
-
-static int ham_ny(int ham_id) {
-#ifdef JB_USER_HAM_HEADER
-  if (ham_id == JB200_HAM_USER) return UserHam::NV;
-#endif
+// ------------------------------------------------------------------ Hamiltonian table
+#if defined(JB_USER_HAM_HEADER)
+static const HamOps jb_ops_user = make_ops<UserHam>();
+static const HamOps* ham_ops(int ham_id) { return ham_id == JB200_HAM_USER ? &jb_ops_user : nullptr; }
+#elif defined(JB_FAST_BUILD)
+static const HamOps jb_ops_vdp = make_ops<HamVdp>();
+static const HamOps* ham_ops(int ham_id) { return ham_id == JB200_HAM_VDP ? &jb_ops_vdp : nullptr; }
+#else
+extern const HamOps jb_ops_harmonic, jb_ops_vdp, jb_ops_vdp_pmp_smooth, jb_ops_vdp_pmp_bang, jb_ops_vdp_aug_bang;
+static const HamOps* ham_ops(int ham_id) {
   switch (ham_id) {
-    case JB200_HAM_HARMONIC: return 2;
-    case JB200_HAM_VDP:
-    case JB200_HAM_VDP_PMP_SMOOTH:
-    case JB200_HAM_VDP_PMP_BANG:
-    case JB200_HAM_VDP_AUG_BANG: return 4;
-    default: return -1;
+    case JB200_HAM_HARMONIC: return &jb_ops_harmonic;
+    case JB200_HAM_VDP: return &jb_ops_vdp;
+    case JB200_HAM_VDP_PMP_SMOOTH: return &jb_ops_vdp_pmp_smooth;
+    case JB200_HAM_VDP_PMP_BANG: return &jb_ops_vdp_pmp_bang;
+    case JB200_HAM_VDP_AUG_BANG: return &jb_ops_vdp_aug_bang;
+    default: return nullptr;
   }
 }
-static int ham_npar(int ham_id) {
-#ifdef JB_USER_HAM_HEADER
-  if (ham_id == JB200_HAM_USER) return UserHam::NPAR;
 #endif
-  switch (ham_id) {
-    case JB200_HAM_HARMONIC: return 1;
-    case JB200_HAM_VDP: return 1;
-    case JB200_HAM_VDP_PMP_SMOOTH: return 1;
-    case JB200_HAM_VDP_PMP_BANG: return 3;
-    case JB200_HAM_VDP_AUG_BANG: return 2;
-    default: return -1;
-  }
-}
 
-// option checks of the reference constructor (radaute_impl.hpp:65-214), returned not exit()ed
 static int validate(const jb200_opts* o, int ny) {
   if (o->n_tol != 1 && o->n_tol != ny) return fail(JB200_EINVAL, "RelTol/AbsTol: vector of length 1 or Ny");
   for (int i = 0; i < o->n_tol; i++) {
@@ -471,172 +176,17 @@ static void fill_params(RadauParams& P, const jb200_opts* o, int ny, const doubl
   for (int i = 0; i < nhp && i < JB200_MAX_HAM_PARAMS; i++) P.ham_par[i] = hp[i];
 }
 
-template <class Ham, int SM, bool VAR>
-static int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                        double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  auto kern = radau_kernel<Ham, SM, VAR>;
-  int bps = 0;
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
-  if (bps < 1) bps = 1;
-  long long blocks = (long long)H->sm_count * bps;
-  const long long need = (M + JB_THREADS - 1) / JB_THREADS;
-  if (blocks > need) blocks = need;
-  if (blocks < 1) blocks = 1;
-  JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
-  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
-  JB_CUDA(cudaGetLastError());
-  H->launches = 1;
-  return 0;
-}
-
-template <class Ham, int S, bool VAR>
-static int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
-                        long long* stats, int* nstg, long long* work, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
-  // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
-  cudaStream_t st = main_st;
-  if (used > 0) {
-    st = H->aux[used - 1];
-    JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
-  }
-  auto kern = epoch_kernel<Ham, S, VAR>;
-  constexpr int TH = EpochCfg<S>::threads;
-  int bps = 0;
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
-  if (bps < 1) bps = 1;
-  if (S >= 5 && bps > EpochCfg<S>::minb) bps = EpochCfg<S>::minb;
-  long long blocks = (long long)H->sm_count * bps;
-  const long long need = ((long long)count + TH - 1) / TH;
-  if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + base, count,
-                                               H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
-                                               stats, nstg, work, tspan, dense);
-  JB_CUDA(cudaGetLastError());
-  H->launches += 1;
-  if (used > 0) {
-    JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
-    JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
-  }
-  used += 1;
-  return 0;
-}
-
-// variable order: init -> { partition by stage count ; one order-homogeneous epoch kernel per
-// non-empty bucket } until no trajectory is left.  Synchronises the stream once per epoch (4 ints).
-template <class Ham, bool VAR = true>
-static int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  constexpr int NY = Ham::NV;
-  if (M > 2000000000LL) return fail(JB200_EINVAL, "M too large for the variable-order path");
-  if (M > H->vcap) {
-    cudaFree(H->d_parked); cudaFree(H->d_tag); cudaFree(H->d_lists); cudaFree(H->d_counts);
-    H->vcap = 0;
-    JB_CUDA(cudaMalloc(&H->d_parked, sizeof(Parked<NY>) * M));
-    JB_CUDA(cudaMalloc(&H->d_tag, sizeof(unsigned short) * M));
-    JB_CUDA(cudaMalloc(&H->d_lists, sizeof(int) * M));
-    JB_CUDA(cudaMalloc(&H->d_counts, sizeof(int) * NKEYS));
-    H->vcap = M;
-  }
-  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
-  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, dense.ntspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
-  JB_CUDA(cudaGetLastError());
-  H->launches = 1;
-  std::vector<int> hist(NKEYS);
-  for (long long epoch = 0;; epoch++) {
-    // counting sort of the live trajectories by regime key -> one contiguous index list, order-major
-    JB_CUDA(cudaMemsetAsync(H->d_counts, 0, sizeof(int) * NKEYS, st));
-    JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
-    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts);
-    JB_CUDA(cudaGetLastError());
-    JB_CUDA(cudaMemcpyAsync(hist.data(), H->d_counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    int cnt[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, run = 0;
-    for (int i = 0; i < NKEYS; i++) {
-      const int c = hist[i];
-      hist[i] = run;           // exclusive prefix sum = scatter cursor
-      if ((i & 255) == 0) base[i >> 8] = run;
-      cnt[i >> 8] += c;
-      run += c;
-    }
-    if (run == 0) break;
-    JB_CUDA(cudaMemcpyAsync(H->d_counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
-    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts, H->d_lists);
-    JB_CUDA(cudaGetLastError());
-    H->launches += 2;
-    int rc = 0, used = 0;
-    JB_CUDA(cudaEventRecord(H->ev_fork, st));
-    // largest stage count first: its kernel is the longest-running per trajectory
-    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (rc) return rc;
-  }
-  return 0;
-}
-
-template <class Ham>
-static int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                          double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  const RadauParams& P = H->P;
-  if (P.MinNbrStg == P.MaxNbrStg && H->fixed_epochs)   // fixed order through the regime-sorted epochs
-    return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
-    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
-    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 5)
-    return launch_radau<Ham, 5, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 7)
-    return launch_radau<Ham, 7, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-  return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
-}
-
-#if defined(JB_USER_HAM_HEADER)
-#define JB_HAM_SWITCH(ID, CALL)                                              \
-  switch (ID) {                                                              \
-    case JB200_HAM_USER: { using HamT = UserHam; return CALL; }              \
-    default: return fail(JB200_ENOTSUP, "plugin library: JB200_HAM_USER only"); \
-  }
-#elif defined(JB_FAST_BUILD)   /* developer builds: van der Pol only (5x faster to compile) */
-#define JB_HAM_SWITCH(ID, CALL)                                              \
-  switch (ID) {                                                              \
-    case JB200_HAM_VDP: { using HamT = HamVdp; return CALL; }                \
-    default: return fail(JB200_ENOTSUP, "fast build: van der Pol only");     \
-  }
-#else
-#define JB_HAM_SWITCH(ID, CALL)                                              \
-  switch (ID) {                                                              \
-    case JB200_HAM_HARMONIC: { using HamT = HamHarmonic; return CALL; }      \
-    case JB200_HAM_VDP: { using HamT = HamVdp; return CALL; }                \
-    case JB200_HAM_VDP_PMP_SMOOTH: { using HamT = HamVdpPmp<false>; return CALL; } \
-    case JB200_HAM_VDP_PMP_BANG: { using HamT = HamVdpPmp<true>; return CALL; }    \
-    case JB200_HAM_VDP_AUG_BANG: { using HamT = HamVdpAugBang; return CALL; }      \
-    default: return fail(JB200_ENOTSUP, "unknown Hamiltonian id");           \
-  }
-#endif
 
 static int solve_dev(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense,
+                     cudaStream_t st) {
   if (M <= 0) {
     H->launches = 0;
     return 0;
   }
-  JB_HAM_SWITCH(H->ham_id, (dispatch_order<HamT>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st)));
-}
-
-template <class Ham>
-static int launch_dyns(Handle* H, const double* y, long long M, double* f, cudaStream_t st) {
-  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
-  dyns_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, f);
-  JB_CUDA(cudaGetLastError());
-  return 0;
-}
-template <class Ham>
-static int launch_jac(Handle* H, const double* y, long long M, double* J, cudaStream_t st) {
-  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
-  jac_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, J);
-  JB_CUDA(cudaGetLastError());
-  return 0;
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops) return fail(JB200_ENOTSUP, "unknown Hamiltonian id");
+  return ops->solve(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
 }
 
 template <int N>
@@ -670,7 +220,10 @@ static int ensure_workspace(Handle* H, long long M) {
   return 0;
 }
 
+
 }  // namespace jb
+
+using namespace jb;
 
 using namespace jb;
 
@@ -707,10 +260,11 @@ int jb200_opts_default(jb200_opts* o) {
 
 int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int n_ham_params, void** handle) {
   if (!o || !handle) return fail(JB200_EINVAL, "null argument");
-  const int ny = ham_ny(ham_id);
-  if (ny < 0) return fail(JB200_ENOTSUP, "unknown Hamiltonian id");
-  if (n_ham_params < ham_npar(ham_id) || (n_ham_params > 0 && !ham_params))
-    return fail(JB200_EINVAL, "Hamiltonian needs " + std::to_string(ham_npar(ham_id)) + " parameters");
+  const HamOps* ops = ham_ops(ham_id);
+  if (!ops) return fail(JB200_ENOTSUP, "unknown Hamiltonian id (not compiled into this library)");
+  const int ny = ops->ny;
+  if (n_ham_params < ops->npar || (n_ham_params > 0 && !ham_params))
+    return fail(JB200_EINVAL, "Hamiltonian needs " + std::to_string(ops->npar) + " parameters");
   int rc = validate(o, ny);
   if (rc) return rc;
   int ndev = 0;
@@ -821,14 +375,14 @@ int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void
   Handle* H = (Handle*)handle;
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M <= 0) return 0;
-  JB_HAM_SWITCH(H->ham_id, (launch_dyns<HamT>(H, y, M, ydot, (cudaStream_t)stream)));
+  return ham_ops(H->ham_id)->dyns(H, y, M, ydot, (cudaStream_t)stream);
 }
 
 int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M <= 0) return 0;
-  JB_HAM_SWITCH(H->ham_id, (launch_jac<HamT>(H, y, M, jac, (cudaStream_t)stream)));
+  return ham_ops(H->ham_id)->jac(H, y, M, jac, (cudaStream_t)stream);
 }
 
 int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre, const double* bim,

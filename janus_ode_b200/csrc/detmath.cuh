@@ -13,7 +13,7 @@
 
 #if defined(__CUDACC__)
 #define JB_HD __host__ __device__ __forceinline__
-#define JB_HD_NOINLINE __host__ __device__ __noinline__
+#define JB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define JB_HD inline
 #define JB_HD_NOINLINE inline

@@ -1,0 +1,453 @@
+// Kernels and host launchers of the Hamiltonian Radau path, templated on the Hamiltonian.
+// Included by one translation unit per Hamiltonian (tu_ham.cu, compiled in parallel by
+// __graft_entry__.build()) and by capi.cu in monolithic builds (plugins around a user Hamiltonian).
+//
+// Kernels:
+//   radau_kernel<Ham,S,false,DENSE>  fixed order: persistent fused integrator, one thread = one
+//                              trajectory, lanes refill from a global work counter when their
+//                              trajectory ends (finished trajectories stop costing work)
+//   init / hist / scatter / epoch_kernel<Ham,S,VAR,DENSE>  variable order: trajectories are regrouped
+//                              by stage count between epochs of <= 12 attempted steps, index lists
+//                              counting-sorted by a regime key, so every warp runs one
+//                              attempt_step<S> instantiation on trajectories that behave alike;
+//                              between epochs a trajectory is a 568-byte Parked record in HBM
+//   dyns_kernel / jac_kernel   stage evaluation only (dual / hyper-dual)
+// Compiled with -fmad=false: every fused multiply-add is an explicit fma() (arithmetic contract,
+// see radau_core.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/janus_b200.h"
+#include "radau_core.cuh"
+
+namespace jb {
+
+int fail(int code, const std::string& msg);   // capi.cu: stores the message for jb200_last_error()
+#define JB_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(JB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+// ------------------------------------------------------------------ kernels
+template <int NY>
+__device__ __forceinline__ void load_row(const double* __restrict__ src, long long m, double* dst) {
+  if (NY % 2 == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(src + m * NY);
+#pragma unroll
+    for (int i = 0; i < NY / 2; i++) {
+      const double2 v = __ldg(s2 + i);
+      dst[2 * i] = v.x;
+      dst[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NY; i++) dst[i] = __ldg(src + m * NY + i);
+  }
+}
+template <int NY>
+__device__ __forceinline__ void store_row(double* __restrict__ dst, long long m, const double* src) {
+  if (NY % 2 == 0) {
+    double2* d2 = reinterpret_cast<double2*>(dst + m * NY);
+#pragma unroll
+    for (int i = 0; i < NY / 2; i++) d2[i] = make_double2(src[2 * i], src[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NY; i++) dst[m * NY + i] = src[i];
+  }
+}
+
+#ifndef JB_MINB_FIXED
+#define JB_MINB_FIXED 2   // resident CTAs/SM targeted for the fixed-order kernels (register budget)
+#endif
+#ifndef JB_MINB_VAR
+#define JB_MINB_VAR 2
+#endif
+#ifndef JB_THREADS
+#define JB_THREADS 128
+#endif
+
+// optional dense output (tspan with interior points): device arrays, nullptr when unused
+struct DenseArgs {
+  int ntspan;      // columns of tspan (>= 2)
+  double* tout;    // [M, ntspan] or nullptr
+  double* yout;    // [M, ntspan, NY]
+  int* nout;       // [M]
+};
+
+template <class Ham, int SM, bool VAR, bool DENSE>
+__global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED) radau_kernel(const __grid_constant__ RadauParams P,
+                                                    const double* __restrict__ y0,
+                                                    const double* __restrict__ tspan, long long M,
+                                                    double* __restrict__ y_out, double* __restrict__ t_out,
+                                                    double* __restrict__ h_out, int* __restrict__ res,
+                                                    long long* __restrict__ stats, int* __restrict__ nstg,
+                                                    long long* __restrict__ work, const DenseArgs dense,
+                                                    unsigned long long* __restrict__ counter) {
+  constexpr int NY = Ham::NV;
+  Traj<NY, SM> T;
+  long long m = -1;
+  bool have = false;
+  const int nts = dense.ntspan;
+  for (;;) {
+    if (!have) {
+      m = (long long)atomicAdd(counter, 1ull);
+      if (m >= M) break;
+      double y[NY];
+      load_row<NY>(y0, m, y);
+      traj_init<Ham, NY, SM>(T, P, y, __ldg(tspan + m * nts), __ldg(tspan + m * nts + nts - 1));
+      have = true;
+    }
+    const DenseOut dout{tspan + m * nts, nts, DENSE ? dense.tout + m * nts : nullptr,
+                        DENSE ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut* dp = DENSE ? &dout : nullptr;   // compile-time: no cost when no dense output is requested
+    bool done;
+    if (T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
+      done = one_pass<Ham, NY, SM, VAR>(T, P, dp);
+    } else {  // failed at init, or the step cap ended the loop (radau.m:1287)
+      if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
+      done = true;
+    }
+    if (done) {
+      store_row<NY>(y_out, m, T.y);
+      t_out[m] = T.t;
+      h_out[m] = T.h;
+      res[m] = T.res;
+#pragma unroll
+      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
+      if (nstg) nstg[m] = T.NbrStg;
+      if (work) work[m] = T.work;
+      if (dp) {
+        dense_finish<NY, SM>(T, dout);
+        dense.nout[m] = T.nout;
+      }
+      have = false;
+    }
+  }
+}
+
+// ---- variable-order path: order-homogeneous epochs over parked trajectories (radau_core.cuh) ----
+// Regime key of a parked trajectory: stage count (2 bits) x step-size octave (6 bits) x Newton
+// iterations of its last attempt (2 bits).  Trajectories with the same key behave alike (same number
+// of Newton iterations, same accept/reject pattern), so warps built from key-sorted lists diverge
+// less.  0 = finished.  Purely a scheduling hint: results do not depend on it.
+constexpr int NKEYS = 4 * 256;
+__device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int Newt) {
+  const int k = (NbrStg - 1) >> 1;
+  int e = (int)((__double_as_longlong(h) >> 52) & 0x7ff) - 1023 + 44;   // |h| in [2^-44, 2^20) -> 0..63
+  e = e < 0 ? 0 : (e > 63 ? 63 : e);
+  int nw = Newt - 1;
+  nw = nw < 0 ? 0 : (nw > 3 ? 3 : nw);
+  return (unsigned short)(1 + k * 256 + e * 4 + nw);
+}
+
+template <class Ham>
+__global__ void init_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
+                            const double* __restrict__ tspan, int nts, long long M,
+                            Parked<Ham::NV>* __restrict__ st, unsigned short* __restrict__ tag) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double y[NY];
+    load_row<NY>(y0, m, y);
+    const double t0 = __ldg(tspan + m * nts);
+    Traj<NY, 7> T;
+    traj_init<Ham, NY, 7>(T, P, y, t0, __ldg(tspan + m * nts + nts - 1));
+    park<NY, 7>(T, t0, false, false, st[m]);
+    tag[m] = regime_key(T.NbrStg, T.h, T.Newt);
+  }
+}
+
+static __global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ counts) {
+  __shared__ int sh[NKEYS];
+  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const int t = tag[m];
+    if (t) atomicAdd(&sh[t - 1], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NKEYS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&counts[i], sh[i]);
+}
+
+// counting-sort scatter: cursor[key] starts at the exclusive prefix sum of the histogram.
+// Warp-aggregated: lanes holding the same key are matched and claim their slots with ONE atomic
+// (the live keys are few, so per-lane atomics serialise on a handful of addresses).
+static __global__ void scatter_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ cursor,
+                               int* __restrict__ list) {
+  const int lane = threadIdx.x & 31;
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
+    const long long m = base + threadIdx.x;
+    const int t = (m < M) ? (int)tag[m] : 0;
+    const unsigned peers = __match_any_sync(0xffffffffu, t);
+    if (t) {
+      const int leader = __ffs(peers) - 1;
+      int pos = 0;
+      if (lane == leader) pos = atomicAdd(&cursor[t - 1], __popc(peers));
+      pos = __shfl_sync(peers, pos, leader);
+      list[pos + __popc(peers & ((1u << lane) - 1u))] = (int)m;
+    }
+  }
+}
+
+#ifndef JB_MINB_HI
+#define JB_MINB_HI 2      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
+#endif
+#ifndef JB_THREADS_HI
+#define JB_THREADS_HI 128
+#endif
+template <int S>
+struct EpochCfg {
+  static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
+  static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_FIXED;
+};
+
+template <class Ham, int S, bool VAR, bool DENSE>
+__global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
+    epoch_kernel(const __grid_constant__ RadauParams P, Parked<Ham::NV>* __restrict__ st, const int* __restrict__ list,
+                 int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
+                 double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
+                 int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
+                 long long* __restrict__ work, const double* __restrict__ tspan, const DenseArgs dense) {
+  constexpr int NY = Ham::NV;
+  const int nts = dense.ntspan;
+  for (;;) {
+    const long long i = (long long)atomicAdd(counter, 1ull);
+    if (i >= count) break;
+    const long long m = list[i];
+    Traj<NY, S> T;
+    double t0;
+    bool head_done;
+    unpark<NY, S>(st[m], T, t0, head_done);
+    const DenseOut dout{tspan + m * nts, nts, DENSE ? dense.tout + m * nts : nullptr,
+                        DENSE ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut* dp = DENSE ? &dout : nullptr;
+    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp);
+    park<NY, S>(T, t0, head_done, fin, st[m]);
+    tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
+    if (fin) {
+      store_row<NY>(y_out, m, T.y);
+      t_out[m] = T.t;
+      h_out[m] = T.h;
+      res[m] = T.res;
+#pragma unroll
+      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
+      if (nstg) nstg[m] = T.NbrStg;
+      if (work) work[m] = T.work;
+      if (dp) {
+        dense_finish<NY, S>(T, dout);
+        dense.nout[m] = T.nout;
+      }
+    }
+  }
+}
+
+template <class Ham>
+__global__ void dyns_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
+                            double* __restrict__ f) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double yy[NY], ff[NY];
+    load_row<NY>(y, m, yy);
+    ham_dyns<Ham>(yy, P.ham_par, P.sign, ff);
+    store_row<NY>(f, m, ff);
+  }
+}
+
+template <class Ham>
+__global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
+                           double* __restrict__ J) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double yy[NY], JJ[NY * NY];
+    load_row<NY>(y, m, yy);
+    ham_jac<Ham>(yy, P.ham_par, P.sign, JJ);
+#pragma unroll
+    for (int r = 0; r < NY; r++) store_row<NY>(J, m * NY + r, &JJ[r * NY]);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct Handle {
+  int ham_id = 0, ny = 0, device = 0, sm_count = 148;
+  RadauParams P;
+  int kernel_sm = 3;     // SM template value in use
+  bool kernel_var = false;
+  unsigned long long* d_counter = nullptr;   // [4] work-fetch counters (one per stage count)
+  int launches = 0;
+  // variable-order epoch workspace
+  long long vcap = 0;
+  void* d_parked = nullptr;
+  unsigned short* d_tag = nullptr;
+  int* d_lists = nullptr;
+  int* d_counts = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  bool fixed_epochs = false;
+  int epoch_passes = 12;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
+  // workspace of jb200_solve_host
+  long long cap = 0;
+  double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
+  int *d_res = nullptr, *d_nstg = nullptr;
+  long long* d_stats = nullptr;
+  long long* d_work = nullptr;
+  cudaStream_t own_stream = nullptr;
+};
+
+template <class Ham, int SM, bool VAR>
+int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                        double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  auto kern = dense.tout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
+  int bps = 0;
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
+  if (bps < 1) bps = 1;
+  long long blocks = (long long)H->sm_count * bps;
+  const long long need = (M + JB_THREADS - 1) / JB_THREADS;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
+  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  return 0;
+}
+
+template <class Ham, int S, bool VAR>
+int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
+                        long long* stats, int* nstg, long long* work, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
+  // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
+  cudaStream_t st = main_st;
+  if (used > 0) {
+    st = H->aux[used - 1];
+    JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
+  }
+  auto kern = dense.tout ? epoch_kernel<Ham, S, VAR, true> : epoch_kernel<Ham, S, VAR, false>;
+  constexpr int TH = EpochCfg<S>::threads;
+  int bps = 0;
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
+  if (bps < 1) bps = 1;
+  if (S >= 5 && bps > EpochCfg<S>::minb) bps = EpochCfg<S>::minb;
+  long long blocks = (long long)H->sm_count * bps;
+  const long long need = ((long long)count + TH - 1) / TH;
+  if (blocks > need) blocks = need;
+  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + base, count,
+                                               H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
+                                               stats, nstg, work, tspan, dense);
+  JB_CUDA(cudaGetLastError());
+  H->launches += 1;
+  if (used > 0) {
+    JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
+    JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
+  }
+  used += 1;
+  return 0;
+}
+
+// variable order: init -> { partition by stage count ; one order-homogeneous epoch kernel per
+// non-empty bucket } until no trajectory is left.  Synchronises the stream once per epoch (4 ints).
+template <class Ham, bool VAR = true>
+int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  constexpr int NY = Ham::NV;
+  if (M > 2000000000LL) return fail(JB200_EINVAL, "M too large for the variable-order path");
+  if (M > H->vcap) {
+    cudaFree(H->d_parked); cudaFree(H->d_tag); cudaFree(H->d_lists); cudaFree(H->d_counts);
+    H->vcap = 0;
+    JB_CUDA(cudaMalloc(&H->d_parked, sizeof(Parked<NY>) * M));
+    JB_CUDA(cudaMalloc(&H->d_tag, sizeof(unsigned short) * M));
+    JB_CUDA(cudaMalloc(&H->d_lists, sizeof(int) * M));
+    JB_CUDA(cudaMalloc(&H->d_counts, sizeof(int) * NKEYS));
+    H->vcap = M;
+  }
+  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
+  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, dense.ntspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  std::vector<int> hist(NKEYS);
+  for (long long epoch = 0;; epoch++) {
+    // counting sort of the live trajectories by regime key -> one contiguous index list, order-major
+    JB_CUDA(cudaMemsetAsync(H->d_counts, 0, sizeof(int) * NKEYS, st));
+    JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
+    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts);
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaMemcpyAsync(hist.data(), H->d_counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    int cnt[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, run = 0;
+    for (int i = 0; i < NKEYS; i++) {
+      const int c = hist[i];
+      hist[i] = run;           // exclusive prefix sum = scatter cursor
+      if ((i & 255) == 0) base[i >> 8] = run;
+      cnt[i >> 8] += c;
+      run += c;
+    }
+    if (run == 0) break;
+    JB_CUDA(cudaMemcpyAsync(H->d_counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
+    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts, H->d_lists);
+    JB_CUDA(cudaGetLastError());
+    H->launches += 2;
+    int rc = 0, used = 0;
+    JB_CUDA(cudaEventRecord(H->ev_fork, st));
+    // largest stage count first: its kernel is the longest-running per trajectory
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <class Ham>
+int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                          double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  const RadauParams& P = H->P;
+  if (P.MinNbrStg == P.MaxNbrStg && H->fixed_epochs)   // fixed order through the regime-sorted epochs
+    return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
+    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 1)
+    return launch_radau<Ham, 1, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 5)
+    return launch_radau<Ham, 5, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 7)
+    return launch_radau<Ham, 7, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+}
+
+template <class Ham>
+int launch_dyns(Handle* H, const double* y, long long M, double* f, cudaStream_t st) {
+  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
+  dyns_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, f);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <class Ham>
+int launch_jac(Handle* H, const double* y, long long M, double* J, cudaStream_t st) {
+  const long long blocks = std::min<long long>((M + 127) / 128, (long long)H->sm_count * 16);
+  jac_kernel<Ham><<<(unsigned)std::max<long long>(blocks, 1), 128, 0, st>>>(H->P, y, M, J);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one table of entry points per Hamiltonian: what capi.cu dispatches on
+struct HamOps {
+  int ny, npar;
+  int (*solve)(Handle*, const double*, const double*, long long, double*, double*, double*, int*, long long*, int*,
+               long long*, const DenseArgs&, cudaStream_t);
+  int (*dyns)(Handle*, const double*, long long, double*, cudaStream_t);
+  int (*jac)(Handle*, const double*, long long, double*, cudaStream_t);
+};
+template <class Ham>
+HamOps make_ops() {
+  return HamOps{Ham::NV, Ham::NPAR, &dispatch_order<Ham>, &launch_dyns<Ham>, &launch_jac<Ham>};
+}
+
+}  // namespace jb
