@@ -122,6 +122,22 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
                      double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                      int64_t* work);
 
+/* Incremental stepping: the state / step(htry, dyns, ft, state) protocol of the reference's Python
+ * steppers (src/python/seulext.py:8-148 SeulexState, :158-581 step; src/python/seulex_dual_example_vdp.py:
+ * 136-175 driver loop), carried by the Radau stepper.  A state holds M trajectories parked on the
+ * device.  jb200_state_step advances every unfinished trajectory by exactly ONE ACCEPTED step
+ * (rejected attempts are retried inside); htry [M] (device, may be NULL = keep the controller's own
+ * proposal) is the trial step, as in step(htry, ...).  Stepping with htry = hnext until every
+ * trajectory is done reproduces jb200_solve bit for bit.  jb200_state_read copies out y [M,Ny],
+ * t [M], hnext [M], hdid [M], res [M], stats [M,8], nstg [M] (may be NULL), done [M] (may be NULL).
+ * The handle must outlive its states.                                                        */
+int jb200_state_create(void* handle, const double* y0, const double* tspan, int64_t M, void** state,
+                       void* stream);
+int jb200_state_step(void* state, const double* htry, void* stream);
+int jb200_state_read(void* state, double* y, double* t, double* hnext, double* hdid, int32_t* res,
+                     int64_t* stats, int32_t* nstg, int32_t* done, void* stream);
+void jb200_state_destroy(void* state);
+
 /* kernels launched by the last jb200_solve* call on this handle */
 int jb200_last_launches(void* handle);
 

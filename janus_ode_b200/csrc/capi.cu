@@ -297,7 +297,7 @@ void jb200_destroy(void* handle) {
   Handle* H = (Handle*)handle;
   if (!H) return;
   cudaFree(H->d_counter);
-  cudaFree(H->d_parked); cudaFree(H->d_tag); cudaFree(H->d_lists); cudaFree(H->d_counts);
+  ws_free(H->ws);
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
   cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
@@ -367,6 +367,52 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   if (work) JB_CUDA(cudaMemcpyAsync(work, H->d_work, sizeof(long long) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+// ---- incremental stepping
+struct State {
+  Handle* H;
+  EpochWS ws;
+};
+
+int jb200_state_create(void* handle, const double* y0, const double* tspan, int64_t M, void** state, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !state) return fail(JB200_EINVAL, "null argument");
+  if (M < 0 || (M > 0 && (!y0 || !tspan))) return fail(JB200_EINVAL, "bad batch");
+  const HamOps* ops = ham_ops(H->ham_id);
+  State* S = new State{H, EpochWS()};
+  if (M > 0) {
+    int rc = ops->st_init(H, S->ws, y0, tspan, 2, (long long)M, (cudaStream_t)stream);
+    if (rc) {
+      ws_free(S->ws);
+      delete S;
+      return rc;
+    }
+  }
+  *state = S;
+  return 0;
+}
+
+int jb200_state_step(void* state, const double* htry, void* stream) {
+  State* S = (State*)state;
+  if (!S) return fail(JB200_EINVAL, "null state");
+  return ham_ops(S->H->ham_id)->st_step(S->H, S->ws, htry, (cudaStream_t)stream);
+}
+
+int jb200_state_read(void* state, double* y, double* t, double* hnext, double* hdid, int32_t* res, int64_t* stats,
+                     int32_t* nstg, int32_t* done, void* stream) {
+  State* S = (State*)state;
+  if (!S) return fail(JB200_EINVAL, "null state");
+  if (S->ws.M > 0 && (!y || !t || !hnext || !hdid || !res || !stats)) return fail(JB200_EINVAL, "null buffer");
+  return ham_ops(S->H->ham_id)->st_read(S->H, S->ws, y, t, hnext, hdid, (int*)res, (long long*)stats, (int*)nstg,
+                                        (int*)done, (cudaStream_t)stream);
+}
+
+void jb200_state_destroy(void* state) {
+  State* S = (State*)state;
+  if (!S) return;
+  ws_free(S->ws);
+  delete S;
 }
 
 int jb200_last_launches(void* handle) { return handle ? ((Handle*)handle)->launches : 0; }

@@ -680,10 +680,13 @@ JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_d
 // Run one parked trajectory at stage count S for at most max_passes attempted steps.
 // Returns true when the trajectory is finished; otherwise it must be re-parked (epoch budget
 // used up, or its order changed -> head_done tells the next owner to skip pass_head).
+// stop_on_accept (incremental step() API): also stop, with *stepped = true, right after the first
+// accepted step.
 template <class Ham, int NY, int S, bool VAR = true>
 JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes,
-                     const DenseOut* out = nullptr) {
+                     const DenseOut* out = nullptr, bool stop_on_accept = false, bool* stepped = nullptr) {
   if (!T.NeedNewLU) decomrc<NY, S, S>(T);  // rebuild the factors this trajectory was parked with
+  const int acc0 = T.st[ST_ACC];
   for (int passes = 0;;) {
     if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
       if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
@@ -698,6 +701,10 @@ JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int 
     }
     head_done = false;
     if (attempt_step<Ham, NY, S, S>(T, P, out)) return true;
+    if (stop_on_accept && T.st[ST_ACC] != acc0) {
+      *stepped = true;
+      return false;
+    }
     if (++passes >= max_passes) return false;
   }
 }

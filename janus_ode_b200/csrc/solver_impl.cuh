@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
                  int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
                  double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
                  int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
-                 long long* __restrict__ work, const double* __restrict__ tspan, const DenseArgs dense) {
+                 long long* __restrict__ work, const double* __restrict__ tspan, const DenseArgs dense,
+                 const int stop_on_accept) {
   constexpr int NY = Ham::NV;
   const int nts = dense.ntspan;
   for (;;) {
@@ -230,10 +231,11 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     const DenseOut dout{tspan + m * nts, nts, DENSE ? dense.tout + m * nts : nullptr,
                         DENSE ? dense.yout + m * nts * NY : nullptr};
     const DenseOut* dp = DENSE ? &dout : nullptr;
-    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp);
+    bool stepped = false;
+    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp, stop_on_accept != 0, &stepped);
     park<NY, S>(T, t0, head_done, fin, st[m]);
-    tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
-    if (fin) {
+    tag[m] = (fin || stepped) ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
+    if (fin && y_out) {
       store_row<NY>(y_out, m, T.y);
       t_out[m] = T.t;
       h_out[m] = T.h;
@@ -276,6 +278,32 @@ __global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* 
 }
 
 // ------------------------------------------------------------------ host side
+// parked trajectories + the index lists of the epoch scheme; owned by a handle (solve) or by an
+// incremental-stepping state (jb200_state_*)
+struct EpochWS {
+  long long cap = 0, M = 0;
+  void* parked = nullptr;
+  unsigned short* tag = nullptr;
+  int* lists = nullptr;
+  int* counts = nullptr;
+};
+inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
+  ws.M = M;
+  if (M <= ws.cap) return 0;
+  cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
+  ws.cap = 0;
+  JB_CUDA(cudaMalloc(&ws.parked, parked_bytes * M));
+  JB_CUDA(cudaMalloc(&ws.tag, sizeof(unsigned short) * M));
+  JB_CUDA(cudaMalloc(&ws.lists, sizeof(int) * M));
+  JB_CUDA(cudaMalloc(&ws.counts, sizeof(int) * NKEYS));
+  ws.cap = M;
+  return 0;
+}
+inline void ws_free(EpochWS& ws) {
+  cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
+  ws = EpochWS();
+}
+
 struct Handle {
   int ham_id = 0, ny = 0, device = 0, sm_count = 148;
   RadauParams P;
@@ -284,11 +312,7 @@ struct Handle {
   unsigned long long* d_counter = nullptr;   // [4] work-fetch counters (one per stage count)
   int launches = 0;
   // variable-order epoch workspace
-  long long vcap = 0;
-  void* d_parked = nullptr;
-  unsigned short* d_tag = nullptr;
-  int* d_lists = nullptr;
-  int* d_counts = nullptr;
+  EpochWS ws;
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool fixed_epochs = false;
@@ -320,9 +344,18 @@ int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, 
   return 0;
 }
 
+// outputs of a solve (device arrays; y_out == nullptr: none, incremental stepping)
+struct OutArgs {
+  double *y_out, *t_out, *h_out;
+  int* res;
+  long long* stats;
+  int* nstg;
+  long long* work;
+};
+
 template <class Ham, int S, bool VAR>
-int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_out, double* t_out, double* h_out, int* res,
-                        long long* stats, int* nstg, long long* work, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
+int launch_epoch(Handle* H, EpochWS& ws, int k, int base, int count, int max_passes, int stop_on_accept,
+                 const OutArgs& o, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
   // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
   cudaStream_t st = main_st;
   if (used > 0) {
@@ -338,9 +371,9 @@ int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_o
   long long blocks = (long long)H->sm_count * bps;
   const long long need = ((long long)count + TH - 1) / TH;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)H->d_parked, H->d_lists + base, count,
-                                               H->epoch_passes, H->d_counter + k, H->d_tag, y_out, t_out, h_out, res,
-                                               stats, nstg, work, tspan, dense);
+  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
+                                        H->d_counter + k, ws.tag, o.y_out, o.t_out, o.h_out, o.res, o.stats, o.nstg,
+                                        o.work, tspan, dense, stop_on_accept);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;
   if (used > 0) {
@@ -351,57 +384,147 @@ int launch_epoch(Handle* H, int k, int base, int count, long long M, double* y_o
   return 0;
 }
 
-// variable order: init -> { partition by stage count ; one order-homogeneous epoch kernel per
-// non-empty bucket } until no trajectory is left.  Synchronises the stream once per epoch (4 ints).
-template <class Ham, bool VAR = true>
-int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
-                     double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  constexpr int NY = Ham::NV;
-  if (M > 2000000000LL) return fail(JB200_EINVAL, "M too large for the variable-order path");
-  if (M > H->vcap) {
-    cudaFree(H->d_parked); cudaFree(H->d_tag); cudaFree(H->d_lists); cudaFree(H->d_counts);
-    H->vcap = 0;
-    JB_CUDA(cudaMalloc(&H->d_parked, sizeof(Parked<NY>) * M));
-    JB_CUDA(cudaMalloc(&H->d_tag, sizeof(unsigned short) * M));
-    JB_CUDA(cudaMalloc(&H->d_lists, sizeof(int) * M));
-    JB_CUDA(cudaMalloc(&H->d_counts, sizeof(int) * NKEYS));
-    H->vcap = M;
-  }
+// { counting sort of the live trajectories by regime key ; one order-homogeneous epoch kernel per
+// non-empty stage-count bucket } until no trajectory is tagged live.  Synchronises the stream once
+// per epoch (1024 counters).
+template <class Ham, bool VAR>
+int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const OutArgs& o, const double* tspan,
+               const DenseArgs& dense, cudaStream_t st) {
+  const long long M = ws.M;
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
-  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, dense.ntspan, M, (Parked<NY>*)H->d_parked, H->d_tag);
-  JB_CUDA(cudaGetLastError());
-  H->launches = 1;
   std::vector<int> hist(NKEYS);
   for (long long epoch = 0;; epoch++) {
-    // counting sort of the live trajectories by regime key -> one contiguous index list, order-major
-    JB_CUDA(cudaMemsetAsync(H->d_counts, 0, sizeof(int) * NKEYS, st));
+    JB_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
-    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts);
+    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts);
     JB_CUDA(cudaGetLastError());
-    JB_CUDA(cudaMemcpyAsync(hist.data(), H->d_counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaMemcpyAsync(hist.data(), ws.counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
     int cnt[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, run = 0;
     for (int i = 0; i < NKEYS; i++) {
       const int c = hist[i];
-      hist[i] = run;           // exclusive prefix sum = scatter cursor
+      hist[i] = run;  // exclusive prefix sum = scatter cursor
       if ((i & 255) == 0) base[i >> 8] = run;
       cnt[i >> 8] += c;
       run += c;
     }
+    H->launches += 1;
     if (run == 0) break;
-    JB_CUDA(cudaMemcpyAsync(H->d_counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
-    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(H->d_tag, M, H->d_counts, H->d_lists);
+    JB_CUDA(cudaMemcpyAsync(ws.counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
+    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, ws.lists);
     JB_CUDA(cudaGetLastError());
-    H->launches += 2;
+    H->launches += 1;
     int rc = 0, used = 0;
     JB_CUDA(cudaEventRecord(H->ev_fork, st));
     // largest stage count first: its kernel is the longest-running per trajectory
-    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, 3, base[3], cnt[3], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, 2, base[2], cnt[2], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, 1, base[1], cnt[1], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
-    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, 0, base[0], cnt[0], M, y_out, t_out, h_out, res, stats, nstg, work, tspan, dense, st, used);
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, ws, 3, base[3], cnt[3], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, ws, 2, base[2], cnt[2], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, ws, 1, base[1], cnt[1], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, ws, 0, base[0], cnt[0], max_passes, stop_on_accept, o, tspan, dense, st, used);
     if (rc) return rc;
   }
+  return 0;
+}
+
+template <class Ham>
+int ws_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int ntspan, long long M, cudaStream_t st) {
+  constexpr int NY = Ham::NV;
+  if (M > 2000000000LL) return fail(JB200_EINVAL, "M too large for the epoch path");
+  int rc = ws_reserve(ws, M, sizeof(Parked<NY>));
+  if (rc) return rc;
+  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
+  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, ntspan, M, (Parked<NY>*)ws.parked, ws.tag);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// variable order (and, optionally, fixed order) through the epochs
+template <class Ham, bool VAR = true>
+int solve_var(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+              double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense,
+              cudaStream_t st) {
+  int rc = ws_init<Ham>(H, H->ws, y0, tspan, dense.ntspan, M, st);
+  if (rc) return rc;
+  H->launches = 1;
+  const OutArgs o{y_out, t_out, h_out, res, stats, nstg, work};
+  return run_epochs<Ham, VAR>(H, H->ws, H->epoch_passes, 0, o, tspan, dense, st);
+}
+
+// ---- incremental stepping (the state / step(htry, ...) protocol of the reference's Python steppers,
+//      src/python/seulext.py:8-148,158-581): a state is a set of parked trajectories
+template <int NY>
+__global__ void rearm_kernel(const __grid_constant__ RadauParams P, Parked<NY>* __restrict__ st,
+                             unsigned short* __restrict__ tag, long long M, const double* __restrict__ htry) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    Parked<NY>& p = st[m];
+    if (p.flags & PF_FINISHED) {
+      tag[m] = 0;
+      continue;
+    }
+    if (htry && htry[m] != p.h) {  // a trial step chosen by the caller: like radau.m:645-655
+      const double PosNeg = (p.tfinal - p.t0) >= 0 ? 1.0 : -1.0;
+      double h = PosNeg * fmin(fabs(htry[m]), fabs(p.tfinal - p.t0));
+      unsigned f = p.flags | PF_NEED_LU;
+      if ((p.t + h * 1.0001 - p.tfinal) * PosNeg >= 0) {
+        h = p.tfinal - p.t;
+        f |= PF_LAST;
+      } else {
+        f &= ~PF_LAST;
+      }
+      p.h = h;
+      p.flags = f;
+    }
+    tag[m] = regime_key(p.NbrStg, p.h, p.Newt);
+  }
+}
+
+template <int NY>
+__global__ void state_read_kernel(const Parked<NY>* __restrict__ st, long long M, double* __restrict__ y,
+                                  double* __restrict__ t, double* __restrict__ hnext, double* __restrict__ hdid,
+                                  int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
+                                  int* __restrict__ done) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const Parked<NY>& p = st[m];
+#pragma unroll
+    for (int i = 0; i < NY; i++) y[m * NY + i] = p.y[i];
+    t[m] = p.t;
+    hnext[m] = p.h;
+    hdid[m] = p.h_old;
+    res[m] = p.res;
+#pragma unroll
+    for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)p.st[k];
+    if (nstg) nstg[m] = p.NbrStg;
+    if (done) done[m] = (p.flags & PF_FINISHED) ? 1 : 0;
+  }
+}
+
+template <class Ham>
+int state_step(Handle* H, EpochWS& ws, const double* htry, cudaStream_t st) {
+  constexpr int NY = Ham::NV;
+  const long long M = ws.M;
+  if (M <= 0) return 0;
+  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
+  rearm_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>(H->P, (Parked<NY>*)ws.parked, ws.tag, M, htry);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  const OutArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const DenseArgs nod{2, nullptr, nullptr, nullptr};
+  const bool var = H->P.MinNbrStg != H->P.MaxNbrStg;
+  // one ACCEPTED step per live trajectory: no pass budget, stop right after the accept
+  return var ? run_epochs<Ham, true>(H, ws, 1 << 30, 1, none, nullptr, nod, st)
+             : run_epochs<Ham, false>(H, ws, 1 << 30, 1, none, nullptr, nod, st);
+}
+
+template <class Ham>
+int state_read(Handle* H, EpochWS& ws, double* y, double* t, double* hnext, double* hdid, int* res, long long* stats,
+               int* nstg, int* done, cudaStream_t st) {
+  constexpr int NY = Ham::NV;
+  const long long M = ws.M;
+  if (M <= 0) return 0;
+  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
+  state_read_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>((const Parked<NY>*)ws.parked, M, y, t, hnext, hdid, res,
+                                                          stats, nstg, done);
+  JB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -444,10 +567,14 @@ struct HamOps {
                long long*, const DenseArgs&, cudaStream_t);
   int (*dyns)(Handle*, const double*, long long, double*, cudaStream_t);
   int (*jac)(Handle*, const double*, long long, double*, cudaStream_t);
+  int (*st_init)(Handle*, EpochWS&, const double*, const double*, int, long long, cudaStream_t);
+  int (*st_step)(Handle*, EpochWS&, const double*, cudaStream_t);
+  int (*st_read)(Handle*, EpochWS&, double*, double*, double*, double*, int*, long long*, int*, int*, cudaStream_t);
 };
 template <class Ham>
 HamOps make_ops() {
-  return HamOps{Ham::NV, Ham::NPAR, &dispatch_order<Ham>, &launch_dyns<Ham>, &launch_jac<Ham>};
+  return HamOps{Ham::NV,           Ham::NPAR,         &dispatch_order<Ham>, &launch_dyns<Ham>,
+                &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>};
 }
 
 }  // namespace jb

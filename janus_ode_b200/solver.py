@@ -214,6 +214,90 @@ class RadauTe:
         return self.res
 
 
+class RadauState:
+    """State object of the incremental protocol, shaped like the reference's SeulexState(y, x, atol, rtol,
+    KMAXX, alpha, ft) (src/python/seulext.py:8-148): y [M,Ny], x [M] (time), ft (final time, scalar or [M]),
+    atol / rtol.  After each step: y, x, hdid (step taken), hnext (proposed next step), done [M] bool,
+    res [M], stats.  The integrator's internal memory (collocation polynomial, Jacobian, flags, counters)
+    stays parked on the device."""
+
+    def __init__(self, y, x, atol=1.0e-6, rtol=1.0e-3, ft=None):
+        if ft is None:
+            raise ValueError("ft (final time) is required")
+        if not y.is_cuda:
+            raise _lib.JanusB200Error("RadauState lives on a CUDA device (no CPU fallback)")
+        self.y = y.contiguous()
+        self.x = x.to(y).contiguous().reshape(-1)
+        self.ft = torch.as_tensor(ft, dtype=torch.float64, device=y.device).expand(self.x.shape).contiguous()
+        self.atol, self.rtol = atol, rtol
+        self.M, self.D = y.shape
+        self.hnext = torch.zeros_like(self.x)
+        self.hdid = torch.zeros_like(self.x)
+        self.done = torch.zeros(self.M, dtype=torch.bool, device=y.device)
+        self.res = torch.zeros(self.M, dtype=torch.int32, device=y.device)
+        self.stats = None
+        self.nstg = None
+        self._native = None
+        self._owner = None
+
+    def __del__(self):
+        try:
+            if self._native is not None:
+                self._owner.L.jb200_state_destroy(self._native)
+                self._native = None
+        except Exception:
+            pass
+
+
+class RadauT:
+    """Stepper object of the incremental protocol: `state = RadauT(options).step(htry, dyns, ft, state)` in a
+    loop `htry = state.hnext` until `state.done.all()`, like SeulexT.step (src/python/seulext.py:158-581,
+    driver src/python/seulex_dual_example_vdp.py:136-175).  Every call advances each unfinished trajectory
+    by exactly one accepted Radau step; looping reproduces RadauTe.solve() bit for bit."""
+
+    def __init__(self, options: OptionsTe | None = None):
+        self.options = options
+
+    def step(self, htry, dyns, ft, state: RadauState):
+        if not isinstance(dyns, HamiltonianSystem):
+            raise TypeError("dyns must be a janus_ode_b200.HamiltonianSystem")
+        dev = state.y.device
+        if state._native is None:
+            op = self.options or OptionsTe(RelTol=state.rtol, AbsTol=state.atol)
+            if htry is not None:
+                import copy
+                op = copy.copy(op)
+                op.InitialStep = float(torch.as_tensor(htry).reshape(-1)[0])   # first trial step, like step(htry, ...)
+            with torch.cuda.device(dev):
+                H = _get_handle(dyns.hamiltonian, op, dyns.costate_sign, dev)
+                tspan = torch.stack([state.x, torch.as_tensor(ft, dtype=torch.float64, device=dev).expand_as(state.x)], 1).contiguous()
+                if bool((tspan[:, 1] == tspan[:, 0]).any()):
+                    raise ValueError("Time vector must be strictly monotonic")
+                nat = C.c_void_p()
+                _lib.check_h(H, H.L.jb200_state_create(H.h, _ptr(state.y), _ptr(tspan), state.M, C.byref(nat), _stream_ptr(dev)))
+            state._native, state._owner = nat, H
+            htry = None                                   # the state starts with InitialStep = htry
+        H = state._owner
+        ht = None
+        if htry is not None:
+            ht = torch.as_tensor(htry, dtype=torch.float64, device=dev).expand_as(state.x).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check_h(H, H.L.jb200_state_step(state._native, _ptr(ht), _stream_ptr(dev)))
+            M, ny = state.M, state.D
+            y = torch.empty(M, ny, dtype=torch.float64, device=dev)
+            t = torch.empty(M, dtype=torch.float64, device=dev)
+            hn, hd = torch.empty_like(t), torch.empty_like(t)
+            res = torch.empty(M, dtype=torch.int32, device=dev)
+            st = torch.empty(M, 8, dtype=torch.int64, device=dev)
+            ns = torch.empty(M, dtype=torch.int32, device=dev)
+            dn = torch.empty(M, dtype=torch.int32, device=dev)
+            _lib.check_h(H, H.L.jb200_state_read(state._native, _ptr(y), _ptr(t), _ptr(hn), _ptr(hd), _ptr(res), _ptr(st),
+                                                 _ptr(ns), _ptr(dn), _stream_ptr(dev)))
+        state.y, state.x, state.hnext, state.hdid = y, t, hn, hd
+        state.res, state.stats, state.nstg, state.done = res, StatsTe.from_tensor(st), ns, dn.bool()
+        return state
+
+
 def lu_solve(A, b):
     """Batched small dense LU factor + solve on CUDA tensors, A [M,n,n], b [M,n], n in {2,3,4};
     real float64 or complex128 (the torch::linalg_lu_factor / lu_solve role on the Radau path,

@@ -98,6 +98,9 @@ int hostsim_solve(int ham_id, const RadauParams* P, const double* y0, const doub
 template <class Ham>
 static void run_epochs(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out,
                        double* t_out, double* h_out, int* res, long long* stats, int* nstg, int K) {
+  const bool stop = K < 0;   // K < 0: incremental step() protocol, one accepted step per sweep
+  if (stop) K = 1 << 30;
+  bool stepped = false;
   constexpr int NY = Ham::NV;
   std::vector<Parked<NY>> st(M);
   for (long long m = 0; m < M; m++) {
@@ -114,10 +117,10 @@ static void run_epochs(const RadauParams& P, const double* y0, const double* tsp
       double t0;
       bool hd, fin;
       switch (p.NbrStg) {
-        case 1: { Traj<NY, 1> T; unpark<NY, 1>(p, T, t0, hd); fin = run_epoch<Ham, NY, 1>(T, P, hd, K); park<NY, 1>(T, t0, hd, fin, p); } break;
-        case 3: { Traj<NY, 3> T; unpark<NY, 3>(p, T, t0, hd); fin = run_epoch<Ham, NY, 3>(T, P, hd, K); park<NY, 3>(T, t0, hd, fin, p); } break;
-        case 5: { Traj<NY, 5> T; unpark<NY, 5>(p, T, t0, hd); fin = run_epoch<Ham, NY, 5>(T, P, hd, K); park<NY, 5>(T, t0, hd, fin, p); } break;
-        default: { Traj<NY, 7> T; unpark<NY, 7>(p, T, t0, hd); fin = run_epoch<Ham, NY, 7>(T, P, hd, K); park<NY, 7>(T, t0, hd, fin, p); } break;
+        case 1: { Traj<NY, 1> T; unpark<NY, 1>(p, T, t0, hd); fin = run_epoch<Ham, NY, 1>(T, P, hd, K, nullptr, stop, &stepped); park<NY, 1>(T, t0, hd, fin, p); } break;
+        case 3: { Traj<NY, 3> T; unpark<NY, 3>(p, T, t0, hd); fin = run_epoch<Ham, NY, 3>(T, P, hd, K, nullptr, stop, &stepped); park<NY, 3>(T, t0, hd, fin, p); } break;
+        case 5: { Traj<NY, 5> T; unpark<NY, 5>(p, T, t0, hd); fin = run_epoch<Ham, NY, 5>(T, P, hd, K, nullptr, stop, &stepped); park<NY, 5>(T, t0, hd, fin, p); } break;
+        default: { Traj<NY, 7> T; unpark<NY, 7>(p, T, t0, hd); fin = run_epoch<Ham, NY, 7>(T, P, hd, K, nullptr, stop, &stepped); park<NY, 7>(T, t0, hd, fin, p); } break;
       }
     }
     if (!active) break;

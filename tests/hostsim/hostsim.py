@@ -60,6 +60,6 @@ def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
     args = [C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
             res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
             nstg.ctypes.data_as(C.POINTER(C.c_int))]
-    rc = lib.hostsim_solve_epochs(*args, C.c_int(epochs_K)) if epochs_K > 0 else lib.hostsim_solve(*args)
+    rc = lib.hostsim_solve_epochs(*args, C.c_int(epochs_K)) if epochs_K != 0 else lib.hostsim_solve(*args)
     assert rc == 0
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, **out)

@@ -64,7 +64,7 @@ def test_core_equals_mirror_other_orders_and_failures():
     assert np.array_equal(a["res"], b["res"]) and np.array_equal(a["stats"], b["stats"])
 
 
-@pytest.mark.parametrize("K", [1, 5, 24])
+@pytest.mark.parametrize("K", [1, 5, 24, -1])   # -1: step() protocol, stop after every accepted step
 def test_epoch_scheme_is_bit_identical(K):
     """variable-order path: park / regroup by stage count / resume (LU recomputed) every K attempted
     steps gives the same bits as the uninterrupted integration."""
