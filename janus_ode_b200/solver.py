@@ -267,7 +267,7 @@ class RadauT:
             if htry is not None:
                 import copy
                 op = copy.copy(op)
-                op.InitialStep = float(torch.as_tensor(htry).reshape(-1)[0])   # first trial step, like step(htry, ...)
+                op.InitialStep = float(torch.as_tensor(htry, dtype=torch.float64).reshape(-1)[0])   # first trial step, like step(htry, ...)
             with torch.cuda.device(dev):
                 H = _get_handle(dyns.hamiltonian, op, dyns.costate_sign, dev)
                 tspan = torch.stack([state.x, torch.as_tensor(ft, dtype=torch.float64, device=dev).expand_as(state.x)], 1).contiguous()
