@@ -254,7 +254,7 @@ def run_ours(a):
                        "api": "RadauTe(dyn, dyn.jacobian, tspan_cpu_pinned, y0_cpu_pinned, opts).solve() -> jb200_solve_host"},
                "gpu_launches": launches,
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "frac": achieved / peak if peak else None, "traffic": _traffic(a),
                             "peak_source": "DFMA probe jb200_fp64_peak on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry)",
                             "algorithmic_flops_per_launch": flops / world,
                             "flops_per_accepted_step": flops / max(acc, 1),
@@ -273,6 +273,17 @@ def run_ours(a):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _traffic(a):
+    """DRAM bytes of one solve from the committed ncu launch list (profiles/), only for the profiled size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if a.M != 1 << 20:
+            return None
+        return t["fixed_bytes_per_solve"] if a.fixed_order else t["default_bytes_per_solve"]
+    except Exception:
+        return None
 
 
 def _hbm_peak():
