@@ -329,7 +329,12 @@ struct Handle {
 template <class Ham, int SM, bool VAR>
 int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                         double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+#ifdef JB_SLIM   // slim plugin builds (large user Hamiltonians): no dense-output kernel variants
+  if (dense.tout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
+  auto kern = radau_kernel<Ham, SM, VAR, false>;
+#else
   auto kern = dense.tout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
+#endif
   int bps = 0;
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
   if (bps < 1) bps = 1;
@@ -362,7 +367,12 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, int base, int count, int max_pas
     st = H->aux[used - 1];
     JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
   }
+#ifdef JB_SLIM
+  if (dense.tout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
+  auto kern = epoch_kernel<Ham, S, VAR, false>;
+#else
   auto kern = dense.tout ? epoch_kernel<Ham, S, VAR, true> : epoch_kernel<Ham, S, VAR, false>;
+#endif
   constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
@@ -509,10 +519,14 @@ int state_step(Handle* H, EpochWS& ws, const double* htry, cudaStream_t st) {
   H->launches = 1;
   const OutArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const DenseArgs nod{2, nullptr, nullptr, nullptr};
-  const bool var = H->P.MinNbrStg != H->P.MaxNbrStg;
   // one ACCEPTED step per live trajectory: no pass budget, stop right after the accept
+#ifdef JB_SLIM
+  return run_epochs<Ham, true>(H, ws, 1 << 30, 1, none, nullptr, nod, st);
+#else
+  const bool var = H->P.MinNbrStg != H->P.MaxNbrStg;
   return var ? run_epochs<Ham, true>(H, ws, 1 << 30, 1, none, nullptr, nod, st)
              : run_epochs<Ham, false>(H, ws, 1 << 30, 1, none, nullptr, nod, st);
+#endif
 }
 
 template <class Ham>
@@ -532,6 +546,11 @@ template <class Ham>
 int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                           double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
   const RadauParams& P = H->P;
+#ifdef JB_SLIM   // only the fused 3-stage kernel and the VAR epoch kernels exist (VAR = true also covers Min == Max)
+  if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
+    return launch_radau<Ham, 3, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+  return solve_var<Ham, true>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+#else
   if (P.MinNbrStg == P.MaxNbrStg && H->fixed_epochs)   // fixed order through the regime-sorted epochs
     return solve_var<Ham, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 3)
@@ -543,6 +562,7 @@ int dispatch_order(Handle* H, const double* y0, const double* tspan, long long M
   if (P.MinNbrStg == P.MaxNbrStg && P.MaxNbrStg == 7)
     return launch_radau<Ham, 7, false>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
   return solve_var<Ham>(H, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, st);
+#endif
 }
 
 template <class Ham>
