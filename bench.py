@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--fixed-order", action="store_true", help="fixed 3 stages instead of the default 3/5/7")
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-kind", default="c", choices=["c", "batched"],
+                    help="reference arm: 'c' = scalar C restatement, OpenMP over trajectories (strong bar, default); "
+                         "'batched' = masked-tensor torch restatement with autograd Hamiltonian (the reference's own op "
+                         "structure, BASELINE.md section 3; ~1 min per step)")
     return ap.parse_args()
 
 
@@ -117,9 +121,48 @@ def cpu_reference_run(a, rows, threads=0):
     return acc / dt, dt, acc, cores
 
 
+def batched_reference_run(a, rows):
+    """masked-tensor torch restatement (oracle/radau_batched.py) with the autograd Hamiltonian adaptor: the op
+    structure of the reference's RadauTe + evalDyns/evalJac, all host threads."""
+    import torch
+    from janus_ode_b200 import configs
+    from oracle import ham, radau_batched
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = configs.c2_vdp(M=a.M * a.gpus, fixed_order=a.fixed_order, lo=0, hi=rows)
+    ode, jac = radau_batched.hamiltonian_callbacks(ham.H_vdp(cfg["ham"].params[0]), None, None, cfg["sign"])
+    t0 = time.perf_counter()
+    r = radau_batched.RadauBatched(ode, jac, cfg["tspan"], cfg["y0"], cfg["options"])
+    res = r.solve()
+    dt = time.perf_counter() - t0
+    assert bool((res == 0).all())
+    acc = int(r.stats[:, 5].sum())
+    return acc / dt, dt, acc, cores
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if a.ref_kind == "batched":
+        rows = a.cpu_sample or 16384
+        rates, times = [], []
+        for _ in range(max(a.steps, 1)):
+            r, dt, acc, cores = batched_reference_run(a, rows)
+            rates.append(r)
+            times.append(dt)
+        value = sum(rates) / len(rates)
+        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+               "warmup": 0, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(a), "sample": f"first {rows} rows of the same seeded batch"},
+               "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"first {rows} rows; masked-tensor torch restatement of RadauTe with the autograd "
+                                          f"Hamiltonian adaptor (oracle/radau_batched.py + oracle/ham.py): the reference's op "
+                                          f"structure; the reference itself cannot be built here (SURVEY.md 8c)"},
+               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out), flush=True)
         return
     from oracle import c_oracle
     c_oracle.build()
