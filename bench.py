@@ -14,9 +14,11 @@ ranks / max-over-ranks device time with inputs resident in HBM; `e2e` = the same
 public API with pinned HOST tensors (jb200_solve_host: H2D + solve + D2H inside the timed call).
 `roofline` = algorithmic FLOPs (SURVEY.md 8d model, counted per trajectory inside the kernel) over
 the CUDA-event kernel time, against the FP64 DFMA peak measured on this GPU in the same run
-(MEASURED_PEAKS.json has no FP64 figure).  `cpu_baseline` / `--impl reference` = the C restatement
-of the reference algorithm (oracle/c, reference arithmetic, all host threads) on a bounded sample
-of the same rows -- the reference itself cannot be built in this environment.
+(MEASURED_PEAKS.json has no FP64 figure).  `cpu_baseline` / `--impl reference` = the masked-tensor
+torch restatement of the reference's RadauTe + autograd Hamiltonian adaptor (oracle/radau_batched.py:
+the reference's own op structure, all host threads) on a bounded sample of the same rows -- the
+reference itself cannot be built in this environment; `cpu_baseline_strong` = the scalar
+C restatement with OpenMP over trajectories (oracle/c), a much faster CPU design than the reference's.
 """
 import argparse
 import json
