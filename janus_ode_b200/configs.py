@@ -6,7 +6,7 @@ import math
 
 import torch
 
-from .hamiltonians import Harmonic, VanDerPol, VdpPmp
+from .hamiltonians import Harmonic, MlpHamiltonian, VanDerPol, VdpPmp
 from .options import OptionsTe
 
 
@@ -41,6 +41,20 @@ def c2_vdp(M=1 << 20, mu=1000.0, seed=0, fixed_order=False, lo=0, hi=None):
     if fixed_order:
         op.MinNbrStg = op.MaxNbrStg = 3
     return dict(ham=VanDerPol(mu), sign=+1, y0=y0, tspan=tspan, options=op)
+
+
+def c4_mlp(M=1 << 20, seed=0, fixed_order=False, lo=0, hi=None):
+    """C4: MLP Hamiltonian 16 -> 128 -> 128 -> 128 -> 1 (tanh), N = 8, canonical sign, y0 ~ 0.5 N(0,1),
+    t in [0,1], rtol 1e-6, atol 1e-9.  Rows lo:hi of the seeded global batch."""
+    g = torch.Generator().manual_seed(seed + 1)
+    y0 = 0.5 * torch.randn(M, 16, generator=g, dtype=torch.float64)
+    hi = M if hi is None else hi
+    y0 = y0[lo:hi].contiguous()
+    tspan = torch.tensor([0.0, 1.0], dtype=torch.float64).repeat(hi - lo, 1)
+    op = OptionsTe(RelTol=1e-6, AbsTol=1e-9, MaxNbrStep=1000000)
+    if fixed_order:
+        op.MinNbrStg = op.MaxNbrStg = 3
+    return dict(ham=MlpHamiltonian(8, 128, seed), sign=-1, y0=y0, tspan=tspan, options=op)
 
 
 def c3_pmp(M=1 << 18, control="bangbang", seed=0, fixed_order=False, tfinal=None):

@@ -92,7 +92,7 @@ static const HamOps* ham_ops(int ham_id) { return ham_id == JB200_HAM_USER ? &jb
 static const HamOps jb_ops_vdp = make_ops<HamVdp>();
 static const HamOps* ham_ops(int ham_id) { return ham_id == JB200_HAM_VDP ? &jb_ops_vdp : nullptr; }
 #else
-extern const HamOps jb_ops_harmonic, jb_ops_vdp, jb_ops_vdp_pmp_smooth, jb_ops_vdp_pmp_bang, jb_ops_vdp_aug_bang;
+extern const HamOps jb_ops_harmonic, jb_ops_vdp, jb_ops_vdp_pmp_smooth, jb_ops_vdp_pmp_bang, jb_ops_vdp_aug_bang, jb_ops_mlp;
 static const HamOps* ham_ops(int ham_id) {
   switch (ham_id) {
     case JB200_HAM_HARMONIC: return &jb_ops_harmonic;
@@ -100,6 +100,7 @@ static const HamOps* ham_ops(int ham_id) {
     case JB200_HAM_VDP_PMP_SMOOTH: return &jb_ops_vdp_pmp_smooth;
     case JB200_HAM_VDP_PMP_BANG: return &jb_ops_vdp_pmp_bang;
     case JB200_HAM_VDP_AUG_BANG: return &jb_ops_vdp_aug_bang;
+    case JB200_HAM_MLP: return &jb_ops_mlp;
     default: return nullptr;
   }
 }
@@ -287,6 +288,13 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
     delete H;
     return fail(JB200_ECUDA, std::string("jb200_create: ") + cudaGetErrorString(e));
   }
+  if (ops->create) {
+    const int rc2 = ops->create(H, ham_params, n_ham_params);
+    if (rc2) {
+      jb200_destroy(H);
+      return rc2;
+    }
+  }
   if (const char* ep = std::getenv("JB200_EPOCH_PASSES")) H->epoch_passes = std::max(1, atoi(ep));
   if (const char* fe = std::getenv("JB200_FIXED_EPOCHS")) H->fixed_epochs = atoi(fe) != 0;
   *handle = H;
@@ -296,6 +304,8 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
 void jb200_destroy(void* handle) {
   Handle* H = (Handle*)handle;
   if (!H) return;
+  if (const HamOps* ops = ham_ops(H->ham_id))
+    if (ops->destroy) ops->destroy(H);
   cudaFree(H->d_counter);
   ws_free(H->ws);
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);

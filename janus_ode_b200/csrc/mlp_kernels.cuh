@@ -1,0 +1,456 @@
+// Stage evaluation for an MLP-parameterised Hamiltonian (config 4 of BASELINE.json):
+//   H(v) = W4 . tanh(W3 tanh(W2 tanh(W1 v + b1) + b2) + b3) + b4,   v = [x ; p] (16 inputs),
+//   width 128, fp64.
+// Replaces, for this Hamiltonian, the reference's autograd ladders
+//   evalDyns  /root/reference/src/cpp/janus_ode_common.hpp:2161-2186  (3 forwards + 2 backwards of H)
+//   evalJac   /root/reference/src/cpp/janus_ode_common.hpp:2220-2256  (5 forwards + 4N row backwards)
+// by two tile kernels in which the batch dimension makes every layer a dense GEMM:
+//   mlp_grad_kernel  64 (trajectory, stage) rows per CTA: forward (3 GEMMs + tanh), reverse sweep
+//                    (2 transposed GEMMs + the 128x16 output product) -> ydot = [sg dH/dx ; dH/dp]
+//   mlp_hess_kernel  4 trajectories x 16 tangent directions per CTA: forward-over-reverse (tangent
+//                    forward 2 GEMMs, tangent reverse 2 GEMMs + output product) -> the 16x16 Jacobian
+// One CTA = 128 threads = one warp per SM sub-partition, each thread owns an 8x8 register tile of
+// the 64x128 layer output (64 independent DFMA chains: the FP64 pipe is the only bound); the
+// activations of the tile stay in shared memory ([feature][row], 3 x 64 KB) from the first layer
+// to the last, weights stream from L2 in 8-row chunks through a cp.async double buffer.
+//
+// ARITHMETIC CONTRACT (mirrored by oracle/c/radau_oracle.c mlp_eval_mirror): every dot product is
+// ONE fma chain in increasing index order, seeded with the bias (forward) or 0.0 (transposed);
+// tanh = det_tanh; 1 - a^2 = fma(-a, a, 1).  The register tiling changes which thread owns an
+// output, never the order of its sum, so results are bit-identical to the scalar mirror.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "detmath.cuh"
+#include "mlp_common.cuh"
+
+namespace jb {
+namespace mlp {
+
+constexpr int TR = 64;        // rows per CTA tile
+constexpr int KC = 8;         // weight rows per cp.async chunk
+constexpr int THREADS = 128;
+constexpr int ACT_WORDS = WD * TR;                                      // one activation buffer
+constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 208 KB
+
+// device-resident weights of one Hamiltonian (both orientations of every matrix, k-major for the
+// GEMM that consumes it)
+struct Weights {
+  const double* W1t;   // [16][128]   W1t[k][c] = W1[c][k]      forward layer 1
+  const double* W2t;   // [128][128]  W2t[k][c] = W2[c][k]      forward layer 2
+  const double* W3t;   // [128][128]
+  const double* W3;    // [128][128]  natural (out-major): reverse through layer 3
+  const double* W2;    // [128][128]
+  const double* W1;    // [128][16]   natural: output product
+  const double* b1;    // [128]
+  const double* b2;
+  const double* b3;
+  const double* W4;    // [128]
+};
+
+// thread -> register tile: lane%8 picks the row pair, warp*4 + lane/8 the column pair
+struct TileMap {
+  int r0, c0;
+  __device__ TileMap() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    r0 = (lane & 7) * 2;
+    c0 = (warp * 4 + (lane >> 3)) * 2;
+  }
+  __device__ __forceinline__ int row(int j, int e) const { return r0 + 16 * j + e; }   // j < 4, e < 2
+  __device__ __forceinline__ int col(int j, int e) const { return c0 + 32 * j + e; }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// acc[ri][ci] += sum_k A[k][row(ri)] * B[k][col(ci)], k = 0..K-1 in order (one fma chain each).
+// A: shared [K][TR]; B: global [K][WD] (row-major, 16-byte aligned); wbuf: shared [2][KC][WD].
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const double* __restrict__ B, int K,
+                                          double* __restrict__ wbuf, const TileMap& tm, double (&acc)[8][8]) {
+  const int nchunks = K / KC;
+  auto issue = [&](int ch) {
+    const double* src = B + (size_t)ch * KC * WD;
+    double* dst = wbuf + (ch & 1) * KC * WD;
+#pragma unroll
+    for (int t = 0; t < (KC * WD / 2) / THREADS; t++) {
+      const int o = (t * THREADS + threadIdx.x) * 2;
+      cp_async16(dst + o, src + o);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int ch = 0; ch < nchunks; ch++) {
+    if (ch + 1 < nchunks) {
+      issue(ch + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* wb = wbuf + (ch & 1) * KC * WD;
+    const double* Ak = A + (size_t)ch * KC * TR;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+      double a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double2 av = *reinterpret_cast<const double2*>(Ak + kk * TR + tm.r0 + 16 * j);
+        a[2 * j] = av.x;
+        a[2 * j + 1] = av.y;
+        const double2 bv = *reinterpret_cast<const double2*>(wb + kk * WD + tm.c0 + 32 * j);
+        b[2 * j] = bv.x;
+        b[2 * j + 1] = bv.y;
+      }
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+        for (int ci = 0; ci < 8; ci++) acc[ri][ci] = fma(b[ci], a[ri], acc[ri][ci]);
+    }
+    __syncthreads();   // everyone is done with this chunk before it is overwritten
+  }
+}
+
+// out[row][j] = sum_i W1[i][j] * D[i][row], j < 16: 64 x 16 outputs, 8 per thread
+// (thread -> row = tid % 64, columns (tid / 64) * 8 ..).  W1 (natural [128][16]) is staged in wbuf.
+__device__ __forceinline__ void output_product(const double* __restrict__ D, const double* __restrict__ W1g,
+                                               double* __restrict__ wbuf, double (&g)[8]) {
+  for (int o = threadIdx.x; o < WD * NV; o += THREADS) wbuf[o] = W1g[o];
+  __syncthreads();
+  const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+#pragma unroll
+  for (int c = 0; c < 8; c++) g[c] = 0.0;
+  for (int i = 0; i < WD; i++) {
+    const double d = D[i * TR + r];
+#pragma unroll
+    for (int c = 0; c < 8; c++) g[c] = fma(wbuf[i * NV + cb + c], d, g[c]);
+  }
+  __syncthreads();
+}
+
+// store the 8x8 register tile raw into a [feature][row] buffer
+__device__ __forceinline__ void store_tile(double* __restrict__ A, const TileMap& tm, const double (&acc)[8][8]) {
+#pragma unroll
+  for (int ci = 0; ci < 8; ci++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(A + tm.col(ci >> 1, ci & 1) * TR + tm.r0 + 16 * j) =
+          make_double2(acc[2 * j][ci], acc[2 * j + 1][ci]);
+}
+
+// a = tanh(a) over a whole buffer: a ROLLED loop (one copy of det_tanh in the instruction stream
+// instead of 64 per layer), 4 independent elements in flight per thread
+__device__ __forceinline__ void tanh_buffer(double* __restrict__ A) {
+#pragma unroll 1
+  for (int o = threadIdx.x; o < ACT_WORDS; o += 4 * THREADS) {
+    const double t0 = det_tanh(A[o]), t1 = det_tanh(A[o + THREADS]), t2 = det_tanh(A[o + 2 * THREADS]),
+                 t3 = det_tanh(A[o + 3 * THREADS]);
+    A[o] = t0;
+    A[o + THREADS] = t1;
+    A[o + 2 * THREADS] = t2;
+    A[o + 3 * THREADS] = t3;
+  }
+}
+
+// Where a row of the gradient kernel comes from / goes to.  Element e of trajectory m of an array
+// lives at base[m * sr + e * se] (SoA state: sr = 1, se = M;  row-major API buffers: sr = 16, se = 1).
+struct GradIO {
+  const int* rows;         // [n_rows] row descriptors: trajectory * 8 + stage  (nullptr: row r = trajectory r, stage 0)
+  const int* n_rows_dev;   // device count (nullptr: use n_rows)
+  int n_rows;
+  const double* y;         // state
+  long long y_sr, y_se;
+  const double* add;       // optional addend: add[(stage * 16 + e) * add_se + m * add_sr]  (stage increments z_q)
+  long long add_sr, add_se;
+  const double* add_scalar;  // optional scalar added to every component ([m]; Estrad's y + err)
+  double* out;             // out[(stage * 16 + e) * out_se + m * out_sr]
+  long long out_sr, out_se;
+  double* act;             // optional [m][5][128] saved activations a1, a2, a3, q1, q2 (for the Jacobian)
+  double sign;             // costate sign: ydot = [sign dH/dx ; dH/dp]
+};
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, const GradIO io) {
+  extern __shared__ __align__(16) double smem[];
+  double* A0 = smem;
+  double* A1 = A0 + ACT_WORDS;
+  double* A2 = A1 + ACT_WORDS;
+  double* wbuf = A2 + ACT_WORDS;
+  __shared__ int s_traj[TR], s_stage[TR];
+  const int n_rows = io.n_rows_dev ? *io.n_rows_dev : io.n_rows;
+  const TileMap tm;
+  for (int tile = blockIdx.x; (long long)tile * TR < n_rows; tile += gridDim.x) {
+    const int base = tile * TR;
+    if (threadIdx.x < TR) {
+      const int r = base + threadIdx.x;
+      int d = -1;
+      if (r < n_rows) d = io.rows ? io.rows[r] : r * 8;
+      s_traj[threadIdx.x] = d < 0 ? -1 : d >> 3;
+      s_stage[threadIdx.x] = d < 0 ? 0 : d & 7;
+    }
+    __syncthreads();
+    // v = [x ; p] of every row -> A2[k][row] (k < 16); state order is y = [p ; x]
+    for (int o = threadIdx.x; o < NV * TR; o += THREADS) {
+      const int r = o & (TR - 1), k = o / TR;
+      const int m = s_traj[r];
+      double v = 0.0;
+      if (m >= 0) {
+        const int e = (k + NH) & (NV - 1);
+        v = io.y[(size_t)m * io.y_sr + (size_t)e * io.y_se];
+        if (io.add) v = v + io.add[(size_t)(s_stage[r] * NV + e) * io.add_se + (size_t)m * io.add_sr];
+        if (io.add_scalar) v = v + io.add_scalar[m];
+      }
+      A2[k * TR + r] = v;
+    }
+    __syncthreads();
+    double acc[8][8];
+    // ---- layer 1: a1 = tanh(W1 v + b1) -> A0
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const double b = Wt.b1[tm.col(ci >> 1, ci & 1)];
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+    }
+    gemm_tile(A2, Wt.W1t, NV, wbuf, tm, acc);
+    store_tile(A0, tm, acc);
+    __syncthreads();
+    tanh_buffer(A0);
+    __syncthreads();
+    // ---- layer 2 -> A1
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const double b = Wt.b2[tm.col(ci >> 1, ci & 1)];
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+    }
+    gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
+    store_tile(A1, tm, acc);
+    __syncthreads();
+    tanh_buffer(A1);
+    __syncthreads();
+    // ---- layer 3: a3 = tanh(.), d3 = W4 (1 - a3^2) -> A2
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const double b = Wt.b3[tm.col(ci >> 1, ci & 1)];
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+    }
+    gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
+    store_tile(A2, tm, acc);
+    __syncthreads();
+    tanh_buffer(A2);
+    __syncthreads();
+    for (int o = threadIdx.x; o < ACT_WORDS; o += THREADS) {
+      const int r = o & (TR - 1), c = o / TR;
+      const double a3 = A2[o];
+      if (io.act && s_traj[r] >= 0) io.act[((size_t)s_traj[r] * 5 + 2) * WD + c] = a3;
+      A2[o] = Wt.W4[c] * fma(-a3, a3, 1.0);
+    }
+    __syncthreads();
+    // ---- reverse through layer 3: q2 = W3^T d3, d2 = q2 (1 - a2^2) -> A1 (in place)
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++) {
+        const int r = tm.row(ri >> 1, ri & 1);
+        const double a2 = A1[c * TR + r], q2 = acc[ri][ci];
+        if (io.act && s_traj[r] >= 0) {
+          io.act[((size_t)s_traj[r] * 5 + 1) * WD + c] = a2;
+          io.act[((size_t)s_traj[r] * 5 + 4) * WD + c] = q2;
+        }
+        A1[c * TR + r] = q2 * fma(-a2, a2, 1.0);
+      }
+    }
+    __syncthreads();
+    // ---- reverse through layer 2: q1 = W2^T d2, d1 = q1 (1 - a1^2) -> A0 (in place)
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int ri = 0; ri < 8; ri++) {
+        const int r = tm.row(ri >> 1, ri & 1);
+        const double a1 = A0[c * TR + r], q1 = acc[ri][ci];
+        if (io.act && s_traj[r] >= 0) {
+          io.act[((size_t)s_traj[r] * 5 + 0) * WD + c] = a1;
+          io.act[((size_t)s_traj[r] * 5 + 3) * WD + c] = q1;
+        }
+        A0[c * TR + r] = q1 * fma(-a1, a1, 1.0);
+      }
+    }
+    __syncthreads();
+    // ---- g = W1^T d1 ; ydot = [sign dH/dx ; dH/dp]
+    double g[8];
+    output_product(A0, Wt.W1, wbuf, g);
+    {
+      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+      const int m = s_traj[r];
+      if (m >= 0) {
+        const int st = s_stage[r];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int e = cb + c;
+          const double v = (e < NH) ? io.sign * g[c] : g[c];
+          io.out[(size_t)(st * NV + e) * io.out_se + (size_t)m * io.out_sr] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Jacobian J = d ydot / d y (rows [pdot ; xdot], columns [p ; x]) of the trajectories in `list`,
+// from the activations saved by the gradient kernel at the same state.
+struct HessIO {
+  const int* list;         // [n] trajectory indices (nullptr: identity)
+  const int* n_dev;        // device count (nullptr: use n)
+  int n;
+  const double* act;       // [m][5][128]: a1, a2, a3, q1, q2
+  double* J;               // J[(r * 16 + c) * J_se + m * J_sr]
+  long long J_sr, J_se;
+  double sign;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, const HessIO io) {
+  extern __shared__ __align__(16) double smem[];
+  double* A0 = smem;
+  double* A1 = A0 + ACT_WORDS;
+  double* A2 = A1 + ACT_WORDS;
+  double* wbuf = A2 + ACT_WORDS;
+  __shared__ int s_traj[4];
+  const int n = io.n_dev ? *io.n_dev : io.n;
+  const TileMap tm;
+  for (int tile = blockIdx.x; (long long)tile * 4 < n; tile += gridDim.x) {
+    if (threadIdx.x < 4) {
+      const int q = tile * 4 + threadIdx.x;
+      s_traj[threadIdx.x] = q < n ? (io.list ? io.list[q] : q) : -1;
+    }
+    __syncthreads();
+    // rows of this thread: slot j (trajectory), tangent direction k = r0 + e
+    const double* actj[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) actj[j] = io.act + (size_t)(s_traj[j] < 0 ? s_traj[0] : s_traj[j]) * 5 * WD;
+    // ---- ta1[c][row] = (1 - a1^2) W1[c][k] -> A0
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double a1 = actj[j][0 * WD + c];
+        const double e1 = fma(-a1, a1, 1.0);
+        *reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 16 * j) =
+            make_double2(e1 * Wt.W1[c * NV + tm.r0], e1 * Wt.W1[c * NV + tm.r0 + 1]);
+      }
+    }
+    __syncthreads();
+    double acc[8][8];
+    // ---- ta2 = (1 - a2^2) (W2 ta1) -> A1
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double a2 = actj[j][1 * WD + c];
+        const double e2 = fma(-a2, a2, 1.0);
+        *reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 16 * j) = make_double2(e2 * acc[2 * j][ci], e2 * acc[2 * j + 1][ci]);
+      }
+    }
+    __syncthreads();
+    // ---- ta3 = (1 - a3^2) (W3 ta2);  td3 = W4 ((-2 a3) ta3) -> A2
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+      const double w4 = Wt.W4[c];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double a3 = actj[j][2 * WD + c];
+        const double e3 = fma(-a3, a3, 1.0), m3 = -2.0 * a3;
+        const double t0 = e3 * acc[2 * j][ci], t1 = e3 * acc[2 * j + 1][ci];
+        *reinterpret_cast<double2*>(A2 + c * TR + tm.r0 + 16 * j) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
+      }
+    }
+    __syncthreads();
+    // ---- td2 = (W3^T td3)(1 - a2^2) + q2 ((-2 a2) ta2) -> A1 (in place)
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double a2 = actj[j][1 * WD + c], q2 = actj[j][4 * WD + c];
+        const double e2 = fma(-a2, a2, 1.0), m2 = -2.0 * a2;
+        double2* p = reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 16 * j);
+        const double2 ta2 = *p;
+        *p = make_double2(fma(q2, m2 * ta2.x, acc[2 * j][ci] * e2), fma(q2, m2 * ta2.y, acc[2 * j + 1][ci] * e2));
+      }
+    }
+    __syncthreads();
+    // ---- td1 = (W2^T td2)(1 - a1^2) + q1 ((-2 a1) ta1) -> A0 (in place)
+#pragma unroll
+    for (int ri = 0; ri < 8; ri++)
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) {
+      const int c = tm.col(ci >> 1, ci & 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double a1 = actj[j][0 * WD + c], q1 = actj[j][3 * WD + c];
+        const double e1 = fma(-a1, a1, 1.0), m1 = -2.0 * a1;
+        double2* p = reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 16 * j);
+        const double2 ta1 = *p;
+        *p = make_double2(fma(q1, m1 * ta1.x, acc[2 * j][ci] * e1), fma(q1, m1 * ta1.y, acc[2 * j + 1][ci] * e1));
+      }
+    }
+    __syncthreads();
+    // ---- Hvv[jj][k] = sum_i W1[i][jj] td1[i][row(slot, k)];  J[r][c] = (r < N ? sign : 1) Hvv[r][vc(c)]
+    double g[8];
+    output_product(A0, Wt.W1, wbuf, g);
+    {
+      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+      const int slot = r >> 4, k = r & 15;
+      const int m = s_traj[slot];
+      if (m >= 0) {
+        const int cc = (k + NH) & (NV - 1);   // column of y whose v-index is k
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int jj = cb + c;
+          const double v = (jj < NH) ? io.sign * g[c] : g[c];
+          io.J[(size_t)(jj * NV + cc) * io.J_se + (size_t)m * io.J_sr] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mlp
+}  // namespace jb

@@ -324,6 +324,7 @@ struct Handle {
   long long* d_stats = nullptr;
   long long* d_work = nullptr;
   cudaStream_t own_stream = nullptr;
+  void* ext = nullptr;   // per-Hamiltonian context (MLP Hamiltonian: device weights + phase workspace, tu_mlp.cu)
 };
 
 template <class Ham, int SM, bool VAR>
@@ -590,6 +591,8 @@ struct HamOps {
   int (*st_init)(Handle*, EpochWS&, const double*, const double*, int, long long, cudaStream_t);
   int (*st_step)(Handle*, EpochWS&, const double*, cudaStream_t);
   int (*st_read)(Handle*, EpochWS&, double*, double*, double*, double*, int*, long long*, int*, int*, cudaStream_t);
+  int (*create)(Handle*, const double* par, int npar) = nullptr;   // optional: device-resident parameters
+  void (*destroy)(Handle*) = nullptr;
 };
 template <class Ham>
 HamOps make_ops() {

@@ -1,0 +1,345 @@
+// MLP-parameterised Hamiltonian (JB200_HAM_MLP, config 4 of BASELINE.json) behind the same C ABI:
+// host orchestration of the phase machine (mlp_phase.cuh) around the tile-GEMM stage evaluations
+// (mlp_kernels.cuh).  One pass = one attempted step of every active trajectory:
+//
+//   head_kernel  ->  [mlp_hess_kernel on the trajectories that need a Jacobian]  ->  prep_kernel
+//   repeat { mlp_grad_kernel on the (trajectory, stage) rows still iterating ; newton_kernel }
+//   [mlp_grad_kernel at y + err ; estrad_b_kernel]      (first-step retry of the error estimate)
+//   mlp_grad_kernel at the accepted points (saves the activations the next Jacobian needs) ; accept_b_kernel
+//
+// Converged / finished trajectories drop out of the row lists (active-set compaction), so the
+// GEMM tiles only ever hold rows that still need work.  The host reads 8 counters once per Newton
+// iteration (a few dozen 32-byte copies per solve); all state stays in HBM as structure of arrays.
+// parameters: [N = 8, width = 128, W1[128][16], b1[128], W2[128][128], b2, W3[128][128], b3, W4[128], b4]
+#include "solver_impl.cuh"
+#include "mlp_kernels.cuh"
+#include "mlp_phase.cuh"
+
+namespace jb {
+namespace mlp {
+
+constexpr int NPAR = 2 + WD * NV + WD + 2 * (WD * WD + WD) + WD + 1;
+enum { C_ACTIVE = 0, C_JAC, C_ROWS_A, C_TRAJ_A, C_ROWS_B, C_TRAJ_B, C_ERR, C_F0, C_N };
+
+struct Ctx {
+  double* d_w = nullptr;   // all weight matrices, both orientations
+  Weights W{};
+  long long cap = 0;       // trajectories the workspace holds
+  int cap_SM = 0;
+  State S{};
+  void* pool = nullptr;
+  double* d_act = nullptr;
+  int *d_rows[2] = {nullptr, nullptr}, *d_trajs[2] = {nullptr, nullptr};
+  int *d_jac = nullptr, *d_err = nullptr, *d_f0 = nullptr, *d_cnt = nullptr;
+  int* h_cnt = nullptr;    // pinned
+};
+
+__device__ __forceinline__ int append(int* counter, int n) { return atomicAdd(counter, n); }
+
+__global__ void init_kernel(const State S, const __grid_constant__ RadauParams P, const double* __restrict__ y0,
+                            const double* __restrict__ tspan) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < S.M) ph_init(S, P, i, y0, tspan);
+}
+__global__ void init_b_kernel(const State S) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < S.M) ph_init_b(S, i);
+}
+__global__ void head_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* jac_list) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= S.M) return;
+  ph_head(S, P, i);
+  const int ph = S.sc[i].phase;
+  if (ph != PH_FINISHED) atomicAdd(&cnt[C_ACTIVE], 1);
+  if (ph == PH_WANT_JAC) jac_list[append(&cnt[C_JAC], 1)] = (int)i;
+}
+__device__ __forceinline__ void enqueue(const State& S, long long i, int* cnt, int c_rows, int c_traj, int* rows, int* trajs,
+                                        int* err_list, int* f0_list) {
+  const TrajS& s = S.sc[i];
+  if (s.phase == PH_NEWTON) {
+    const int n = s.NbrStg;
+    const int at = append(&cnt[c_rows], n);
+    for (int q = 0; q < n; q++) rows[at + q] = (int)i * 8 + q;
+    trajs[append(&cnt[c_traj], 1)] = (int)i;
+  } else if (s.phase == PH_ERR_EVAL) {
+    err_list[append(&cnt[C_ERR], 1)] = (int)i * 8;
+  } else if (s.phase == PH_F0_EVAL) {
+    f0_list[append(&cnt[C_F0], 1)] = (int)i * 8;
+  }
+}
+__global__ void prep_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* rows, int* trajs) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= S.M) return;
+  const int ph = S.sc[i].phase;
+  if (ph != PH_WANT_JAC && ph != PH_PREP) return;
+  ph_prep(S, P, i);
+  enqueue(S, i, cnt, C_ROWS_A, C_TRAJ_A, rows, trajs, nullptr, nullptr);
+}
+__global__ void newton_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in, int n_in,
+                              int* cnt, int c_rows, int c_traj, int* rows_out, int* trajs_out, int* err_list, int* f0_list) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_in) return;
+  const long long i = trajs_in[k];
+  ph_newton(S, P, i);
+  enqueue(S, i, cnt, c_rows, c_traj, rows_out, trajs_out, err_list, f0_list);
+}
+__global__ void estrad_b_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ err_list, int n,
+                                int* cnt, int* f0_list) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long long i = err_list[k] >> 3;
+  ph_estrad_b(S, P, i);
+  if (S.sc[i].phase == PH_F0_EVAL) f0_list[append(&cnt[C_F0], 1)] = (int)i * 8;
+}
+__global__ void accept_b_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ f0_list, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  ph_accept_b(S, P, f0_list[k] >> 3);
+}
+__global__ void output_kernel(const State S, double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
+                              int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
+                              long long* __restrict__ work) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= S.M) return;
+  const TrajS s = S.sc[i];
+  for (int e = 0; e < MN; e++) y_out[i * MN + e] = S.y[(size_t)e * S.M + i];
+  t_out[i] = s.t;
+  h_out[i] = s.h;
+  res[i] = s.res;
+  for (int k = 0; k < 8; k++) stats[i * 8 + k] = s.st[k];
+  if (nstg) nstg[i] = s.NbrStg;
+  if (work) work[i] = s.work;
+}
+
+static Ctx* ctx_of(Handle* H) { return (Ctx*)H->ext; }
+
+static void free_workspace(Ctx* C) {
+  cudaFree(C->pool);
+  cudaFree(C->d_act);
+  for (int k = 0; k < 2; k++) { cudaFree(C->d_rows[k]); cudaFree(C->d_trajs[k]); }
+  cudaFree(C->d_jac); cudaFree(C->d_err); cudaFree(C->d_f0);
+  C->pool = nullptr; C->d_act = nullptr; C->d_rows[0] = C->d_rows[1] = C->d_trajs[0] = C->d_trajs[1] = nullptr;
+  C->d_jac = C->d_err = C->d_f0 = nullptr;
+  C->cap = 0;
+}
+
+static int ensure(Handle* H, long long M, bool need_state) {
+  Ctx* C = ctx_of(H);
+  const int SM = H->P.MaxNbrStg;
+  if (M <= C->cap && SM <= C->cap_SM && (C->pool || !need_state)) return 0;
+  if (M > (1LL << 27)) return fail(JB200_EINVAL, "MLP Hamiltonian path: M must be <= 2^27 per GPU");
+  free_workspace(C);
+  const int nq = (SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1;
+  JB_CUDA(cudaMalloc(&C->d_act, sizeof(double) * 5 * WD * (size_t)M));
+  if (need_state) {
+    const size_t per_d = MN * 6 + MN * MN * 2 + (size_t)SM * MN * 4 + 1 + MN + (size_t)nq * (2 * MN * MN + 2 * MN);
+    const size_t per_i = MN + (size_t)nq * MN;
+    const size_t bytes = sizeof(TrajS) * (size_t)M + 256 + sizeof(double) * per_d * (size_t)M + sizeof(int) * per_i * (size_t)M;
+    JB_CUDA(cudaMalloc(&C->pool, bytes));
+    char* p = (char*)C->pool;
+    State& S = C->S;
+    S.M = M;
+    S.SM = SM;
+    S.sc = (TrajS*)p;
+    p += ((sizeof(TrajS) * (size_t)M + 255) / 256) * 256;
+    double* d = (double*)p;
+    auto take = [&](size_t per) { double* r = d; d += per * (size_t)M; return r; };
+    S.y = take(MN); S.f0 = take(MN); S.Jac = take(MN * MN); S.cont = take(SM * MN); S.z = take(SM * MN);
+    S.w = take(SM * MN); S.F = take(SM * MN); S.rscal = take(MN); S.temp = take(MN); S.ev = take(MN); S.errs = take(1);
+    S.L0a = take(MN * MN); S.L0rd = take(MN);
+    S.Lre = take(nq * MN * MN); S.Lim = take(nq * MN * MN); S.Lrdre = take(nq * MN); S.Lrdim = take(nq * MN);
+    int* ip = (int*)d;
+    S.L0piv = ip;
+    S.Lpiv = ip + (size_t)MN * M;
+    for (int k = 0; k < 2; k++) {
+      JB_CUDA(cudaMalloc(&C->d_rows[k], sizeof(int) * (size_t)SM * M));
+      JB_CUDA(cudaMalloc(&C->d_trajs[k], sizeof(int) * (size_t)M));
+    }
+    JB_CUDA(cudaMalloc(&C->d_jac, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C->d_err, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C->d_f0, sizeof(int) * (size_t)M));
+  }
+  C->cap = M;
+  C->cap_SM = SM;
+  return 0;
+}
+
+static int launch_grad(Handle* H, const GradIO& io, int n_rows, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  const int tiles = (n_rows + TR - 1) / TR;
+  const int grid = tiles < H->sm_count ? tiles : H->sm_count;
+  mlp_grad_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ctx_of(H)->W, io);
+  JB_CUDA(cudaGetLastError());
+  H->launches += 1;
+  return 0;
+}
+static int launch_hess(Handle* H, const HessIO& io, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int tiles = (n + 3) / 4;
+  const int grid = tiles < H->sm_count ? tiles : H->sm_count;
+  mlp_hess_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ctx_of(H)->W, io);
+  JB_CUDA(cudaGetLastError());
+  H->launches += 1;
+  return 0;
+}
+
+static int read_counters(Ctx* C, cudaStream_t st) {
+  JB_CUDA(cudaMemcpyAsync(C->h_cnt, C->d_cnt, sizeof(int) * C_N, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int solve(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out, double* h_out,
+                 int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  if (dense.tout) return fail(JB200_ENOTSUP, "MLP Hamiltonian path: output at tspan points is not available yet");
+  int rc = ensure(H, M, true);
+  if (rc) return rc;
+  Ctx* C = ctx_of(H);
+  State S = C->S;
+  S.M = M;   // element stride = this batch (the pool was sized for cap >= M)
+  const RadauParams& P = H->P;
+  H->launches = 0;
+  const unsigned gb = (unsigned)((M + 127) / 128);
+  auto blocks = [](int n) { return (unsigned)((n + 127) / 128); };
+  init_kernel<<<gb, 128, 0, st>>>(S, P, y0, tspan);
+  GradIO g0{nullptr, nullptr, (int)M, S.y, 1, M, nullptr, 0, 0, nullptr, S.f0, 1, M, C->d_act, P.sign};
+  if ((rc = launch_grad(H, g0, (int)M, st))) return rc;
+  init_b_kernel<<<gb, 128, 0, st>>>(S);
+  H->launches += 2;
+  for (;;) {
+    JB_CUDA(cudaMemsetAsync(C->d_cnt, 0, sizeof(int) * C_N, st));
+    head_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_jac);
+    H->launches += 1;
+    if ((rc = read_counters(C, st))) return rc;
+    if (C->h_cnt[C_ACTIVE] == 0) break;
+    if (C->h_cnt[C_JAC] > 0) {
+      HessIO hio{C->d_jac, nullptr, C->h_cnt[C_JAC], C->d_act, S.Jac, 1, M, P.sign};
+      if ((rc = launch_hess(H, hio, C->h_cnt[C_JAC], st))) return rc;
+    }
+    prep_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_rows[0], C->d_trajs[0]);
+    H->launches += 1;
+    int cur = 0;
+    for (;;) {
+      if ((rc = read_counters(C, st))) return rc;
+      const int n_rows = C->h_cnt[cur ? C_ROWS_B : C_ROWS_A], n_traj = C->h_cnt[cur ? C_TRAJ_B : C_TRAJ_A];
+      if (n_traj == 0) break;
+      GradIO gi{C->d_rows[cur], nullptr, n_rows, S.y, 1, M, S.z, 1, M, nullptr, S.F, 1, M, nullptr, P.sign};
+      if ((rc = launch_grad(H, gi, n_rows, st))) return rc;
+      const int nxt = cur ^ 1;
+      JB_CUDA(cudaMemsetAsync(C->d_cnt + (nxt ? C_ROWS_B : C_ROWS_A), 0, 2 * sizeof(int), st));
+      newton_kernel<<<blocks(n_traj), 128, 0, st>>>(S, P, C->d_trajs[cur], n_traj, C->d_cnt, nxt ? C_ROWS_B : C_ROWS_A,
+                                                    nxt ? C_TRAJ_B : C_TRAJ_A, C->d_rows[nxt], C->d_trajs[nxt], C->d_err,
+                                                    C->d_f0);
+      H->launches += 1;
+      cur = nxt;
+    }
+    if (C->h_cnt[C_ERR] > 0) {
+      const int n = C->h_cnt[C_ERR];
+      GradIO ge{C->d_err, nullptr, n, S.y, 1, M, nullptr, 0, 0, S.errs, S.ev, 1, M, nullptr, P.sign};
+      if ((rc = launch_grad(H, ge, n, st))) return rc;
+      estrad_b_kernel<<<blocks(n), 128, 0, st>>>(S, P, C->d_err, n, C->d_cnt, C->d_f0);
+      H->launches += 1;
+      if ((rc = read_counters(C, st))) return rc;
+    }
+    if (C->h_cnt[C_F0] > 0) {
+      const int n = C->h_cnt[C_F0];
+      GradIO gf{C->d_f0, nullptr, n, S.y, 1, M, nullptr, 0, 0, nullptr, S.f0, 1, M, C->d_act, P.sign};
+      if ((rc = launch_grad(H, gf, n, st))) return rc;
+      accept_b_kernel<<<blocks(n), 128, 0, st>>>(S, P, C->d_f0, n);
+      H->launches += 1;
+    }
+  }
+  output_kernel<<<gb, 128, 0, st>>>(S, y_out, t_out, h_out, res, stats, nstg, work);
+  H->launches += 1;
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int dyns(Handle* H, const double* y, long long M, double* ydot, cudaStream_t st) {
+  const GradIO io{nullptr, nullptr, (int)M, y, MN, 1, nullptr, 0, 0, nullptr, ydot, MN, 1, nullptr, H->P.sign};
+  return launch_grad(H, io, (int)M, st);
+}
+
+static int jac(Handle* H, const double* y, long long M, double* J, cudaStream_t st) {
+  int rc = ensure(H, M, false);
+  if (rc) return rc;
+  Ctx* C = ctx_of(H);
+  double* tmp = nullptr;
+  JB_CUDA(cudaMalloc(&tmp, sizeof(double) * MN * (size_t)M));
+  const GradIO io{nullptr, nullptr, (int)M, y, MN, 1, nullptr, 0, 0, nullptr, tmp, MN, 1, C->d_act, H->P.sign};
+  rc = launch_grad(H, io, (int)M, st);
+  if (!rc) {
+    const HessIO hio{nullptr, nullptr, (int)M, C->d_act, J, MN * MN, 1, H->P.sign};
+    rc = launch_hess(H, hio, (int)M, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return rc;
+}
+
+static int create(Handle* H, const double* par, int npar) {
+  if (npar != NPAR) return fail(JB200_EINVAL, "MLP Hamiltonian needs " + std::to_string(NPAR) + " parameters");
+  if ((int)par[0] != NH || (int)par[1] != WD)
+    return fail(JB200_ENOTSUP, "MLP Hamiltonian kernels are built for N = 8 (16 inputs), width 128");
+  Ctx* C = new Ctx();
+  H->ext = C;
+  const double* W1 = par + 2;
+  const double* b1 = W1 + WD * NV;
+  const double* W2 = b1 + WD;
+  const double* b2 = W2 + WD * WD;
+  const double* W3 = b2 + WD;
+  const double* b3 = W3 + WD * WD;
+  const double* W4 = b3 + WD;
+  std::vector<double> buf;
+  auto push = [&](const double* src, int rows, int cols, bool transpose) {
+    const size_t at = buf.size();
+    buf.resize(at + (size_t)rows * cols);
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) {
+        if (transpose) buf[at + (size_t)c * rows + r] = src[(size_t)r * cols + c];
+        else buf[at + (size_t)r * cols + c] = src[(size_t)r * cols + c];
+      }
+    return at;
+  };
+  const size_t oW1t = push(W1, WD, NV, true), oW2t = push(W2, WD, WD, true), oW3t = push(W3, WD, WD, true);
+  const size_t oW3 = push(W3, WD, WD, false), oW2 = push(W2, WD, WD, false), oW1 = push(W1, WD, NV, false);
+  const size_t ob1 = push(b1, 1, WD, false), ob2 = push(b2, 1, WD, false), ob3 = push(b3, 1, WD, false);
+  const size_t oW4 = push(W4, 1, WD, false);
+  JB_CUDA(cudaMalloc(&C->d_w, sizeof(double) * buf.size()));
+  JB_CUDA(cudaMemcpy(C->d_w, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+  C->W = Weights{C->d_w + oW1t, C->d_w + oW2t, C->d_w + oW3t, C->d_w + oW3, C->d_w + oW2, C->d_w + oW1,
+                 C->d_w + ob1,  C->d_w + ob2,  C->d_w + ob3,  C->d_w + oW4};
+  JB_CUDA(cudaMalloc(&C->d_cnt, sizeof(int) * C_N));
+  JB_CUDA(cudaMallocHost(&C->h_cnt, sizeof(int) * C_N));
+  JB_CUDA(cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  JB_CUDA(cudaFuncSetAttribute(mlp_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  return 0;
+}
+
+static void destroy(Handle* H) {
+  Ctx* C = ctx_of(H);
+  if (!C) return;
+  free_workspace(C);
+  cudaFree(C->d_w);
+  cudaFree(C->d_cnt);
+  if (C->h_cnt) cudaFreeHost(C->h_cnt);
+  delete C;
+  H->ext = nullptr;
+}
+
+static int st_init(Handle*, EpochWS&, const double*, const double*, int, long long, cudaStream_t) {
+  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+}
+static int st_step(Handle*, EpochWS&, const double*, cudaStream_t) {
+  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+}
+static int st_read(Handle*, EpochWS&, double*, double*, double*, double*, int*, long long*, int*, int*, cudaStream_t) {
+  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+}
+
+}  // namespace mlp
+
+extern const HamOps jb_ops_mlp = HamOps{mlp::MN,       mlp::NPAR,     &mlp::solve,   &mlp::dyns,   &mlp::jac,
+                                        &mlp::st_init, &mlp::st_step, &mlp::st_read, &mlp::create, &mlp::destroy};
+
+}  // namespace jb

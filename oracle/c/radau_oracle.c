@@ -114,6 +114,13 @@ static double det_exp(double t) {
   return q * scale;
 }
 static double det_pow(double x, double y) { return det_exp(y * det_log(x)); }
+static double det_tanh(double x) {   /* csrc/detmath.cuh det_tanh */
+  const double ax = fabs(x);
+  if (ax > 20.0) return x > 0 ? 1.0 : -1.0;
+  const double e = det_exp(-2.0 * ax);
+  const double th = (1.0 - e) / (1.0 + e);
+  return x < 0 ? -th : th;
+}
 static double POW(double x, double y) { return g_mirror ? det_pow(x, y) : pow(x, y); }
 
 /* ---- problem ids (shared numbering with include/janus_b200.h JB200_HAM_*) ---- */
@@ -147,6 +154,7 @@ static double bang(double p2, double x1, double x2, double umin, double umax) {
 }
 
 static void mlp_eval(const problem_t *pb, const double *y, double *f, double *J);
+static void mlp_eval_mirror(const problem_t *pb, const double *y, double *f, double *J);
 
 /* ------------------------------------------------------------------ mirror-mode derivatives
  * Dense dual / hyper-dual arithmetic following the ARITHMETIC CONTRACT of csrc/dual.cuh (the
@@ -286,7 +294,8 @@ static void jac_mirror(const problem_t *pb, const double *y, double *J) {
 static void rhs(const problem_t *pb, double t, const double *y, double *f) {
   (void)t;
   const double sg = pb->sign;
-  if (g_mirror && pb->id != PB_MLP) { rhs_mirror(pb, y, f); return; }
+  if (g_mirror && pb->id == PB_MLP) { mlp_eval_mirror(pb, y, f, NULL); return; }
+  if (g_mirror) { rhs_mirror(pb, y, f); return; }
   switch (pb->id) {
     case PB_HARMONIC: {
       double w = pb->par[0];
@@ -328,7 +337,8 @@ static void jacobian(const problem_t *pb, double t, const double *y, double *J /
   (void)t;
   const int n = pb->Ny;
   const double sg = pb->sign;
-  if (g_mirror && pb->id != PB_MLP) { jac_mirror(pb, y, J); return; }
+  if (g_mirror && pb->id == PB_MLP) { double fm[NYMAX]; mlp_eval_mirror(pb, y, fm, J); return; }
+  if (g_mirror) { jac_mirror(pb, y, J); return; }
   memset(J, 0, sizeof(double) * n * n);
   switch (pb->id) {
     case PB_HARMONIC: {
@@ -430,6 +440,61 @@ static void mlp_eval(const problem_t *pb, const double *y, double *f, double *J)
     /* map v-index -> y-index: v_i (x_i) = y_{N+i}; v_{N+i} (p_i) = y_i.
      * ydot_r: r<N  -> sg*g[r]   (g index r = x_r);  r>=N -> g[r] (p_{r-N})
      * column c of y: c<N -> p_c = v_{N+c}; c>=N -> x_{c-N} = v_{c-N}                     */
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < n; c++) {
+        int vc = (c < N) ? (N + c) : (c - N);
+        double val = Hvv[r * n + vc];
+        J[r * n + c] = (r < N) ? pb->sign * val : val;
+      }
+  }
+  free(a1);
+}
+
+
+/* Mirror of the GPU's MLP kernels (csrc/mlp_kernels.cuh), operation by operation: every dot
+ * product is ONE fma chain in increasing index order (forward: seeded with the bias; transposed
+ * products: seeded with 0.0), tanh = det_tanh, 1 - a^2 = fma(-a, a, 1).                     */
+static void mlp_eval_mirror(const problem_t *pb, const double *y, double *f, double *J) {
+  const int N = (int)pb->par[0], Wd = (int)pb->par[1], n = 2 * N;
+  const double *W1 = pb->par + 2, *b1 = W1 + (size_t)Wd * n;
+  const double *W2 = b1 + Wd, *b2 = W2 + (size_t)Wd * Wd;
+  const double *W3 = b2 + Wd, *b3 = W3 + (size_t)Wd * Wd;
+  const double *W4 = b3 + Wd;
+  double v[NYMAX];
+  for (int i = 0; i < N; i++) { v[i] = y[N + i]; v[N + i] = y[i]; }   /* v=[x;p] */
+  double *a1 = (double *)malloc(sizeof(double) * Wd * 17);
+  double *a2 = a1 + Wd, *a3 = a2 + Wd, *d1 = a3 + Wd, *d2 = d1 + Wd, *d3 = d2 + Wd;
+  double *ta1 = d3 + Wd, *ta2 = ta1 + Wd, *ta3 = ta2 + Wd, *td1 = ta3 + Wd, *td2 = td1 + Wd, *td3 = td2 + Wd;
+  double *q1 = td3 + Wd, *q2 = q1 + Wd, *e1 = q2 + Wd, *e2 = e1 + Wd, *e3 = e2 + Wd;
+  for (int i = 0; i < Wd; i++) { double s = b1[i]; for (int j = 0; j < n; j++) s = fma(W1[(size_t)i * n + j], v[j], s); a1[i] = det_tanh(s); }
+  for (int i = 0; i < Wd; i++) { double s = b2[i]; for (int j = 0; j < Wd; j++) s = fma(W2[(size_t)i * Wd + j], a1[j], s); a2[i] = det_tanh(s); }
+  for (int i = 0; i < Wd; i++) { double s = b3[i]; for (int j = 0; j < Wd; j++) s = fma(W3[(size_t)i * Wd + j], a2[j], s); a3[i] = det_tanh(s); }
+  for (int i = 0; i < Wd; i++) { e1[i] = fma(-a1[i], a1[i], 1.0); e2[i] = fma(-a2[i], a2[i], 1.0); e3[i] = fma(-a3[i], a3[i], 1.0); }
+  for (int i = 0; i < Wd; i++) d3[i] = W4[i] * e3[i];
+  for (int j = 0; j < Wd; j++) { double s = 0.0; for (int i = 0; i < Wd; i++) s = fma(W3[(size_t)i * Wd + j], d3[i], s); q2[j] = s; d2[j] = s * e2[j]; }
+  for (int j = 0; j < Wd; j++) { double s = 0.0; for (int i = 0; i < Wd; i++) s = fma(W2[(size_t)i * Wd + j], d2[i], s); q1[j] = s; d1[j] = s * e1[j]; }
+  double g[NYMAX];
+  for (int j = 0; j < n; j++) { double s = 0.0; for (int i = 0; i < Wd; i++) s = fma(W1[(size_t)i * n + j], d1[i], s); g[j] = s; }
+  for (int i = 0; i < N; i++) { f[i] = pb->sign * g[i]; f[N + i] = g[N + i]; }
+  if (J) {
+    double Hvv[NYMAX * NYMAX];
+    for (int k = 0; k < n; k++) {   /* tangent direction e_k in v */
+      for (int i = 0; i < Wd; i++) ta1[i] = e1[i] * W1[(size_t)i * n + k];
+      for (int i = 0; i < Wd; i++) { double s = 0.0; for (int j = 0; j < Wd; j++) s = fma(W2[(size_t)i * Wd + j], ta1[j], s); ta2[i] = e2[i] * s; }
+      for (int i = 0; i < Wd; i++) { double s = 0.0; for (int j = 0; j < Wd; j++) s = fma(W3[(size_t)i * Wd + j], ta2[j], s); ta3[i] = e3[i] * s; }
+      for (int i = 0; i < Wd; i++) td3[i] = W4[i] * ((-2.0 * a3[i]) * ta3[i]);
+      for (int j = 0; j < Wd; j++) {
+        double ts = 0.0;
+        for (int i = 0; i < Wd; i++) ts = fma(W3[(size_t)i * Wd + j], td3[i], ts);
+        td2[j] = fma(q2[j], (-2.0 * a2[j]) * ta2[j], ts * e2[j]);
+      }
+      for (int j = 0; j < Wd; j++) {
+        double ts = 0.0;
+        for (int i = 0; i < Wd; i++) ts = fma(W2[(size_t)i * Wd + j], td2[i], ts);
+        td1[j] = fma(q1[j], (-2.0 * a1[j]) * ta1[j], ts * e1[j]);
+      }
+      for (int j = 0; j < n; j++) { double s = 0.0; for (int i = 0; i < Wd; i++) s = fma(W1[(size_t)i * n + j], td1[i], s); Hvv[j * n + k] = s; }
+    }
     for (int r = 0; r < n; r++)
       for (int c = 0; c < n; c++) {
         int vc = (c < N) ? (N + c) : (c - N);

@@ -145,3 +145,85 @@ extern "C" int hostsim_solve_epochs(int ham_id, const RadauParams* P, const doub
   }
   return -1;
 }
+
+// ---- MLP Hamiltonian path (csrc/mlp_phase.cuh): the same phase functions the GPU kernels wrap,
+// driven by the same pass protocol; the stage / Jacobian evaluations (tile GEMMs on the GPU) are
+// delegated to callbacks (the mirror oracle's scalar evaluation, passed in from the test).
+#include "../../janus_ode_b200/csrc/mlp_phase.cuh"
+
+typedef int (*mlp_dyns_fn)(int problem, const double* par, int sign, int Ny, long long M, const double* y, double* f);
+typedef int (*mlp_jac_fn)(int problem, const double* par, int sign, int Ny, long long M, const double* y, double* J);
+
+extern "C" int hostsim_mlp_solve(mlp_dyns_fn dyns, mlp_jac_fn jacf, const double* par, const RadauParams* Pp,
+                                 const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
+                                 double* h_out, int* res, long long* stats, int* nstg, long long* work) {
+  using namespace jb::mlp;
+  const RadauParams& P = *Pp;
+  const int sign = (int)P.sign, SM = P.MaxNbrStg, nq = (SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1;
+  std::vector<TrajS> sc(M);
+  auto dv = [&](size_t per) { return std::vector<double>(per * M, 0.0); };
+  auto y = dv(MN), f0 = dv(MN), Jac = dv(MN * MN), cont = dv(SM * MN), z = dv(SM * MN), w = dv(SM * MN), F = dv(SM * MN),
+       rscal = dv(MN), temp = dv(MN), ev = dv(MN), errs = dv(1), L0a = dv(MN * MN), L0rd = dv(MN), Lre = dv(nq * MN * MN),
+       Lim = dv(nq * MN * MN), Lrdre = dv(nq * MN), Lrdim = dv(nq * MN);
+  std::vector<int> L0piv(MN * M), Lpiv((size_t)nq * MN * M);
+  State S{M, SM, sc.data(), y.data(), f0.data(), Jac.data(), cont.data(), z.data(), w.data(), F.data(), rscal.data(),
+          temp.data(), ev.data(), errs.data(), L0a.data(), L0rd.data(), L0piv.data(), Lre.data(), Lim.data(),
+          Lrdre.data(), Lrdim.data(), Lpiv.data()};
+  double yy[MN], ff[MN], JJ[MN * MN];
+  auto eval_at = [&](long long i, const double* add /*SoA offset or null*/, double scalar, double* out) {
+    for (int e = 0; e < MN; e++) {
+      double v = S.y[(size_t)e * M + i];
+      if (add) v = v + add[(size_t)e * M + i];
+      else if (scalar != 0.0) v = v + scalar;
+      yy[e] = v;
+    }
+    dyns(5, par, sign, MN, 1, yy, ff);
+    for (int e = 0; e < MN; e++) out[(size_t)e * M + i] = ff[e];
+  };
+  for (long long i = 0; i < M; i++) {
+    ph_init(S, P, i, y0, tspan);
+    eval_at(i, nullptr, 0.0, S.f0);
+    ph_init_b(S, i);
+  }
+  for (;;) {
+    long long active = 0;
+    for (long long i = 0; i < M; i++) {
+      ph_head(S, P, i);
+      if (sc[i].phase != PH_FINISHED) active++;
+      if (sc[i].phase == PH_WANT_JAC) {
+        for (int e = 0; e < MN; e++) yy[e] = S.y[(size_t)e * M + i];
+        jacf(5, par, sign, MN, 1, yy, JJ);
+        for (int k = 0; k < MN * MN; k++) S.Jac[(size_t)k * M + i] = JJ[k];
+      }
+    }
+    if (!active) break;
+    for (long long i = 0; i < M; i++) ph_prep(S, P, i);
+    for (;;) {
+      long long n = 0;
+      for (long long i = 0; i < M; i++)
+        if (sc[i].phase == PH_NEWTON) {
+          n++;
+          for (int q = 0; q < sc[i].NbrStg; q++) eval_at(i, S.z + (size_t)q * MN * M, 0.0, S.F + (size_t)q * MN * M);
+        }
+      if (!n) break;
+      for (long long i = 0; i < M; i++) ph_newton(S, P, i);
+    }
+    for (long long i = 0; i < M; i++)
+      if (sc[i].phase == PH_ERR_EVAL) {
+        eval_at(i, nullptr, S.errs[i], S.ev);
+        ph_estrad_b(S, P, i);
+      }
+    for (long long i = 0; i < M; i++)
+      if (sc[i].phase == PH_F0_EVAL) {
+        eval_at(i, nullptr, 0.0, S.f0);
+        ph_accept_b(S, P, i);
+      }
+  }
+  for (long long i = 0; i < M; i++) {
+    for (int e = 0; e < MN; e++) y_out[i * MN + e] = S.y[(size_t)e * M + i];
+    t_out[i] = sc[i].t; h_out[i] = sc[i].h; res[i] = sc[i].res; nstg[i] = sc[i].NbrStg;
+    for (int k = 0; k < 8; k++) stats[i * 8 + k] = sc[i].st[k];
+    if (work) work[i] = sc[i].work;
+  }
+  return 0;
+}

@@ -25,6 +25,47 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def _params(lib, opts, ny, sign, par):
+    P = (C.c_char * lib.hostsim_params_size())()
+    rt = np.ascontiguousarray(np.broadcast_to(np.asarray(opts.RelTol, dtype=np.float64), (ny,)))
+    at = np.ascontiguousarray(np.broadcast_to(np.asarray(opts.AbsTol, dtype=np.float64), (ny,)))
+    d = C.c_double
+    lib.hostsim_fill_params(P, _dp(rt), _dp(at), C.c_int(ny), d(opts.InitialStep), d(opts.JacRecompute),
+                            d(opts.Safe), d(opts.Quot1), d(opts.Quot2), d(opts.FacL), d(opts.FacR), d(opts.Vitu),
+                            d(opts.Vitd), d(opts.hhou), d(opts.hhod), C.c_int(sign), C.c_longlong(opts.MaxNbrStep),
+                            C.c_int(int(opts.Start_Newt)), C.c_int(opts.MaxNbrNewton), C.c_int(opts.NbrStg),
+                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(int(opts.Gustafsson)),
+                            _dp(par[:8]), C.c_int(min(par.size, 8)))
+    return P
+
+
+def solve_mlp(par, sign, y0, tspan, opts, oracle_lib):
+    """The MLP-Hamiltonian phase machine (csrc/mlp_phase.cuh) on the CPU; stage / Jacobian evaluations
+    are the callbacks oracle_eval_dyns / oracle_eval_jac of `oracle_lib` (set it to mirror arithmetic)."""
+    build()
+    lib = C.CDLL(_SO)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, ny = y0.shape
+    assert ny == 16 and tspan.shape[1] == 2
+    P = _params(lib, opts, ny, sign, par)
+    y = np.empty_like(y0)
+    t = np.empty(M)
+    h = np.empty(M)
+    res = np.empty(M, dtype=np.int32)
+    stats = np.empty((M, 8), dtype=np.int64)
+    nstg = np.empty(M, dtype=np.int32)
+    work = np.empty(M, dtype=np.int64)
+    fd = C.cast(oracle_lib.oracle_eval_dyns, C.c_void_p)
+    fj = C.cast(oracle_lib.oracle_eval_jac, C.c_void_p)
+    rc = lib.hostsim_mlp_solve(fd, fj, _dp(par), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(t), _dp(h),
+                               res.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+                               nstg.ctypes.data_as(C.POINTER(C.c_int)), work.ctypes.data_as(C.POINTER(C.c_longlong)))
+    assert rc == 0
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, work=work)
+
+
 def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
     """epochs_K > 0: emulate the variable-order epoch scheme (park / regroup / resume every K passes)."""
     build()
