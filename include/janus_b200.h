@@ -52,7 +52,7 @@ extern "C" {
 #define JB200_HAM_VDP_PMP_BANG 3    /* N=2 par: W,umin,umax        same Hu, u=umax if p2(1-x1^2)x2<0 else umin */
 #define JB200_HAM_VDP_AUG_BANG 4    /* N=2 par: umin,umax          H=p1x2+p2(u(1-x1^2)x2-x1), bang-bang u */
 #define JB200_HAM_MLP 5             /* N=8 par: [8, 128, W1[128][16], b1[128], W2[128][128], b2, W3[128][128], b3,
-                                       W4[128], b4] (35,075 numbers)  H = W4.tanh(W3 tanh(W2 tanh(W1 [x;p]+b1)+b2)+b3)+b4:
+                                       W4[128], b4] (35,331 numbers)  H = W4.tanh(W3 tanh(W2 tanh(W1 [x;p]+b1)+b2)+b3)+b4:
                                        stage evaluations as batched fp64 GEMM tiles (csrc/mlp_kernels.cuh)         */
 #define JB200_HAM_USER 100          /* plugin libraries only: the user-supplied Hamiltonian the plugin was
                                        compiled around (janus_ode_b200/user.py; same ABI, N <= 2)          */

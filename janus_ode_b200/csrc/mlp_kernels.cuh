@@ -9,8 +9,8 @@
 //                    (2 transposed GEMMs + the 128x16 output product) -> ydot = [sg dH/dx ; dH/dp]
 //   mlp_hess_kernel  4 trajectories x 16 tangent directions per CTA: forward-over-reverse (tangent
 //                    forward 2 GEMMs, tangent reverse 2 GEMMs + output product) -> the 16x16 Jacobian
-// One CTA = 128 threads = one warp per SM sub-partition, each thread owns an 8x8 register tile of
-// the 64x128 layer output (64 independent DFMA chains: the FP64 pipe is the only bound); the
+// One CTA = 256 threads = two warps per SM sub-partition, each thread owns a 4x8 register tile of
+// the 64x128 layer output (32 independent DFMA chains: the FP64 pipe is the only bound); the
 // activations of the tile stay in shared memory ([feature][row], 3 x 64 KB) from the first layer
 // to the last, weights stream from L2 in 8-row chunks through a cp.async double buffer.
 //
@@ -29,7 +29,8 @@ namespace mlp {
 
 constexpr int TR = 64;        // rows per CTA tile
 constexpr int KC = 8;         // weight rows per cp.async chunk
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;     // 2 warps per SM sub-partition: a lone warp cannot re-issue DFMAs back to back
+constexpr int RJ = 2;            // row groups per thread: register tile = (2 RJ) rows x 8 columns
 constexpr int ACT_WORDS = WD * TR;                                      // one activation buffer
 constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 208 KB
 
@@ -48,17 +49,20 @@ struct Weights {
   const double* W4;    // [128]
 };
 
-// thread -> register tile: lane%8 picks the row pair, warp*4 + lane/8 the column pair
+// thread -> register tile: rows {r0, r0+1} + 32 j (j < RJ), columns {c0, c0+1} + 32 j (j < 4);
+// within a warp 8 row pairs x 4 column pairs, so every shared-memory access is a full-width or
+// broadcast wavefront
 struct TileMap {
   int r0, c0;
   __device__ TileMap() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    r0 = (lane & 7) * 2;
-    c0 = (warp * 4 + (lane >> 3)) * 2;
+    r0 = ((lane & 7) + 8 * (warp & 1)) * 2;
+    c0 = ((warp >> 1) * 4 + (lane >> 3)) * 2;
   }
-  __device__ __forceinline__ int row(int j, int e) const { return r0 + 16 * j + e; }   // j < 4, e < 2
-  __device__ __forceinline__ int col(int j, int e) const { return c0 + 32 * j + e; }
+  __device__ __forceinline__ int row(int j, int e) const { return r0 + 32 * j + e; }   // j < RJ, e < 2
+  __device__ __forceinline__ int col(int j, int e) const { return c0 + 32 * j + e; }   // j < 4
 };
+constexpr int NR = 2 * RJ;   // rows of the register tile
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -71,7 +75,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // acc[ri][ci] += sum_k A[k][row(ri)] * B[k][col(ci)], k = 0..K-1 in order (one fma chain each).
 // A: shared [K][TR]; B: global [K][WD] (row-major, 16-byte aligned); wbuf: shared [2][KC][WD].
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const double* __restrict__ B, int K,
-                                          double* __restrict__ wbuf, const TileMap& tm, double (&acc)[8][8]) {
+                                          double* __restrict__ wbuf, const TileMap& tm, double (&acc)[NR][8]) {
   const int nchunks = K / KC;
   auto issue = [&](int ch) {
     const double* src = B + (size_t)ch * KC * WD;
@@ -96,18 +100,21 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
     const double* Ak = A + (size_t)ch * KC * TR;
 #pragma unroll
     for (int kk = 0; kk < KC; kk++) {
-      double a[8], b[8];
+      double a[NR], b[8];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double2 av = *reinterpret_cast<const double2*>(Ak + kk * TR + tm.r0 + 16 * j);
+      for (int j = 0; j < RJ; j++) {
+        const double2 av = *reinterpret_cast<const double2*>(Ak + kk * TR + tm.r0 + 32 * j);
         a[2 * j] = av.x;
         a[2 * j + 1] = av.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
         const double2 bv = *reinterpret_cast<const double2*>(wb + kk * WD + tm.c0 + 32 * j);
         b[2 * j] = bv.x;
         b[2 * j + 1] = bv.y;
       }
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++)
+      for (int ri = 0; ri < NR; ri++)
 #pragma unroll
         for (int ci = 0; ci < 8; ci++) acc[ri][ci] = fma(b[ci], a[ri], acc[ri][ci]);
     }
@@ -115,44 +122,48 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
   }
 }
 
-// out[row][j] = sum_i W1[i][j] * D[i][row], j < 16: 64 x 16 outputs, 8 per thread
-// (thread -> row = tid % 64, columns (tid / 64) * 8 ..).  W1 (natural [128][16]) is staged in wbuf.
+// out[row][j] = sum_i W1[i][j] * D[i][row], j < 16: 64 x 16 outputs, OC per thread
+// (thread -> row = tid % 64, columns (tid / 64) * OC ..).  W1 (natural [128][16]) is staged in wbuf.
+constexpr int OC = NV * TR / THREADS;
 __device__ __forceinline__ void output_product(const double* __restrict__ D, const double* __restrict__ W1g,
-                                               double* __restrict__ wbuf, double (&g)[8]) {
+                                               double* __restrict__ wbuf, double (&g)[OC]) {
   for (int o = threadIdx.x; o < WD * NV; o += THREADS) wbuf[o] = W1g[o];
   __syncthreads();
-  const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+  const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
 #pragma unroll
-  for (int c = 0; c < 8; c++) g[c] = 0.0;
+  for (int c = 0; c < OC; c++) g[c] = 0.0;
   for (int i = 0; i < WD; i++) {
     const double d = D[i * TR + r];
 #pragma unroll
-    for (int c = 0; c < 8; c++) g[c] = fma(wbuf[i * NV + cb + c], d, g[c]);
+    for (int c = 0; c < OC; c++) g[c] = fma(wbuf[i * NV + cb + c], d, g[c]);
   }
   __syncthreads();
 }
 
 // store the 8x8 register tile raw into a [feature][row] buffer
-__device__ __forceinline__ void store_tile(double* __restrict__ A, const TileMap& tm, const double (&acc)[8][8]) {
+__device__ __forceinline__ void store_tile(double* __restrict__ A, const TileMap& tm, const double (&acc)[NR][8]) {
 #pragma unroll
   for (int ci = 0; ci < 8; ci++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-      *reinterpret_cast<double2*>(A + tm.col(ci >> 1, ci & 1) * TR + tm.r0 + 16 * j) =
+    for (int j = 0; j < RJ; j++)
+      *reinterpret_cast<double2*>(A + tm.col(ci >> 1, ci & 1) * TR + tm.r0 + 32 * j) =
           make_double2(acc[2 * j][ci], acc[2 * j + 1][ci]);
 }
 
 // a = tanh(a) over a whole buffer: a ROLLED loop (one copy of det_tanh in the instruction stream
-// instead of 64 per layer), 4 independent elements in flight per thread
+// instead of 32 per layer), TI independent elements in flight per thread -- det_tanh is one long
+// dependent FMA chain, the FP64 pipe needs ~16 of them per sub-partition to stay busy
+constexpr int TI = 8;
 __device__ __forceinline__ void tanh_buffer(double* __restrict__ A) {
 #pragma unroll 1
-  for (int o = threadIdx.x; o < ACT_WORDS; o += 4 * THREADS) {
-    const double t0 = det_tanh(A[o]), t1 = det_tanh(A[o + THREADS]), t2 = det_tanh(A[o + 2 * THREADS]),
-                 t3 = det_tanh(A[o + 3 * THREADS]);
-    A[o] = t0;
-    A[o + THREADS] = t1;
-    A[o + 2 * THREADS] = t2;
-    A[o + 3 * THREADS] = t3;
+  for (int o = threadIdx.x; o < ACT_WORDS; o += TI * THREADS) {
+    double t[TI];
+#pragma unroll
+    for (int u = 0; u < TI; u++) t[u] = A[o + u * THREADS];
+#pragma unroll
+    for (int u = 0; u < TI; u++) t[u] = det_tanh(t[u]);
+#pragma unroll
+    for (int u = 0; u < TI; u++) A[o + u * THREADS] = t[u];
   }
 }
 
@@ -180,8 +191,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
   double* A2 = A1 + ACT_WORDS;
   double* wbuf = A2 + ACT_WORDS;
   __shared__ int s_traj[TR], s_stage[TR];
+  __shared__ double s_w4[WD];
   const int n_rows = io.n_rows_dev ? *io.n_rows_dev : io.n_rows;
   const TileMap tm;
+  if (threadIdx.x < WD) s_w4[threadIdx.x] = Wt.W4[threadIdx.x];
   for (int tile = blockIdx.x; (long long)tile * TR < n_rows; tile += gridDim.x) {
     const int base = tile * TR;
     if (threadIdx.x < TR) {
@@ -193,26 +206,35 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     }
     __syncthreads();
     // v = [x ; p] of every row -> A2[k][row] (k < 16); state order is y = [p ; x]
-    for (int o = threadIdx.x; o < NV * TR; o += THREADS) {
-      const int r = o & (TR - 1), k = o / TR;
-      const int m = s_traj[r];
-      double v = 0.0;
-      if (m >= 0) {
-        const int e = (k + NH) & (NV - 1);
-        v = io.y[(size_t)m * io.y_sr + (size_t)e * io.y_se];
-        if (io.add) v = v + io.add[(size_t)(s_stage[r] * NV + e) * io.add_se + (size_t)m * io.add_sr];
-        if (io.add_scalar) v = v + io.add_scalar[m];
+    {
+      double v[NV * TR / THREADS], ad[NV * TR / THREADS];
+#pragma unroll
+      for (int u = 0; u < NV * TR / THREADS; u++) {   // all loads in flight before the first use
+        const int o = threadIdx.x + u * THREADS;
+        const int r = o & (TR - 1), e = ((o / TR) + NH) & (NV - 1);
+        const int m = s_traj[r];
+        v[u] = 0.0;
+        ad[u] = 0.0;
+        if (m >= 0) {
+          v[u] = io.y[(size_t)m * io.y_sr + (size_t)e * io.y_se];
+          if (io.add) ad[u] = io.add[(size_t)(s_stage[r] * NV + e) * io.add_se + (size_t)m * io.add_sr];
+          else if (io.add_scalar) ad[u] = io.add_scalar[m];
+        }
       }
-      A2[k * TR + r] = v;
+#pragma unroll
+      for (int u = 0; u < NV * TR / THREADS; u++) {
+        const int o = threadIdx.x + u * THREADS;
+        A2[o] = (io.add || io.add_scalar) ? v[u] + ad[u] : v[u];
+      }
     }
     __syncthreads();
-    double acc[8][8];
+    double acc[NR][8];
     // ---- layer 1: a1 = tanh(W1 v + b1) -> A0
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const double b = Wt.b1[tm.col(ci >> 1, ci & 1)];
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
     }
     gemm_tile(A2, Wt.W1t, NV, wbuf, tm, acc);
     store_tile(A0, tm, acc);
@@ -224,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const double b = Wt.b2[tm.col(ci >> 1, ci & 1)];
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
     }
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
     store_tile(A1, tm, acc);
@@ -236,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const double b = Wt.b3[tm.col(ci >> 1, ci & 1)];
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++) acc[ri][ci] = b;
+      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
     }
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
     store_tile(A2, tm, acc);
@@ -247,12 +269,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
       const int r = o & (TR - 1), c = o / TR;
       const double a3 = A2[o];
       if (io.act && s_traj[r] >= 0) io.act[((size_t)s_traj[r] * 5 + 2) * WD + c] = a3;
-      A2[o] = Wt.W4[c] * fma(-a3, a3, 1.0);
+      A2[o] = s_w4[c] * fma(-a3, a3, 1.0);
     }
     __syncthreads();
     // ---- reverse through layer 3: q2 = W3^T d3, d2 = q2 (1 - a2^2) -> A1 (in place)
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++) {
+      for (int ri = 0; ri < NR; ri++) {
         const int r = tm.row(ri >> 1, ri & 1);
         const double a2 = A1[c * TR + r], q2 = acc[ri][ci];
         if (io.act && s_traj[r] >= 0) {
@@ -273,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     __syncthreads();
     // ---- reverse through layer 2: q1 = W2^T d2, d1 = q1 (1 - a1^2) -> A0 (in place)
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
@@ -281,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int ri = 0; ri < 8; ri++) {
+      for (int ri = 0; ri < NR; ri++) {
         const int r = tm.row(ri >> 1, ri & 1);
         const double a1 = A0[c * TR + r], q1 = acc[ri][ci];
         if (io.act && s_traj[r] >= 0) {
@@ -293,15 +315,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     }
     __syncthreads();
     // ---- g = W1^T d1 ; ydot = [sign dH/dx ; dH/dp]
-    double g[8];
+    double g[OC];
     output_product(A0, Wt.W1, wbuf, g);
     {
-      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
       const int m = s_traj[r];
       if (m >= 0) {
         const int st = s_stage[r];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < OC; c++) {
           const int e = cb + c;
           const double v = (e < NH) ? io.sign * g[c] : g[c];
           io.out[(size_t)(st * NV + e) * io.out_se + (size_t)m * io.out_sr] = v;
@@ -331,35 +353,42 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
   double* A2 = A1 + ACT_WORDS;
   double* wbuf = A2 + ACT_WORDS;
   __shared__ int s_traj[4];
+  __shared__ double s_w4[WD];
   const int n = io.n_dev ? *io.n_dev : io.n;
   const TileMap tm;
+  if (threadIdx.x < WD) s_w4[threadIdx.x] = Wt.W4[threadIdx.x];
   for (int tile = blockIdx.x; (long long)tile * 4 < n; tile += gridDim.x) {
     if (threadIdx.x < 4) {
       const int q = tile * 4 + threadIdx.x;
       s_traj[threadIdx.x] = q < n ? (io.list ? io.list[q] : q) : -1;
     }
     __syncthreads();
-    // rows of this thread: slot j (trajectory), tangent direction k = r0 + e
-    const double* actj[4];
+    // rows of this thread: row r = r0 + 32 j + e  ->  trajectory slot r / 16 = (r0 >> 4) + 2 j,
+    // tangent direction k = (r0 & 15) + e
+    const int k0 = tm.r0 & 15;
+    const double* actj[RJ];
 #pragma unroll
-    for (int j = 0; j < 4; j++) actj[j] = io.act + (size_t)(s_traj[j] < 0 ? s_traj[0] : s_traj[j]) * 5 * WD;
+    for (int j = 0; j < RJ; j++) {
+      const int sl = (tm.r0 >> 4) + 2 * j;
+      actj[j] = io.act + (size_t)(s_traj[sl] < 0 ? s_traj[0] : s_traj[sl]) * 5 * WD;
+    }
     // ---- ta1[c][row] = (1 - a1^2) W1[c][k] -> A0
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < RJ; j++) {
         const double a1 = actj[j][0 * WD + c];
         const double e1 = fma(-a1, a1, 1.0);
-        *reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 16 * j) =
-            make_double2(e1 * Wt.W1[c * NV + tm.r0], e1 * Wt.W1[c * NV + tm.r0 + 1]);
+        *reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 32 * j) =
+            make_double2(e1 * Wt.W1[c * NV + k0], e1 * Wt.W1[c * NV + k0 + 1]);
       }
     }
     __syncthreads();
-    double acc[8][8];
+    double acc[NR][8];
     // ---- ta2 = (1 - a2^2) (W2 ta1) -> A1
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
@@ -367,35 +396,35 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < RJ; j++) {
         const double a2 = actj[j][1 * WD + c];
         const double e2 = fma(-a2, a2, 1.0);
-        *reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 16 * j) = make_double2(e2 * acc[2 * j][ci], e2 * acc[2 * j + 1][ci]);
+        *reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j) = make_double2(e2 * acc[2 * j][ci], e2 * acc[2 * j + 1][ci]);
       }
     }
     __syncthreads();
     // ---- ta3 = (1 - a3^2) (W3 ta2);  td3 = W4 ((-2 a3) ta3) -> A2
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
-      const double w4 = Wt.W4[c];
+      const double w4 = s_w4[c];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < RJ; j++) {
         const double a3 = actj[j][2 * WD + c];
         const double e3 = fma(-a3, a3, 1.0), m3 = -2.0 * a3;
         const double t0 = e3 * acc[2 * j][ci], t1 = e3 * acc[2 * j + 1][ci];
-        *reinterpret_cast<double2*>(A2 + c * TR + tm.r0 + 16 * j) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
+        *reinterpret_cast<double2*>(A2 + c * TR + tm.r0 + 32 * j) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
       }
     }
     __syncthreads();
     // ---- td2 = (W3^T td3)(1 - a2^2) + q2 ((-2 a2) ta2) -> A1 (in place)
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
@@ -403,10 +432,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < RJ; j++) {
         const double a2 = actj[j][1 * WD + c], q2 = actj[j][4 * WD + c];
         const double e2 = fma(-a2, a2, 1.0), m2 = -2.0 * a2;
-        double2* p = reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 16 * j);
+        double2* p = reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j);
         const double2 ta2 = *p;
         *p = make_double2(fma(q2, m2 * ta2.x, acc[2 * j][ci] * e2), fma(q2, m2 * ta2.y, acc[2 * j + 1][ci] * e2));
       }
@@ -414,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     __syncthreads();
     // ---- td1 = (W2^T td2)(1 - a1^2) + q1 ((-2 a1) ta1) -> A0 (in place)
 #pragma unroll
-    for (int ri = 0; ri < 8; ri++)
+    for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
     gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
@@ -422,26 +451,26 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < RJ; j++) {
         const double a1 = actj[j][0 * WD + c], q1 = actj[j][3 * WD + c];
         const double e1 = fma(-a1, a1, 1.0), m1 = -2.0 * a1;
-        double2* p = reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 16 * j);
+        double2* p = reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 32 * j);
         const double2 ta1 = *p;
         *p = make_double2(fma(q1, m1 * ta1.x, acc[2 * j][ci] * e1), fma(q1, m1 * ta1.y, acc[2 * j + 1][ci] * e1));
       }
     }
     __syncthreads();
     // ---- Hvv[jj][k] = sum_i W1[i][jj] td1[i][row(slot, k)];  J[r][c] = (r < N ? sign : 1) Hvv[r][vc(c)]
-    double g[8];
+    double g[OC];
     output_product(A0, Wt.W1, wbuf, g);
     {
-      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * 8;
+      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
       const int slot = r >> 4, k = r & 15;
       const int m = s_traj[slot];
       if (m >= 0) {
         const int cc = (k + NH) & (NV - 1);   // column of y whose v-index is k
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < OC; c++) {
           const int jj = cb + c;
           const double v = (jj < NH) ? io.sign * g[c] : g[c];
           io.J[(size_t)(jj * NV + cc) * io.J_se + (size_t)m * io.J_sr] = v;

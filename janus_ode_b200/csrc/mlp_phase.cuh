@@ -48,17 +48,30 @@ struct TrajS {   // per-trajectory scalars (array of structs)
   int phase;
 };
 
-// structure-of-arrays vector state: element e of trajectory i at arr[e * M + i]
+// vector state: structure of arrays, element e of trajectory i at arr[e * M + i] (one thread per
+// trajectory: coalesced).  The matrices are arrays of structures -- Jac[i][256] and one LU block per
+// trajectory -- because they are produced / factored by 16 lanes per trajectory, one row per lane.
 struct State {
   long long M;
   int SM;          // stage capacity (MaxNbrStg)
   TrajS* sc;
-  double *y, *f0, *Jac, *cont, *z, *w, *F, *rscal, *temp, *ev, *errs;
-  double *L0a, *L0rd;
-  int* L0piv;
-  double *Lre, *Lim, *Lrdre, *Lrdim;   // complex blocks q = 0..(SM-1)/2-1: [(q * 256 + e) * M + i]
-  int* Lpiv;
+  double *y, *f0, *cont, *z, *w, *F, *rscal, *temp, *ev, *errs;
+  double* Jac;     // [i][16][16]
+  double* LU;      // [i][lud]: L0a[256] L0rd[16] { re[256] im[256] rdre[16] rdim[16] } x (SM-1)/2
+  int* LUpiv;      // [i][lui]: L0piv[16] { piv[16] } x (SM-1)/2
+  int lud, lui;
+  JB_HD double* L0a(long long i) const { return LU + (size_t)i * lud; }
+  JB_HD double* L0rd(long long i) const { return LU + (size_t)i * lud + 256; }
+  JB_HD int* L0piv(long long i) const { return LUpiv + (size_t)i * lui; }
+  JB_HD double* Lre(long long i, int q) const { return LU + (size_t)i * lud + 272 + q * 544; }
+  JB_HD double* Lim(long long i, int q) const { return Lre(i, q) + 256; }
+  JB_HD double* Lrdre(long long i, int q) const { return Lre(i, q) + 512; }
+  JB_HD double* Lrdim(long long i, int q) const { return Lre(i, q) + 528; }
+  JB_HD int* Lpiv(long long i, int q) const { return LUpiv + (size_t)i * lui + 16 + q * 16; }
 };
+JB_HD int lu_doubles(int SM) { return 272 + ((SM - 1) / 2) * 544; }
+JB_HD int lu_ints(int SM) { return 16 + ((SM - 1) / 2) * 16; }
+constexpr unsigned PF_LU_PENDING = 2048u;   // ph_prep(defer_lu): factorisation left to the 16-lane LU kernel
 
 #define JB_FLAG(s, f) (((s).flags & (f)) != 0u)
 JB_HD void set_flag(TrajS& s, unsigned f, bool v) { s.flags = v ? (s.flags | f) : (s.flags & ~f); }
@@ -93,10 +106,11 @@ JB_HD void rlu_factor_g(double* a, double* rd, int* piv, long long M) {
   }
 }
 
-JB_HD void rlu_solve_g(const double* a, const double* rd, const int* piv, long long M, double* b /*stride M*/) {
+JB_HD void rlu_solve_g(const double* a, const double* rd, const int* piv, long long LS /*matrix element stride*/,
+                       long long M /*vector element stride*/, double* b) {
   constexpr int n = MN;
   for (int k = 0; k < n; k++) {
-    const int p = piv[(size_t)k * M];
+    const int p = piv[(size_t)k * LS];
     if (p != k) {
       const double x = b[(size_t)k * M];
       b[(size_t)k * M] = b[(size_t)p * M];
@@ -105,13 +119,13 @@ JB_HD void rlu_solve_g(const double* a, const double* rd, const int* piv, long l
   }
   for (int i = 1; i < n; i++) {
     double s = b[(size_t)i * M];
-    for (int j = 0; j < i; j++) s = fma(-a[(size_t)(i * n + j) * M], b[(size_t)j * M], s);
+    for (int j = 0; j < i; j++) s = fma(-a[(size_t)(i * n + j) * LS], b[(size_t)j * M], s);
     b[(size_t)i * M] = s;
   }
   for (int i = n - 1; i >= 0; i--) {
     double s = b[(size_t)i * M];
-    for (int j = i + 1; j < n; j++) s = fma(-a[(size_t)(i * n + j) * M], b[(size_t)j * M], s);
-    b[(size_t)i * M] = s * rd[(size_t)i * M];
+    for (int j = i + 1; j < n; j++) s = fma(-a[(size_t)(i * n + j) * LS], b[(size_t)j * M], s);
+    b[(size_t)i * M] = s * rd[(size_t)i * LS];
   }
 }
 
@@ -154,10 +168,10 @@ JB_HD void zlu_factor_g(double* re, double* im, double* rdre, double* rdim, int*
 }
 
 JB_HD void zlu_solve_g(const double* re, const double* im, const double* rdre, const double* rdim, const int* piv,
-                       long long M, double* br, double* bi) {
+                       long long LS, long long M, double* br, double* bi) {
   constexpr int n = MN;
   for (int k = 0; k < n; k++) {
-    const int p = piv[(size_t)k * M];
+    const int p = piv[(size_t)k * LS];
     if (p != k) {
       double x = br[(size_t)k * M];
       br[(size_t)k * M] = br[(size_t)p * M];
@@ -170,7 +184,7 @@ JB_HD void zlu_solve_g(const double* re, const double* im, const double* rdre, c
   for (int i = 1; i < n; i++) {
     double sr = br[(size_t)i * M], si = bi[(size_t)i * M];
     for (int j = 0; j < i; j++) {
-      const double lr = re[(size_t)(i * n + j) * M], li = im[(size_t)(i * n + j) * M];
+      const double lr = re[(size_t)(i * n + j) * LS], li = im[(size_t)(i * n + j) * LS];
       const double bj = br[(size_t)j * M], cj = bi[(size_t)j * M];
       sr = fma(li, cj, fma(-lr, bj, sr));
       si = fma(-li, bj, fma(-lr, cj, si));
@@ -181,12 +195,12 @@ JB_HD void zlu_solve_g(const double* re, const double* im, const double* rdre, c
   for (int i = n - 1; i >= 0; i--) {
     double sr = br[(size_t)i * M], si = bi[(size_t)i * M];
     for (int j = i + 1; j < n; j++) {
-      const double ur = re[(size_t)(i * n + j) * M], ui = im[(size_t)(i * n + j) * M];
+      const double ur = re[(size_t)(i * n + j) * LS], ui = im[(size_t)(i * n + j) * LS];
       const double bj = br[(size_t)j * M], cj = bi[(size_t)j * M];
       sr = fma(ui, cj, fma(-ur, bj, sr));
       si = fma(-ui, bj, fma(-ur, cj, si));
     }
-    const double rr = rdre[(size_t)i * M], ri = rdim[(size_t)i * M];
+    const double rr = rdre[(size_t)i * LS], ri = rdim[(size_t)i * LS];
     br[(size_t)i * M] = fma(-si, ri, sr * rr);
     bi[(size_t)i * M] = fma(si, rr, sr * ri);
   }
@@ -283,39 +297,40 @@ JB_HD void newton_begin(TrajS& s, const RadauParams& P) {
 template <int S_>
 JB_HD void decomrc_g(const State& S, const TrajS& s, long long i) {
   using Tab = RadauTab<S_>;
-  const long long M = S.M;
   const double rh = 1.0 / s.h;
   const double valp0 = Tab::ValP(0) * rh;
+  const double* Jac = S.Jac + (size_t)i * MN * MN;
+  double* a0 = S.L0a(i);
   for (int r = 0; r < MN; r++)
     for (int c = 0; c < MN; c++) {
-      const double J = S.Jac[(size_t)(r * MN + c) * M + i];
-      S.L0a[(size_t)(r * MN + c) * M + i] = (r == c) ? (valp0 - J) : -J;
+      const double J = Jac[r * MN + c];
+      a0[r * MN + c] = (r == c) ? (valp0 - J) : -J;
     }
-  rlu_factor_g(S.L0a + i, S.L0rd + i, S.L0piv + i, M);
+  rlu_factor_g(a0, S.L0rd(i), S.L0piv(i), 1);
 #pragma unroll
   for (int q = 1; q <= (S_ - 1) / 2; q++) {
     const double al = Tab::ValP(2 * q - 1) * rh, be = Tab::ValP(2 * q) * rh;
-    double* re = S.Lre + (size_t)(q - 1) * MN * MN * M + i;
-    double* im = S.Lim + (size_t)(q - 1) * MN * MN * M + i;
+    double* re = S.Lre(i, q - 1);
+    double* im = S.Lim(i, q - 1);
     for (int r = 0; r < MN; r++)
       for (int c = 0; c < MN; c++) {
-        const double J = S.Jac[(size_t)(r * MN + c) * M + i];
-        re[(size_t)(r * MN + c) * M] = (r == c) ? (al - J) : -J;
-        im[(size_t)(r * MN + c) * M] = (r == c) ? be : 0.0;
+        const double J = Jac[r * MN + c];
+        re[r * MN + c] = (r == c) ? (al - J) : -J;
+        im[r * MN + c] = (r == c) ? be : 0.0;
       }
-    zlu_factor_g(re, im, S.Lrdre + (size_t)(q - 1) * MN * M + i, S.Lrdim + (size_t)(q - 1) * MN * M + i,
-                 S.Lpiv + (size_t)(q - 1) * MN * M + i, M);
+    zlu_factor_g(re, im, S.Lrdre(i, q - 1), S.Lrdim(i, q - 1), S.Lpiv(i, q - 1), 1);
   }
 }
 
 // attempt_step up to the first stage evaluation (radau.m:827-911)
 template <int S_>
-JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long long i) {
+JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long long i, bool defer_lu) {
   using Tab = RadauTab<S_>;
   constexpr int si = (S_ - 1) / 2;
   const long long M = S.M;
   if (JB_FLAG(s, PF_NEED_LU)) {
-    decomrc_g<S_>(S, s, i);
+    if (defer_lu) s.flags |= PF_LU_PENDING;   // h and the stage count are final from here on
+    else decomrc_g<S_>(S, s, i);
     s.st[ST_DEC] += 1;
     s.work += W_lu(S_, MN);
     s.flags &= ~PF_NEED_LU;
@@ -374,15 +389,28 @@ JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long lo
   newton_begin<S_>(s, P);
 }
 
+// the factorisation ph_prep(defer_lu = true) left pending, scalar form (the GPU runs lu16_kernel instead)
+JB_HD void ph_lu(const State& S, long long i) {
+  TrajS& s = S.sc[i];
+  if (!JB_FLAG(s, PF_LU_PENDING)) return;
+  s.flags &= ~PF_LU_PENDING;
+  switch (s.NbrStg) {
+    case 1: decomrc_g<1>(S, s, i); break;
+    case 3: decomrc_g<3>(S, s, i); break;
+    case 5: decomrc_g<5>(S, s, i); break;
+    default: decomrc_g<7>(S, s, i); break;
+  }
+}
+
 // the rest of pass_head (Jacobian bookkeeping, order selection radau.m:766-824), then attempt_begin
-JB_HD void ph_prep(const State& S, const RadauParams& P, long long i) {
+JB_HD void ph_prep(const State& S, const RadauParams& P, long long i, bool defer_lu = false) {
   const long long M = S.M;
   TrajS s = S.sc[i];
   if (s.phase != PH_WANT_JAC && s.phase != PH_PREP) return;
   if (s.phase == PH_WANT_JAC) {
     bool nanf = false;
     for (int k = 0; k < MN * MN; k++) {
-      const double v = S.Jac[(size_t)k * M + i];
+      const double v = S.Jac[(size_t)i * MN * MN + k];
       nanf = nanf || (v != v);
     }
     if (nanf) {
@@ -415,10 +443,10 @@ JB_HD void ph_prep(const State& S, const RadauParams& P, long long i) {
     }
   }
   switch (s.NbrStg) {
-    case 1: attempt_begin<1>(S, P, s, i); break;
-    case 3: attempt_begin<3>(S, P, s, i); break;
-    case 5: attempt_begin<5>(S, P, s, i); break;
-    default: attempt_begin<7>(S, P, s, i); break;
+    case 1: attempt_begin<1>(S, P, s, i, defer_lu); break;
+    case 3: attempt_begin<3>(S, P, s, i, defer_lu); break;
+    case 5: attempt_begin<5>(S, P, s, i, defer_lu); break;
+    default: attempt_begin<7>(S, P, s, i, defer_lu); break;
   }
   S.sc[i] = s;
 }
@@ -525,7 +553,7 @@ JB_HD void estrad_a(const State& S, const RadauParams& P, TrajS& s, long long i)
     S.temp[(size_t)e * M + i] = sum;
     S.ev[(size_t)e * M + i] = S.f0[(size_t)e * M + i] + sum;
   }
-  rlu_solve_g(S.L0a + i, S.L0rd + i, S.L0piv + i, M, S.ev + i);
+  rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.ev + i);
   s.err = scaled_err(S, P, i);
   if (s.err >= 1.0 && (JB_FLAG(s, PF_FIRST) || JB_FLAG(s, PF_REJECT))) {
     S.errs[i] = s.err;   // sic: the scalar err is added to every component (radaute_impl.hpp:1951)
@@ -541,7 +569,7 @@ template <int S_>
 JB_HD void estrad_b(const State& S, const RadauParams& P, TrajS& s, long long i) {
   const long long M = S.M;
   for (int e = 0; e < MN; e++) S.ev[(size_t)e * M + i] = S.ev[(size_t)e * M + i] + S.temp[(size_t)e * M + i];
-  rlu_solve_g(S.L0a + i, S.L0rd + i, S.L0piv + i, M, S.ev + i);
+  rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.ev + i);
   s.err = scaled_err(S, P, i);
   controller_a<S_>(S, P, s, i);
 }
@@ -593,7 +621,7 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
   {  // Solvrad
     const double valp0 = Tab::ValP(0) * rh;
     for (int e = 0; e < MN; e++) S.z[(size_t)e * M + i] = fma(-valp0, S.w[(size_t)e * M + i], S.z[(size_t)e * M + i]);
-    rlu_solve_g(S.L0a + i, S.L0rd + i, S.L0piv + i, M, S.z + i);
+    rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.z + i);
 #pragma unroll
     for (int q = 1; q <= (S_ - 1) / 2; q++) {
       const int q2 = 2 * q - 1, q3 = 2 * q;
@@ -605,9 +633,8 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
         S.z[(size_t)(q2 * MN + e) * M + i] = a;
         S.z[(size_t)(q3 * MN + e) * M + i] = b;
       }
-      zlu_solve_g(S.Lre + (size_t)(q - 1) * MN * MN * M + i, S.Lim + (size_t)(q - 1) * MN * MN * M + i,
-                  S.Lrdre + (size_t)(q - 1) * MN * M + i, S.Lrdim + (size_t)(q - 1) * MN * M + i,
-                  S.Lpiv + (size_t)(q - 1) * MN * M + i, M, S.z + (size_t)q2 * MN * M + i, S.z + (size_t)q3 * MN * M + i);
+      zlu_solve_g(S.Lre(i, q - 1), S.Lim(i, q - 1), S.Lrdre(i, q - 1), S.Lrdim(i, q - 1), S.Lpiv(i, q - 1), 1, M,
+                  S.z + (size_t)q2 * MN * M + i, S.z + (size_t)q3 * MN * M + i);
     }
   }
   s.st[ST_SOL] += 1;

@@ -14,12 +14,13 @@
 #include "solver_impl.cuh"
 #include "mlp_kernels.cuh"
 #include "mlp_phase.cuh"
+#include "lu16.cuh"
 
 namespace jb {
 namespace mlp {
 
 constexpr int NPAR = 2 + WD * NV + WD + 2 * (WD * WD + WD) + WD + 1;
-enum { C_ACTIVE = 0, C_JAC, C_ROWS_A, C_TRAJ_A, C_ROWS_B, C_TRAJ_B, C_ERR, C_F0, C_N };
+enum { C_ACTIVE = 0, C_JAC, C_ROWS_A, C_TRAJ_A, C_ROWS_B, C_TRAJ_B, C_ERR, C_F0, C_LU, C_N };
 
 struct Ctx {
   double* d_w = nullptr;   // all weight matrices, both orientations
@@ -30,7 +31,7 @@ struct Ctx {
   void* pool = nullptr;
   double* d_act = nullptr;
   int *d_rows[2] = {nullptr, nullptr}, *d_trajs[2] = {nullptr, nullptr};
-  int *d_jac = nullptr, *d_err = nullptr, *d_f0 = nullptr, *d_cnt = nullptr;
+  int *d_jac = nullptr, *d_err = nullptr, *d_f0 = nullptr, *d_lu = nullptr, *d_cnt = nullptr;
   int* h_cnt = nullptr;    // pinned
 };
 
@@ -67,13 +68,86 @@ __device__ __forceinline__ void enqueue(const State& S, long long i, int* cnt, i
     f0_list[append(&cnt[C_F0], 1)] = (int)i * 8;
   }
 }
-__global__ void prep_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* rows, int* trajs) {
+__global__ void prep_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* rows, int* trajs,
+                            int* lu_list) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= S.M) return;
   const int ph = S.sc[i].phase;
   if (ph != PH_WANT_JAC && ph != PH_PREP) return;
-  ph_prep(S, P, i);
+  ph_prep(S, P, i, true);
+  if (S.sc[i].flags & PF_LU_PENDING) lu_list[append(&cnt[C_LU], 1)] = (int)i;
   enqueue(S, i, cnt, C_ROWS_A, C_TRAJ_A, rows, trajs, nullptr, nullptr);
+}
+
+// DecomRC (radaute_impl.hpp:1502-1625) for the trajectories ph_prep left pending: 16 lanes per
+// trajectory, one matrix row per lane (lu16.cuh); block = 256 threads = 16 trajectories
+template <int S_>
+__device__ __forceinline__ void decomrc16(const State& S, long long i, double h, unsigned mask, int l) {
+  using Tab = RadauTab<S_>;
+  const double rh = 1.0 / h;
+  double J[16];
+  {
+    const double2* src = reinterpret_cast<const double2*>(S.Jac + (size_t)i * 256 + l * 16);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const double2 v = src[j];
+      J[2 * j] = v.x;
+      J[2 * j + 1] = v.y;
+    }
+  }
+  {
+    const double valp0 = Tab::ValP(0) * rh;
+    double a[16], rd = 0.0;
+    int piv = 0;
+#pragma unroll
+    for (int c = 0; c < 16; c++) a[c] = (c == l) ? (valp0 - J[c]) : -J[c];
+    rlu16_factor(mask, l, a, rd, piv);
+    double2* dst = reinterpret_cast<double2*>(S.L0a(i) + l * 16);
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[j] = make_double2(a[2 * j], a[2 * j + 1]);
+    S.L0rd(i)[l] = rd;
+    S.L0piv(i)[l] = piv;
+  }
+#pragma unroll
+  for (int q = 1; q <= (S_ - 1) / 2; q++) {
+    const double al = Tab::ValP(2 * q - 1) * rh, be = Tab::ValP(2 * q) * rh;
+    double re[16], im[16], rdre = 0.0, rdim = 0.0;
+    int piv = 0;
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+      re[c] = (c == l) ? (al - J[c]) : -J[c];
+      im[c] = (c == l) ? be : 0.0;
+    }
+    zlu16_factor(mask, l, re, im, rdre, rdim, piv);
+    double2* dr = reinterpret_cast<double2*>(S.Lre(i, q - 1) + l * 16);
+    double2* di = reinterpret_cast<double2*>(S.Lim(i, q - 1) + l * 16);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      dr[j] = make_double2(re[2 * j], re[2 * j + 1]);
+      di[j] = make_double2(im[2 * j], im[2 * j + 1]);
+    }
+    S.Lrdre(i, q - 1)[l] = rdre;
+    S.Lrdim(i, q - 1)[l] = rdim;
+    S.Lpiv(i, q - 1)[l] = piv;
+  }
+}
+
+__global__ void __launch_bounds__(256) lu16_kernel(const State S, const int* __restrict__ lu_list, int n) {
+  const int slot = blockIdx.x * 16 + (threadIdx.x >> 4);
+  if (slot >= n) return;   // whole half-warp leaves together
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  const int l = threadIdx.x & 15;
+  const long long i = lu_list[slot];
+  const double h = S.sc[i].h;
+  const int ns = S.sc[i].NbrStg;
+  __syncwarp(mask);
+  if (l == 0) S.sc[i].flags &= ~PF_LU_PENDING;
+  switch (ns) {
+    case 1: decomrc16<1>(S, i, h, mask, l); break;
+    case 3: decomrc16<3>(S, i, h, mask, l); break;
+    case 5: decomrc16<5>(S, i, h, mask, l); break;
+    default: decomrc16<7>(S, i, h, mask, l); break;
+  }
 }
 __global__ void newton_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in, int n_in,
                               int* cnt, int c_rows, int c_traj, int* rows_out, int* trajs_out, int* err_list, int* f0_list) {
@@ -117,9 +191,9 @@ static void free_workspace(Ctx* C) {
   cudaFree(C->pool);
   cudaFree(C->d_act);
   for (int k = 0; k < 2; k++) { cudaFree(C->d_rows[k]); cudaFree(C->d_trajs[k]); }
-  cudaFree(C->d_jac); cudaFree(C->d_err); cudaFree(C->d_f0);
+  cudaFree(C->d_jac); cudaFree(C->d_err); cudaFree(C->d_f0); cudaFree(C->d_lu);
   C->pool = nullptr; C->d_act = nullptr; C->d_rows[0] = C->d_rows[1] = C->d_trajs[0] = C->d_trajs[1] = nullptr;
-  C->d_jac = C->d_err = C->d_f0 = nullptr;
+  C->d_jac = C->d_err = C->d_f0 = C->d_lu = nullptr;
   C->cap = 0;
 }
 
@@ -132,9 +206,10 @@ static int ensure(Handle* H, long long M, bool need_state) {
   const int nq = (SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1;
   JB_CUDA(cudaMalloc(&C->d_act, sizeof(double) * 5 * WD * (size_t)M));
   if (need_state) {
-    const size_t per_d = MN * 6 + MN * MN * 2 + (size_t)SM * MN * 4 + 1 + MN + (size_t)nq * (2 * MN * MN + 2 * MN);
-    const size_t per_i = MN + (size_t)nq * MN;
-    const size_t bytes = sizeof(TrajS) * (size_t)M + 256 + sizeof(double) * per_d * (size_t)M + sizeof(int) * per_i * (size_t)M;
+    (void)nq;
+    const size_t per_d = MN * 5 + MN * MN + (size_t)SM * MN * 4 + 1 + (size_t)lu_doubles(SM);
+    const size_t per_i = (size_t)lu_ints(SM);
+    const size_t bytes = sizeof(TrajS) * (size_t)M + 1024 + sizeof(double) * per_d * (size_t)M + sizeof(int) * per_i * (size_t)M;
     JB_CUDA(cudaMalloc(&C->pool, bytes));
     char* p = (char*)C->pool;
     State& S = C->S;
@@ -143,14 +218,14 @@ static int ensure(Handle* H, long long M, bool need_state) {
     S.sc = (TrajS*)p;
     p += ((sizeof(TrajS) * (size_t)M + 255) / 256) * 256;
     double* d = (double*)p;
-    auto take = [&](size_t per) { double* r = d; d += per * (size_t)M; return r; };
-    S.y = take(MN); S.f0 = take(MN); S.Jac = take(MN * MN); S.cont = take(SM * MN); S.z = take(SM * MN);
+    auto take = [&](size_t per) { double* r = d; d += ((per * (size_t)M + 1) / 2) * 2; return r; };   // 16-byte aligned
+    S.y = take(MN); S.f0 = take(MN); S.cont = take(SM * MN); S.z = take(SM * MN);
     S.w = take(SM * MN); S.F = take(SM * MN); S.rscal = take(MN); S.temp = take(MN); S.ev = take(MN); S.errs = take(1);
-    S.L0a = take(MN * MN); S.L0rd = take(MN);
-    S.Lre = take(nq * MN * MN); S.Lim = take(nq * MN * MN); S.Lrdre = take(nq * MN); S.Lrdim = take(nq * MN);
-    int* ip = (int*)d;
-    S.L0piv = ip;
-    S.Lpiv = ip + (size_t)MN * M;
+    S.Jac = take(MN * MN);
+    S.lud = lu_doubles(SM);
+    S.lui = lu_ints(SM);
+    S.LU = take(S.lud);
+    S.LUpiv = (int*)d;
     for (int k = 0; k < 2; k++) {
       JB_CUDA(cudaMalloc(&C->d_rows[k], sizeof(int) * (size_t)SM * M));
       JB_CUDA(cudaMalloc(&C->d_trajs[k], sizeof(int) * (size_t)M));
@@ -158,6 +233,7 @@ static int ensure(Handle* H, long long M, bool need_state) {
     JB_CUDA(cudaMalloc(&C->d_jac, sizeof(int) * (size_t)M));
     JB_CUDA(cudaMalloc(&C->d_err, sizeof(int) * (size_t)M));
     JB_CUDA(cudaMalloc(&C->d_f0, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C->d_lu, sizeof(int) * (size_t)M));
   }
   C->cap = M;
   C->cap_SM = SM;
@@ -213,14 +289,18 @@ static int solve(Handle* H, const double* y0, const double* tspan, long long M, 
     if ((rc = read_counters(C, st))) return rc;
     if (C->h_cnt[C_ACTIVE] == 0) break;
     if (C->h_cnt[C_JAC] > 0) {
-      HessIO hio{C->d_jac, nullptr, C->h_cnt[C_JAC], C->d_act, S.Jac, 1, M, P.sign};
+      HessIO hio{C->d_jac, nullptr, C->h_cnt[C_JAC], C->d_act, S.Jac, MN * MN, 1, P.sign};
       if ((rc = launch_hess(H, hio, C->h_cnt[C_JAC], st))) return rc;
     }
-    prep_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_rows[0], C->d_trajs[0]);
+    prep_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_rows[0], C->d_trajs[0], C->d_lu);
     H->launches += 1;
     int cur = 0;
-    for (;;) {
+    for (int it = 0;; it++) {
       if ((rc = read_counters(C, st))) return rc;
+      if (it == 0 && C->h_cnt[C_LU] > 0) {
+        lu16_kernel<<<(unsigned)((C->h_cnt[C_LU] + 15) / 16), 256, 0, st>>>(S, C->d_lu, C->h_cnt[C_LU]);
+        H->launches += 1;
+      }
       const int n_rows = C->h_cnt[cur ? C_ROWS_B : C_ROWS_A], n_traj = C->h_cnt[cur ? C_TRAJ_B : C_TRAJ_A];
       if (n_traj == 0) break;
       GradIO gi{C->d_rows[cur], nullptr, n_rows, S.y, 1, M, S.z, 1, M, nullptr, S.F, 1, M, nullptr, P.sign};

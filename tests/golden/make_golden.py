@@ -57,6 +57,12 @@ def main():
         solve_case(f"c3_pmp_bang_{tag}", "vdp_pmp_bang", configs.c3_pmp(M=32, control="bangbang", fixed_order=fixed),
                    problems.vdp_pmp(problems.ctrl_bangbang(1.0, 100.0), 1.0, +1), n_py=2, rtol=2e-3, dacc=0.1)
         # (discontinuous control: the switching times are tolerance-level quantities)
+    # C4 (MLP Hamiltonian, Ny = 16): the Python restatement integrates the autograd dynamics (the engine the
+    # reference differentiates H with) on the first rows
+    mlp = ham.MLPHamiltonian(N=8, width=128, seed=0)
+    for fixed in (True, False):
+        solve_case(f"c4_mlp_{'s3' if fixed else 'var'}", "mlp", configs.c4_mlp(M=16, fixed_order=fixed),
+                   problems.from_hamiltonian(mlp, sign=-1), n_py=2)
     # Hamiltonian adaptor golden: autograd (reference engine) on seeded points
     torch.manual_seed(0)
     y = torch.rand(32, 4, dtype=torch.float64) * 4 - 2

@@ -162,13 +162,12 @@ extern "C" int hostsim_mlp_solve(mlp_dyns_fn dyns, mlp_jac_fn jacf, const double
   const int sign = (int)P.sign, SM = P.MaxNbrStg, nq = (SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1;
   std::vector<TrajS> sc(M);
   auto dv = [&](size_t per) { return std::vector<double>(per * M, 0.0); };
+  (void)nq;
   auto y = dv(MN), f0 = dv(MN), Jac = dv(MN * MN), cont = dv(SM * MN), z = dv(SM * MN), w = dv(SM * MN), F = dv(SM * MN),
-       rscal = dv(MN), temp = dv(MN), ev = dv(MN), errs = dv(1), L0a = dv(MN * MN), L0rd = dv(MN), Lre = dv(nq * MN * MN),
-       Lim = dv(nq * MN * MN), Lrdre = dv(nq * MN), Lrdim = dv(nq * MN);
-  std::vector<int> L0piv(MN * M), Lpiv((size_t)nq * MN * M);
-  State S{M, SM, sc.data(), y.data(), f0.data(), Jac.data(), cont.data(), z.data(), w.data(), F.data(), rscal.data(),
-          temp.data(), ev.data(), errs.data(), L0a.data(), L0rd.data(), L0piv.data(), Lre.data(), Lim.data(),
-          Lrdre.data(), Lrdim.data(), Lpiv.data()};
+       rscal = dv(MN), temp = dv(MN), ev = dv(MN), errs = dv(1), LU = dv(lu_doubles(SM));
+  std::vector<int> LUpiv((size_t)lu_ints(SM) * M);
+  State S{M, SM, sc.data(), y.data(), f0.data(), cont.data(), z.data(), w.data(), F.data(), rscal.data(),
+          temp.data(), ev.data(), errs.data(), Jac.data(), LU.data(), LUpiv.data(), lu_doubles(SM), lu_ints(SM)};
   double yy[MN], ff[MN], JJ[MN * MN];
   auto eval_at = [&](long long i, const double* add /*SoA offset or null*/, double scalar, double* out) {
     for (int e = 0; e < MN; e++) {
@@ -193,11 +192,12 @@ extern "C" int hostsim_mlp_solve(mlp_dyns_fn dyns, mlp_jac_fn jacf, const double
       if (sc[i].phase == PH_WANT_JAC) {
         for (int e = 0; e < MN; e++) yy[e] = S.y[(size_t)e * M + i];
         jacf(5, par, sign, MN, 1, yy, JJ);
-        for (int k = 0; k < MN * MN; k++) S.Jac[(size_t)k * M + i] = JJ[k];
+        for (int k = 0; k < MN * MN; k++) S.Jac[(size_t)i * MN * MN + k] = JJ[k];
       }
     }
     if (!active) break;
-    for (long long i = 0; i < M; i++) ph_prep(S, P, i);
+    for (long long i = 0; i < M; i++) ph_prep(S, P, i, (i & 1) != 0);   // odd rows: deferred factorisation (GPU protocol)
+    for (long long i = 0; i < M; i++) ph_lu(S, i);
     for (;;) {
       long long n = 0;
       for (long long i = 0; i < M; i++)

@@ -1,0 +1,128 @@
+"""GPU parity of the MLP-Hamiltonian path (config 4): public API -> C ABI -> tile-GEMM kernels + phase
+kernels, bit for bit against the oracle in mirror arithmetic; 1e-8 against reference arithmetic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import janus_ode_b200 as jb
+from janus_ode_b200 import configs
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def gpu_solve(cfg, host=False):
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    y0, ts = cfg["y0"], cfg["tspan"]
+    if not host:
+        y0, ts = y0.to(DEV), ts.to(DEV)
+    r = jb.RadauTe(dyn, dyn.jacobian, ts, y0, cfg["options"])
+    res = r.solve()
+    torch.cuda.synchronize()
+    return dict(y=r.y.cpu().numpy(), t=r.t.cpu().numpy(), h=r.h.cpu().numpy(), res=res.cpu().numpy().astype(np.int32),
+                stats=r.stats.raw.cpu().numpy(), nstg=r.nstg.cpu().numpy(), launches=r.gpu_launches,
+                work=r.work.cpu().numpy())
+
+
+def oracle_solve(cfg, arith):
+    return c_oracle.solve("mlp", np.array(cfg["ham"].params), cfg["sign"], cfg["y0"].numpy(), cfg["tspan"].numpy(),
+                          cfg["options"], arith=arith)
+
+
+def assert_bitwise(a, b):
+    for k in ("y", "t", "h", "res", "stats", "nstg"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("M", [1, 3, 63, 64, 65, 200])
+@pytest.mark.parametrize("bias", [0.0, 0.25])
+def test_stage_evaluation_bitwise(M, bias):
+    """mlp_grad_kernel / mlp_hess_kernel (ragged tiles included) == scalar mirror, every bit."""
+    H = jb.MlpHamiltonian(8, 128, 0, bias_scale=bias)
+    par = np.array(H.params)
+    torch.manual_seed(M)
+    y = 0.7 * torch.randn(M, 16, dtype=torch.float64)
+    for sign in (-1, +1):
+        dyn = jb.HamiltonianSystem(H, sign)
+        f = dyn(None, y.to(DEV)).cpu().numpy()
+        J = dyn.jacobian(None, y.to(DEV)).cpu().numpy()
+        assert np.array_equal(f, c_oracle.eval_dyns("mlp", par, sign, y.numpy(), arith="mirror"))
+        assert np.array_equal(J, c_oracle.eval_jac("mlp", par, sign, y.numpy(), arith="mirror"))
+
+
+def test_stage_evaluation_vs_reference_arithmetic_and_saturation():
+    H = jb.MlpHamiltonian(8, 128, 0)
+    par = np.array(H.params)
+    torch.manual_seed(1)
+    y = torch.cat([0.5 * torch.randn(40, 16, dtype=torch.float64), 50.0 * torch.randn(8, 16, dtype=torch.float64)])
+    dyn = jb.HamiltonianSystem(H, -1)
+    f = dyn(None, y.to(DEV)).cpu().numpy()
+    J = dyn.jacobian(None, y.to(DEV)).cpu().numpy()
+    assert np.allclose(f, c_oracle.eval_dyns("mlp", par, -1, y.numpy()), rtol=1e-11, atol=1e-13)
+    assert np.allclose(J, c_oracle.eval_jac("mlp", par, -1, y.numpy()), rtol=1e-10, atol=1e-12)
+    assert np.array_equal(f, c_oracle.eval_dyns("mlp", par, -1, y.numpy(), arith="mirror"))   # saturated tanh rows too
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+@pytest.mark.parametrize("M", [1, 65, 300])
+def test_solve_bitwise_vs_mirror(fixed, M):
+    cfg = configs.c4_mlp(M=M, fixed_order=fixed)
+    g = gpu_solve(cfg)
+    assert_bitwise(g, oracle_solve(cfg, "mirror"))
+    assert (g["res"] == 0).all() and g["launches"] > 10 and (g["work"] > 0).all()
+
+
+@pytest.mark.parametrize("opts", [dict(RelTol=1e-9, AbsTol=1e-12), dict(NbrStg=1, MinNbrStg=1, MaxNbrStg=7, RelTol=1e-4, AbsTol=1e-6),
+                                  dict(Start_Newt=True), dict(MaxNbrStep=5), dict(Gustafsson=False)])
+def test_solve_options_bitwise(opts):
+    cfg = configs.c4_mlp(M=96)
+    for k, v in opts.items():
+        setattr(cfg["options"], k, v)
+    g = gpu_solve(cfg)
+    assert_bitwise(g, oracle_solve(cfg, "mirror"))
+    if "MaxNbrStep" in opts:
+        assert (g["res"] == 3).any()
+
+
+def test_solve_host_buffers_and_reverse_time():
+    cfg = configs.c4_mlp(M=130)
+    cfg["tspan"] = torch.tensor([1.0, 0.5], dtype=torch.float64).repeat(130, 1)
+    g = gpu_solve(cfg, host=True)
+    assert_bitwise(g, oracle_solve(cfg, "mirror"))
+    assert np.all(g["t"] == 0.5)
+
+
+def test_solve_vs_reference_arithmetic():
+    cfg = configs.c4_mlp(M=256)
+    g, o = gpu_solve(cfg), oracle_solve(cfg, "reference")
+    rel = np.abs(g["y"] - o["y"]).max(1) / np.abs(o["y"]).max(1)
+    assert rel.max() < 1e-8
+    assert (g["stats"][:, 5] == o["stats"][:, 5]).mean() >= 0.9
+
+
+@pytest.mark.parametrize("tag", ["s3", "var"])
+def test_golden_c4(tag):
+    gd = np.load(os.path.join(GOLD, f"c4_mlp_{tag}.npz"))
+    cfg = configs.c4_mlp(M=gd["y0"].shape[0], fixed_order=(tag == "s3"))
+    g = gpu_solve(cfg)
+    assert np.array_equal(g["y"], gd["mir_y"]) and np.array_equal(g["stats"], gd["mir_stats"])
+    assert np.allclose(g["y"], gd["ref_y"], rtol=1e-8, atol=1e-12)
+
+
+def test_unsupported_and_invalid():
+    H = jb.MlpHamiltonian(8, 128, 0)
+    dyn = jb.HamiltonianSystem(H, -1)
+    y0 = torch.zeros(4, 16, dtype=torch.float64, device=DEV)
+    tgrid = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64, device=DEV).repeat(4, 1)
+    with pytest.raises(jb.JanusB200Error, match="not available"):
+        jb.RadauTe(dyn, None, tgrid, y0, jb.OptionsTe()).solve()
+    bad = jb.Hamiltonian("mlp", 5, 8, H.params[:100])
+    with pytest.raises(ValueError, match="parameters"):
+        jb.RadauTe(jb.HamiltonianSystem(bad, -1), None, tgrid[:, [0, 2]].contiguous(), y0, jb.OptionsTe()).solve()
+    small = jb.Hamiltonian("mlp", 5, 8, (4.0, 128.0) + H.params[2:])
+    with pytest.raises(jb.JanusB200Error, match="N = 8"):
+        jb.RadauTe(jb.HamiltonianSystem(small, -1), None, tgrid[:, [0, 2]].contiguous(), y0, jb.OptionsTe()).solve()
