@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--M", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 = the headline (stiff van der Pol, BASELINE.json configs[1]); c4 = MLP Hamiltonian "
+                         "(configs[3]: 4-layer width-128 MLP, Ny = 16) -- reported under profiles/, not the driver's line")
     ap.add_argument("--fixed-order", action="store_true", help="fixed 3 stages instead of the default 3/5/7")
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -53,8 +56,18 @@ def parse():
     return ap.parse_args()
 
 
+def make_cfg(a, M, lo=0, hi=None):
+    from janus_ode_b200 import configs
+    if a.workload == "c4":
+        return configs.c4_mlp(M=M, fixed_order=a.fixed_order, lo=lo, hi=hi), "mlp"
+    return configs.c2_vdp(M=M, fixed_order=a.fixed_order, lo=lo, hi=hi), "vdp"
+
+
 def workload_name(a):
     order = "fixed s=3" if a.fixed_order else "variable order 3/5/7 (reference default)"
+    if a.workload == "c4":
+        return (f"config 4: MLP Hamiltonian 16->128->128->128->1 tanh (N=8, Ny=16), {a.M} trajectories/GPU fp64, "
+                f"RelTol 1e-6 AbsTol 1e-9, t in [0,1], canonical sign, {order}")
     return (f"config 2: stiff van der Pol Hamiltonian form mu=1000, {a.M} trajectories/GPU fp64, "
             f"RelTol 1e-6 AbsTol 1e-9, t in [0,(3-2ln2)mu], {order}")
 
@@ -111,12 +124,12 @@ def cpu_reference_run(a, rows, threads=0):
     import numpy as np
     from janus_ode_b200 import configs
     from oracle import c_oracle
-    cfg = configs.c2_vdp(M=a.M * a.gpus, fixed_order=a.fixed_order, lo=0, hi=rows)
+    cfg, pb = make_cfg(a, a.M * a.gpus, 0, rows)
     y0, ts = cfg["y0"].numpy(), cfg["tspan"].numpy()
     # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: do not inherit that)
     cores = len(os.sched_getaffinity(0)) if threads <= 0 else threads
     t0 = time.perf_counter()
-    o = c_oracle.solve("vdp", list(cfg["ham"].params), cfg["sign"], y0, ts, cfg["options"], nthreads=cores,
+    o = c_oracle.solve(pb, list(cfg["ham"].params), cfg["sign"], y0, ts, cfg["options"], nthreads=cores,
                        arith="reference")
     dt = time.perf_counter() - t0
     acc = int(o["stats"][:, 5].sum())
@@ -132,8 +145,9 @@ def batched_reference_run(a, rows):
     from oracle import ham, radau_batched
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    cfg = configs.c2_vdp(M=a.M * a.gpus, fixed_order=a.fixed_order, lo=0, hi=rows)
-    ode, jac = radau_batched.hamiltonian_callbacks(ham.H_vdp(cfg["ham"].params[0]), None, None, cfg["sign"])
+    cfg, pb = make_cfg(a, a.M * a.gpus, 0, rows)
+    H = ham.MLPHamiltonian(N=8, width=128, seed=0) if pb == "mlp" else ham.H_vdp(cfg["ham"].params[0])
+    ode, jac = radau_batched.hamiltonian_callbacks(H, None, None, cfg["sign"])
     t0 = time.perf_counter()
     r = radau_batched.RadauBatched(ode, jac, cfg["tspan"], cfg["y0"], cfg["options"])
     res = r.solve()
@@ -148,7 +162,8 @@ def run_reference(a):
     if rank != 0:
         return
     if a.ref_kind == "batched":
-        rows = a.cpu_sample or 16384
+        rows = a.cpu_sample or (16384 if a.workload == "c2" else 256)
+        srows = 65536 if a.workload == "c2" else 4096
         rates, times = [], []
         for _ in range(max(a.steps, 1)):
             r, dt, acc, cores = batched_reference_run(a, rows)
@@ -157,11 +172,11 @@ def run_reference(a):
         value = sum(rates) / len(rates)
         from oracle import c_oracle
         c_oracle.build()
-        s_rate, s_dt, _, s_cores = cpu_reference_run(a, 65536)
+        s_rate, s_dt, _, s_cores = cpu_reference_run(a, srows)
         out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                "warmup": 0, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
                "cpu_baseline_strong": {"value": s_rate, "unit": UNIT, "cores": s_cores, "kind": "port",
-                                       "sample": f"first 65536 rows, {s_dt:.1f} s; scalar C restatement, one trajectory per "
+                                       "sample": f"first {srows} rows, {s_dt:.1f} s; scalar C restatement, one trajectory per "
                                                  f"OpenMP thread (oracle/c) -- a stronger bar than the reference's design"},
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload_name(a), "sample": f"first {rows} rows of the same seeded batch"},
@@ -176,10 +191,11 @@ def run_reference(a):
     from oracle import c_oracle
     c_oracle.build()
     rows = a.cpu_sample or 65536
-    rate0, dt0, _, cores = cpu_reference_run(a, 8192)               # size the sample: ~10 s per step
-    rows = a.cpu_sample or int(min(a.M * a.gpus, max(8192, 8192 * 10.0 / max(dt0, 1e-3))))
+    r0 = 8192 if a.workload == "c2" else 1024
+    rate0, dt0, _, cores = cpu_reference_run(a, r0)                 # size the sample: ~10 s per step
+    rows = a.cpu_sample or int(min(a.M * a.gpus, max(r0, r0 * 10.0 / max(dt0, 1e-3))))
     for _ in range(a.warmup and 1):
-        cpu_reference_run(a, min(rows, 8192))
+        cpu_reference_run(a, min(rows, r0))
     rates, times = [], []
     for _ in range(a.steps):
         r, dt, acc, cores = cpu_reference_run(a, rows)
@@ -219,7 +235,7 @@ def run_ours(a):
 
     # shard: rows rank, rank+world, ... of the seeded global batch
     Mg = a.M * world
-    cfg = configs.c2_vdp(M=Mg, fixed_order=a.fixed_order)
+    cfg, _ = make_cfg(a, Mg)
     idx = configs.shard_rows(Mg, rank, world)
     y0_h = cfg["y0"][idx].contiguous().pin_memory()
     ts_h = cfg["tspan"][idx].contiguous().pin_memory()
@@ -316,14 +332,15 @@ def run_ours(a):
         if not a.no_cpu_baseline and world == 1:
             from oracle import c_oracle
             c_oracle.build()
-            rate0, dt0, _, cores = cpu_reference_run(a, 8192)
-            rows = a.cpu_sample or int(min(Mg, max(8192, 8192 * 12.0 / max(dt0, 1e-3))))
+            r0 = 8192 if a.workload == "c2" else 1024
+            rate0, dt0, _, cores = cpu_reference_run(a, r0)
+            rows = a.cpu_sample or int(min(Mg, max(r0, r0 * 12.0 / max(dt0, 1e-3))))
             rate, dt, _, cores = cpu_reference_run(a, rows)
             out["cpu_baseline_strong"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                           "sample": f"first {rows} rows of the workload, {dt:.1f} s; scalar C restatement, one "
                                                     f"trajectory per OpenMP thread (oracle/c, reference arithmetic) -- a "
                                                     f"stronger bar than the reference's masked-tensor design"}
-            brows = 8192
+            brows = 8192 if a.workload == "c2" else 256
             brate, bdt, _, bcores = batched_reference_run(a, brows)
             out["cpu_baseline"] = {"value": brate, "unit": UNIT, "cores": bcores, "kind": "port",
                                    "sample": f"first {brows} rows of the workload, {bdt:.1f} s; masked-tensor torch restatement "

@@ -191,4 +191,111 @@ JB_HD void zlu_solve(const ZLU<N>& L, double* br, double* bi) {
   }
 }
 
+
+// ------------------------------------------------------------------ complex factors in shared memory
+// Optional placement (JB_LC_SMEM, device code): the complex L\U of a trajectory is written once
+// per factorisation and read once per Newton iteration -- 40 doubles per block for n = 4, which
+// the 5- and 7-stage steppers otherwise spill to local memory (more than the L1 holds at 256
+// threads per SM).  Word e of block b of this thread lives at
+//   jb_lc_smem[(b * WORDS + e) * blockDim.x + threadIdx.x]     (conflict-free),
+// the pivots stay in registers.  Same arithmetic as zlu_solve, bit for bit.
+template <int N>
+struct ZLUS {
+  static constexpr int WORDS = 2 * N * N + 2 * N;
+  int piv[N];
+  int base;   // b * WORDS
+#if !(defined(__CUDA_ARCH__) && defined(JB_LC_SMEM))
+  ZLU<N> host;   // host pass / placement disabled: a plain copy
+#endif
+};
+
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+__device__ __forceinline__ double& lc_smem(int e) {
+  extern __shared__ double jb_lc_smem[];
+  return jb_lc_smem[e * blockDim.x + threadIdx.x];
+}
+#endif
+
+template <int N>
+JB_HD void zlus_store(ZLUS<N>& S, const ZLU<N>& L, int block) {
+  S.base = block * ZLUS<N>::WORDS;
+#pragma unroll
+  for (int k = 0; k < N; k++) S.piv[k] = L.piv[k];
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+#pragma unroll
+  for (int k = 0; k < N * N; k++) {
+    lc_smem(S.base + k) = L.re[k];
+    lc_smem(S.base + N * N + k) = L.im[k];
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    lc_smem(S.base + 2 * N * N + k) = L.rdre[k];
+    lc_smem(S.base + 2 * N * N + N + k) = L.rdim[k];
+  }
+#else
+  S.host = L;
+#endif
+}
+
+template <int N>
+JB_HD void zlu_solve(const ZLUS<N>& S, double* br, double* bi) {
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+  const int b0 = S.base;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (S.piv[k] == i);
+      double x = br[k], y = br[i];
+      br[k] = sw ? y : x;
+      br[i] = sw ? x : y;
+      x = bi[k];
+      y = bi[i];
+      bi[k] = sw ? y : x;
+      bi[i] = sw ? x : y;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) {
+      const double lr = lc_smem(b0 + i * N + j), li = lc_smem(b0 + N * N + i * N + j);
+      sr = fma(li, bi[j], fma(-lr, br[j], sr));
+      si = fma(-li, br[j], fma(-lr, bi[j], si));
+    }
+    br[i] = sr;
+    bi[i] = si;
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = i + 1; j < N; j++) {
+      const double ur = lc_smem(b0 + i * N + j), ui = lc_smem(b0 + N * N + i * N + j);
+      sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+      si = fma(-ui, br[j], fma(-ur, bi[j], si));
+    }
+    const double rr = lc_smem(b0 + 2 * N * N + i), ri = lc_smem(b0 + 2 * N * N + N + i);
+    br[i] = fma(-si, ri, sr * rr);
+    bi[i] = fma(si, rr, sr * ri);
+  }
+#else
+  zlu_solve<N>(S.host, br, bi);
+#endif
+}
+
+// how many of the (s-1)/2 complex blocks of an s-stage stepper are parked in shared memory
+template <int N, int S>
+struct LcPlace {
+#if defined(JB_LC_SMEM)
+  static constexpr int NQ = (S - 1) / 2;
+  static constexpr int NS = (N <= 4) ? (NQ < 2 ? NQ : 2) : 0;   // 40 words per block and thread for n = 4
+#else
+  static constexpr int NQ = (S - 1) / 2;
+  static constexpr int NS = 0;
+#endif
+  static constexpr int NR = NQ - NS;
+};
+
 }  // namespace jb

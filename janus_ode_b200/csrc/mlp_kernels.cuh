@@ -12,7 +12,7 @@
 // One CTA = 256 threads = two warps per SM sub-partition, each thread owns a 4x8 register tile of
 // the 64x128 layer output (32 independent DFMA chains: the FP64 pipe is the only bound); the
 // activations of the tile stay in shared memory ([feature][row], 3 x 64 KB) from the first layer
-// to the last, weights stream from L2 in 8-row chunks through a cp.async double buffer.
+// to the last, weights stream from L2 in 16-row chunks through a cp.async double buffer.
 //
 // ARITHMETIC CONTRACT (mirrored by oracle/c/radau_oracle.c mlp_eval_mirror): every dot product is
 // ONE fma chain in increasing index order, seeded with the bias (forward) or 0.0 (transposed);
@@ -28,11 +28,11 @@ namespace jb {
 namespace mlp {
 
 constexpr int TR = 64;        // rows per CTA tile
-constexpr int KC = 8;         // weight rows per cp.async chunk
+constexpr int KC = 16;        // weight rows per cp.async chunk (two barriers per chunk: fewer, larger chunks)
 constexpr int THREADS = 256;     // 2 warps per SM sub-partition: a lone warp cannot re-issue DFMAs back to back
 constexpr int RJ = 2;            // row groups per thread: register tile = (2 RJ) rows x 8 columns
 constexpr int ACT_WORDS = WD * TR;                                      // one activation buffer
-constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 208 KB
+constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 224 KB
 
 // device-resident weights of one Hamiltonian (both orientations of every matrix, k-major for the
 // GEMM that consumes it)
@@ -346,6 +346,16 @@ struct HessIO {
   double sign;
 };
 
+// the epilogue operands of one layer (saved activations of this thread's 8 columns x RJ
+// trajectories), loaded BEFORE the layer's GEMM so that their L2 latency hides behind it
+__device__ __forceinline__ void prefetch_act(const double* const (&actj)[RJ], int layer, const TileMap& tm,
+                                             double (&v)[RJ][8]) {
+#pragma unroll
+  for (int j = 0; j < RJ; j++)
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) v[j][ci] = __ldg(actj[j] + layer * WD + tm.col(ci >> 1, ci & 1));
+}
+
 __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, const HessIO io) {
   extern __shared__ __align__(16) double smem[];
   double* A0 = smem;
@@ -391,13 +401,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    double pa[RJ][8], pq[RJ][8];
+    prefetch_act(actj, 1, tm, pa);
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
       for (int j = 0; j < RJ; j++) {
-        const double a2 = actj[j][1 * WD + c];
+        const double a2 = pa[j][ci];
         const double e2 = fma(-a2, a2, 1.0);
         *reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j) = make_double2(e2 * acc[2 * j][ci], e2 * acc[2 * j + 1][ci]);
       }
@@ -408,6 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    prefetch_act(actj, 2, tm, pa);
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
@@ -415,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
       const double w4 = s_w4[c];
 #pragma unroll
       for (int j = 0; j < RJ; j++) {
-        const double a3 = actj[j][2 * WD + c];
+        const double a3 = pa[j][ci];
         const double e3 = fma(-a3, a3, 1.0), m3 = -2.0 * a3;
         const double t0 = e3 * acc[2 * j][ci], t1 = e3 * acc[2 * j + 1][ci];
         *reinterpret_cast<double2*>(A2 + c * TR + tm.r0 + 32 * j) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
@@ -427,13 +440,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    prefetch_act(actj, 1, tm, pa);
+    prefetch_act(actj, 4, tm, pq);
     gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
       for (int j = 0; j < RJ; j++) {
-        const double a2 = actj[j][1 * WD + c], q2 = actj[j][4 * WD + c];
+        const double a2 = pa[j][ci], q2 = pq[j][ci];
         const double e2 = fma(-a2, a2, 1.0), m2 = -2.0 * a2;
         double2* p = reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j);
         const double2 ta2 = *p;
@@ -446,13 +461,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     for (int ri = 0; ri < NR; ri++)
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    prefetch_act(actj, 0, tm, pa);
+    prefetch_act(actj, 3, tm, pq);
     gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
 #pragma unroll
     for (int ci = 0; ci < 8; ci++) {
       const int c = tm.col(ci >> 1, ci & 1);
 #pragma unroll
       for (int j = 0; j < RJ; j++) {
-        const double a1 = actj[j][0 * WD + c], q1 = actj[j][3 * WD + c];
+        const double a1 = pa[j][ci], q1 = pq[j][ci];
         const double e1 = fma(-a1, a1, 1.0), m1 = -2.0 * a1;
         double2* p = reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 32 * j);
         const double2 ta1 = *p;

@@ -83,7 +83,10 @@ struct Traj {
   int st[8];
   long long work;  // algorithmic FLOPs spent on this trajectory (SURVEY.md 8d formula, see W_* below)
   RLU<NY> L0;
-  ZLU<NY> Lc[(SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1];
+  // complex blocks q = 1..(SM-1)/2: the first LcPlace::NS in shared memory (lu.cuh ZLUS), the rest here
+  using Place = LcPlace<NY, SM>;
+  ZLUS<NY> LcS[Place::NS > 0 ? Place::NS : 1];
+  ZLU<NY> Lc[Place::NR > 0 ? Place::NR : 1];
 };
 
 JB_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -157,7 +160,10 @@ JB_HD void decomrc(Traj<NY, SM>& T) {
 #pragma unroll
   for (int q = 1; q <= (S - 1) / 2; q++) {
     const double al = Tab::ValP(2 * q - 1) * rh, be = Tab::ValP(2 * q) * rh;
-    ZLU<NY>& Z = T.Lc[q - 1];
+    constexpr int NS = LcPlace<NY, SM>::NS;
+    const bool parked = (q - 1) < NS;
+    ZLU<NY> Ztmp;
+    ZLU<NY>& Z = parked ? Ztmp : T.Lc[(q - 1 - NS) > 0 ? (q - 1 - NS) : 0];
 #pragma unroll
     for (int i = 0; i < NY; i++)
 #pragma unroll
@@ -166,6 +172,7 @@ JB_HD void decomrc(Traj<NY, SM>& T) {
         Z.im[i * NY + j] = (i == j) ? be : 0.0;
       }
     zlu_factor<NY>(Z);
+    if (parked) zlus_store<NY>(T.LcS[(q - 1) < NS ? (q - 1) : 0], Ztmp, q - 1);
   }
 }
 
@@ -335,7 +342,9 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* o
           z[q2 * NY + i] = a;
           z[q3 * NY + i] = b;
         }
-        zlu_solve<NY>(T.Lc[q - 1], &z[q2 * NY], &z[q3 * NY]);
+        constexpr int NS = LcPlace<NY, SM>::NS;
+        if ((q - 1) < NS) zlu_solve(T.LcS[(q - 1) < NS ? (q - 1) : 0], &z[q2 * NY], &z[q3 * NY]);
+        else zlu_solve<NY>(T.Lc[(q - 1 - NS) > 0 ? (q - 1 - NS) : 0], &z[q2 * NY], &z[q3 * NY]);
       }
     }
     T.st[ST_SOL] += 1;

@@ -327,6 +327,12 @@ struct Handle {
   void* ext = nullptr;   // per-Hamiltonian context (MLP Hamiltonian: device weights + phase workspace, tu_mlp.cu)
 };
 
+// dynamic shared memory of a kernel whose stepper parks complex LU blocks there (lu.cuh: ZLUS)
+template <int NY, int S>
+inline size_t lc_smem_bytes(int threads) {
+  return sizeof(double) * (size_t)LcPlace<NY, S>::NS * (size_t)ZLUS<NY>::WORDS * (size_t)threads;
+}
+
 template <class Ham, int SM, bool VAR>
 int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                         double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
@@ -337,14 +343,16 @@ int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, 
   auto kern = dense.tout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
 #endif
   int bps = 0;
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, 0));
+  const size_t smem = lc_smem_bytes<Ham::NV, SM>(JB_THREADS);
+  if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, smem));
   if (bps < 1) bps = 1;
   long long blocks = (long long)H->sm_count * bps;
   const long long need = (M + JB_THREADS - 1) / JB_THREADS;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
-  kern<<<(unsigned)blocks, JB_THREADS, 0, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
+  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
@@ -376,13 +384,15 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, int base, int count, int max_pas
 #endif
   constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, 0));
+  const size_t smem = lc_smem_bytes<Ham::NV, S>(TH);
+  if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, smem));
   if (bps < 1) bps = 1;
   if (S >= 5 && bps > EpochCfg<S>::minb) bps = EpochCfg<S>::minb;
   long long blocks = (long long)H->sm_count * bps;
   const long long need = ((long long)count + TH - 1) / TH;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, TH, 0, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
+  kern<<<(unsigned)blocks, TH, smem, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
                                         H->d_counter + k, ws.tag, o.y_out, o.t_out, o.h_out, o.res, o.stats, o.nstg,
                                         o.work, tspan, dense, stop_on_accept);
   JB_CUDA(cudaGetLastError());
