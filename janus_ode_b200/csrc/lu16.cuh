@@ -95,5 +95,65 @@ __device__ __forceinline__ void zlu16_factor(unsigned mask, int l, double (&re)[
   }
 }
 
+
+// ---- solves with the factors above: lane l holds row l of L\U, 1/U_ll, the pivot of step l and
+// element l of the right-hand side.  Column-oriented substitution, one broadcast + one fma per lane
+// and column: forward  b_i -= l_ij b_j  (j = 0..14, rows i > j: row i accumulates in increasing j,
+// as the scalar code), backward  x_j = b_j / u_jj, b_i -= u_ij x_j  (j = 15..0, rows i < j) --
+// the same sequences as rlu_solve_g / zlu_solve_g (mlp_phase.cuh).
+__device__ __forceinline__ void rlu16_solve(unsigned mask, int l, const double (&a)[16], double rd, int piv, double& b) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int p = __shfl_sync(mask, piv, k, 16);
+    const int src = (l == k) ? p : (l == p) ? k : l;
+    b = __shfl_sync(mask, b, src, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 15; j++) {
+    const double bj = __shfl_sync(mask, b, j, 16);
+    if (l > j) b = fma(-a[j], bj, b);
+  }
+#pragma unroll
+  for (int j = 15; j >= 0; j--) {
+    const double xj = __shfl_sync(mask, b * rd, j, 16);
+    if (l == j) b = xj;
+    if (l < j) b = fma(-a[j], xj, b);
+  }
+}
+
+__device__ __forceinline__ void zlu16_solve(unsigned mask, int l, const double (&re)[16], const double (&im)[16],
+                                            double rdre, double rdim, int piv, double& br, double& bi) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int p = __shfl_sync(mask, piv, k, 16);
+    const int src = (l == k) ? p : (l == p) ? k : l;
+    br = __shfl_sync(mask, br, src, 16);
+    bi = __shfl_sync(mask, bi, src, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 15; j++) {
+    const double xr = __shfl_sync(mask, br, j, 16), xi = __shfl_sync(mask, bi, j, 16);
+    if (l > j) {
+      const double nr = fma(im[j], xi, fma(-re[j], xr, br));
+      bi = fma(-im[j], xr, fma(-re[j], xi, bi));
+      br = nr;
+    }
+  }
+#pragma unroll
+  for (int j = 15; j >= 0; j--) {
+    const double qr = fma(-bi, rdim, br * rdre), qi = fma(bi, rdre, br * rdim);
+    const double xr = __shfl_sync(mask, qr, j, 16), xi = __shfl_sync(mask, qi, j, 16);
+    if (l == j) {
+      br = xr;
+      bi = xi;
+    }
+    if (l < j) {
+      const double nr = fma(im[j], xi, fma(-re[j], xr, br));
+      bi = fma(-im[j], xr, fma(-re[j], xi, bi));
+      br = nr;
+    }
+  }
+}
+
 }  // namespace mlp
 }  // namespace jb

@@ -77,8 +77,9 @@ constexpr unsigned PF_LU_PENDING = 2048u;   // ph_prep(defer_lu): factorisation 
 JB_HD void set_flag(TrajS& s, unsigned f, bool v) { s.flags = v ? (s.flags | f) : (s.flags & ~f); }
 
 // ------------------------------------------------------------------ small dense LU on SoA columns
-// a[(r * n + c) * M]: same operations, same order as lu.cuh (rows exchanged for real instead of
-// by predicated selects: identical values)
+// Factorisation and forward substitution: same operations, same order as lu.cuh (rows exchanged for
+// real instead of by predicated selects: identical values).  Back substitution: column-oriented
+// (ARITHMETIC CONTRACT of the Ny = 16 path, mirrored by oracle/c rlu_solve / zlu_solve for n = 16).
 JB_HD void rlu_factor_g(double* a, double* rd, int* piv, long long M) {
   constexpr int n = MN;
   for (int k = 0; k < n; k++) {
@@ -122,10 +123,12 @@ JB_HD void rlu_solve_g(const double* a, const double* rd, const int* piv, long l
     for (int j = 0; j < i; j++) s = fma(-a[(size_t)(i * n + j) * LS], b[(size_t)j * M], s);
     b[(size_t)i * M] = s;
   }
-  for (int i = n - 1; i >= 0; i--) {
-    double s = b[(size_t)i * M];
-    for (int j = i + 1; j < n; j++) s = fma(-a[(size_t)(i * n + j) * LS], b[(size_t)j * M], s);
-    b[(size_t)i * M] = s * rd[(size_t)i * LS];
+  // column-oriented back substitution (the order the 16-lane solve of lu16.cuh produces; also the
+  // order of reference-BLAS dtrsm): unknown j is finished, then every row above it is updated
+  for (int j = n - 1; j >= 0; j--) {
+    const double xj = b[(size_t)j * M] * rd[(size_t)j * LS];
+    b[(size_t)j * M] = xj;
+    for (int i = 0; i < j; i++) b[(size_t)i * M] = fma(-a[(size_t)(i * n + j) * LS], xj, b[(size_t)i * M]);
   }
 }
 
@@ -192,17 +195,18 @@ JB_HD void zlu_solve_g(const double* re, const double* im, const double* rdre, c
     br[(size_t)i * M] = sr;
     bi[(size_t)i * M] = si;
   }
-  for (int i = n - 1; i >= 0; i--) {
-    double sr = br[(size_t)i * M], si = bi[(size_t)i * M];
-    for (int j = i + 1; j < n; j++) {
+  for (int j = n - 1; j >= 0; j--) {   // column-oriented, see rlu_solve_g
+    const double rr = rdre[(size_t)j * LS], ri = rdim[(size_t)j * LS];
+    const double bj = br[(size_t)j * M], cj = bi[(size_t)j * M];
+    const double xr = fma(-cj, ri, bj * rr), xi = fma(cj, rr, bj * ri);
+    br[(size_t)j * M] = xr;
+    bi[(size_t)j * M] = xi;
+    for (int i = 0; i < j; i++) {
       const double ur = re[(size_t)(i * n + j) * LS], ui = im[(size_t)(i * n + j) * LS];
-      const double bj = br[(size_t)j * M], cj = bi[(size_t)j * M];
-      sr = fma(ui, cj, fma(-ur, bj, sr));
-      si = fma(-ui, bj, fma(-ur, cj, si));
+      const double sr = br[(size_t)i * M], si = bi[(size_t)i * M];
+      br[(size_t)i * M] = fma(ui, xi, fma(-ur, xr, sr));
+      bi[(size_t)i * M] = fma(-ui, xr, fma(-ur, xi, si));
     }
-    const double rr = rdre[(size_t)i * LS], ri = rdim[(size_t)i * LS];
-    br[(size_t)i * M] = fma(-si, ri, sr * rr);
-    bi[(size_t)i * M] = fma(si, rr, sr * ri);
   }
 }
 
@@ -586,14 +590,15 @@ JB_HD void ph_estrad_b(const State& S, const RadauParams& P, long long i) {
   S.sc[i] = s;
 }
 
-// one simplified-Newton iteration after its stage evaluations (radau.m:932-1018)
+// one simplified-Newton iteration after its stage evaluations (radau.m:932-1018), in three parts so
+// that the GPU can run the linear solves with 16 lanes per trajectory (lu16.cuh) between them:
+//   newton_pre    z = TI f, right-hand sides of Solvrad        (false: NaN, trajectory finished)
+//   newton_solves the real + complex triangular solves          (scalar form; GPU: solve16_kernel)
+//   newton_post   norms, convergence logic, w += z, z = T w, then Estrad / controller or next iteration
 template <int S_>
-JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long i) {
+JB_HD bool newton_pre(const State& S, const RadauParams& P, TrajS& s, long long i) {
   using Tab = RadauTab<S_>;
-  constexpr int si = (S_ - 1) / 2;
   const long long M = S.M;
-  const int Nit = nit_of(S_, P.MaxNbrNewton);
-  const double FNewt = P.FNewt[si];
   const double rh = 1.0 / s.h;
   bool nanf = false;
   for (int k = 0; k < S_ * MN; k++) {
@@ -603,7 +608,7 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
   if (nanf) {
     s.res = 2;
     finish(s);
-    return;
+    return false;
   }
   s.st[ST_FCN] += S_;
   for (int e = 0; e < MN; e++) {
@@ -618,10 +623,9 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
       S.z[(size_t)(j * MN + e) * M + i] = acc;
     }
   }
-  {  // Solvrad
+  {  // Solvrad right-hand sides
     const double valp0 = Tab::ValP(0) * rh;
     for (int e = 0; e < MN; e++) S.z[(size_t)e * M + i] = fma(-valp0, S.w[(size_t)e * M + i], S.z[(size_t)e * M + i]);
-    rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.z + i);
 #pragma unroll
     for (int q = 1; q <= (S_ - 1) / 2; q++) {
       const int q2 = 2 * q - 1, q3 = 2 * q;
@@ -633,10 +637,28 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
         S.z[(size_t)(q2 * MN + e) * M + i] = a;
         S.z[(size_t)(q3 * MN + e) * M + i] = b;
       }
-      zlu_solve_g(S.Lre(i, q - 1), S.Lim(i, q - 1), S.Lrdre(i, q - 1), S.Lrdim(i, q - 1), S.Lpiv(i, q - 1), 1, M,
-                  S.z + (size_t)q2 * MN * M + i, S.z + (size_t)q3 * MN * M + i);
     }
   }
+  return true;
+}
+
+template <int S_>
+JB_HD void newton_solves(const State& S, long long i) {
+  const long long M = S.M;
+  rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.z + i);
+#pragma unroll
+  for (int q = 1; q <= (S_ - 1) / 2; q++)
+    zlu_solve_g(S.Lre(i, q - 1), S.Lim(i, q - 1), S.Lrdre(i, q - 1), S.Lrdim(i, q - 1), S.Lpiv(i, q - 1), 1, M,
+                S.z + (size_t)(2 * q - 1) * MN * M + i, S.z + (size_t)(2 * q) * MN * M + i);
+}
+
+template <int S_>
+JB_HD void newton_post(const State& S, const RadauParams& P, TrajS& s, long long i) {
+  using Tab = RadauTab<S_>;
+  constexpr int si = (S_ - 1) / 2;
+  const long long M = S.M;
+  const int Nit = nit_of(S_, P.MaxNbrNewton);
+  const double FNewt = P.FNewt[si];
   s.st[ST_SOL] += 1;
   s.work += W_newt(S_, MN, (int)FLOPS_F);
   double NewNrm = 0.0;
@@ -708,6 +730,13 @@ JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long
   estrad_a<S_>(S, P, s, i);
 }
 
+template <int S_>
+JB_HD void newton_step(const State& S, const RadauParams& P, TrajS& s, long long i) {
+  if (!newton_pre<S_>(S, P, s, i)) return;
+  newton_solves<S_>(S, i);
+  newton_post<S_>(S, P, s, i);
+}
+
 JB_HD void ph_newton(const State& S, const RadauParams& P, long long i) {
   TrajS s = S.sc[i];
   if (s.phase != PH_NEWTON) return;
@@ -716,6 +745,32 @@ JB_HD void ph_newton(const State& S, const RadauParams& P, long long i) {
     case 3: newton_step<3>(S, P, s, i); break;
     case 5: newton_step<5>(S, P, s, i); break;
     default: newton_step<7>(S, P, s, i); break;
+  }
+  S.sc[i] = s;
+}
+
+// the GPU's split of ph_newton around solve16_kernel
+JB_HD void ph_newton_pre(const State& S, const RadauParams& P, long long i) {
+  TrajS s = S.sc[i];
+  if (s.phase != PH_NEWTON) return;
+  bool ok;
+  switch (s.NbrStg) {
+    case 1: ok = newton_pre<1>(S, P, s, i); break;
+    case 3: ok = newton_pre<3>(S, P, s, i); break;
+    case 5: ok = newton_pre<5>(S, P, s, i); break;
+    default: ok = newton_pre<7>(S, P, s, i); break;
+  }
+  (void)ok;
+  S.sc[i] = s;
+}
+JB_HD void ph_newton_post(const State& S, const RadauParams& P, long long i) {
+  TrajS s = S.sc[i];
+  if (s.phase != PH_NEWTON) return;   // finished by ph_newton_pre (NaN in the stage values)
+  switch (s.NbrStg) {
+    case 1: newton_post<1>(S, P, s, i); break;
+    case 3: newton_post<3>(S, P, s, i); break;
+    case 5: newton_post<5>(S, P, s, i); break;
+    default: newton_post<7>(S, P, s, i); break;
   }
   S.sc[i] = s;
 }

@@ -3,7 +3,7 @@
 // (mlp_kernels.cuh).  One pass = one attempted step of every active trajectory:
 //
 //   head_kernel  ->  [mlp_hess_kernel on the trajectories that need a Jacobian]  ->  prep_kernel
-//   repeat { mlp_grad_kernel on the (trajectory, stage) rows still iterating ; newton_kernel }
+//   repeat { mlp_grad_kernel on the (trajectory, stage) rows still iterating ; newton_pre / solve16 / newton_post }
 //   [mlp_grad_kernel at y + err ; estrad_b_kernel]      (first-step retry of the error estimate)
 //   mlp_grad_kernel at the accepted points (saves the activations the next Jacobian needs) ; accept_b_kernel
 //
@@ -149,12 +149,64 @@ __global__ void __launch_bounds__(256) lu16_kernel(const State S, const int* __r
     default: decomrc16<7>(S, i, h, mask, l); break;
   }
 }
-__global__ void newton_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in, int n_in,
-                              int* cnt, int c_rows, int c_traj, int* rows_out, int* trajs_out, int* err_list, int* f0_list) {
+// one Newton iteration = newton_pre_kernel (z = TI f, right-hand sides; one thread per trajectory)
+//                      -> solve16_kernel (Solvrad's triangular solves; 16 lanes per trajectory, lu16.cuh)
+//                      -> newton_post_kernel (norms, convergence logic, Estrad / controller; one thread)
+__global__ void newton_pre_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
+                                  int n_in) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_in) return;
+  ph_newton_pre(S, P, trajs_in[k]);
+}
+__global__ void __launch_bounds__(256) solve16_kernel(const State S, const int* __restrict__ trajs_in, int n_in) {
+  const int slot = blockIdx.x * 16 + (threadIdx.x >> 4);
+  if (slot >= n_in) return;
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  const int l = threadIdx.x & 15;
+  const long long i = trajs_in[slot];
+  if (S.sc[i].phase != PH_NEWTON) return;   // finished by newton_pre (uniform over the 16 lanes)
+  const int nq = (S.sc[i].NbrStg - 1) / 2;
+  const long long M = S.M;
+  {
+    double a[16];
+    const double2* src = reinterpret_cast<const double2*>(S.L0a(i) + l * 16);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const double2 v = src[j];
+      a[2 * j] = v.x;
+      a[2 * j + 1] = v.y;
+    }
+    double b = S.z[(size_t)l * M + i];
+    rlu16_solve(mask, l, a, S.L0rd(i)[l], S.L0piv(i)[l], b);
+    S.z[(size_t)l * M + i] = b;
+  }
+  for (int q = 0; q < nq; q++) {
+    double re[16], im[16];
+    const double2* sr = reinterpret_cast<const double2*>(S.Lre(i, q) + l * 16);
+    const double2* si = reinterpret_cast<const double2*>(S.Lim(i, q) + l * 16);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const double2 v = sr[j], u = si[j];
+      re[2 * j] = v.x;
+      re[2 * j + 1] = v.y;
+      im[2 * j] = u.x;
+      im[2 * j + 1] = u.y;
+    }
+    double* zr = S.z + (size_t)((2 * q + 1) * MN + l) * M + i;
+    double* zi = S.z + (size_t)((2 * q + 2) * MN + l) * M + i;
+    double br = *zr, bi = *zi;
+    zlu16_solve(mask, l, re, im, S.Lrdre(i, q)[l], S.Lrdim(i, q)[l], S.Lpiv(i, q)[l], br, bi);
+    *zr = br;
+    *zi = bi;
+  }
+}
+__global__ void newton_post_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
+                                   int n_in, int* cnt, int c_rows, int c_traj, int* rows_out, int* trajs_out, int* err_list,
+                                   int* f0_list) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_in) return;
   const long long i = trajs_in[k];
-  ph_newton(S, P, i);
+  ph_newton_post(S, P, i);
   enqueue(S, i, cnt, c_rows, c_traj, rows_out, trajs_out, err_list, f0_list);
 }
 __global__ void estrad_b_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ err_list, int n,
@@ -307,10 +359,12 @@ static int solve(Handle* H, const double* y0, const double* tspan, long long M, 
       if ((rc = launch_grad(H, gi, n_rows, st))) return rc;
       const int nxt = cur ^ 1;
       JB_CUDA(cudaMemsetAsync(C->d_cnt + (nxt ? C_ROWS_B : C_ROWS_A), 0, 2 * sizeof(int), st));
-      newton_kernel<<<blocks(n_traj), 128, 0, st>>>(S, P, C->d_trajs[cur], n_traj, C->d_cnt, nxt ? C_ROWS_B : C_ROWS_A,
-                                                    nxt ? C_TRAJ_B : C_TRAJ_A, C->d_rows[nxt], C->d_trajs[nxt], C->d_err,
-                                                    C->d_f0);
-      H->launches += 1;
+      newton_pre_kernel<<<blocks(n_traj), 128, 0, st>>>(S, P, C->d_trajs[cur], n_traj);
+      solve16_kernel<<<(unsigned)((n_traj + 15) / 16), 256, 0, st>>>(S, C->d_trajs[cur], n_traj);
+      newton_post_kernel<<<blocks(n_traj), 128, 0, st>>>(S, P, C->d_trajs[cur], n_traj, C->d_cnt, nxt ? C_ROWS_B : C_ROWS_A,
+                                                         nxt ? C_TRAJ_B : C_TRAJ_A, C->d_rows[nxt], C->d_trajs[nxt],
+                                                         C->d_err, C->d_f0);
+      H->launches += 3;
       cur = nxt;
     }
     if (C->h_cnt[C_ERR] > 0) {

@@ -551,6 +551,17 @@ static void rlu_solve(int n, const rlu_t *L, double *b) {
     for (int j = 0; j < i; j++) s = FMA(-a[i * n + j], b[j], s);
     b[i] = s;
   }
+  if (g_mirror && n == NYMAX) {
+    /* Ny = 16 (MLP Hamiltonian path, csrc/lu16.cuh): column-oriented back substitution, the order a
+     * lane-parallel triangular solve (and reference-BLAS dtrsm) produces: unknown j is finished, then
+     * every row above it is updated                                                              */
+    for (int j = n - 1; j >= 0; j--) {
+      const double xj = b[j] * L->rd[j];
+      b[j] = xj;
+      for (int i = 0; i < j; i++) b[i] = fma(-a[i * n + j], xj, b[i]);
+    }
+    return;
+  }
   for (int i = n - 1; i >= 0; i--) {
     double s = b[i];
     for (int j = i + 1; j < n; j++) s = FMA(-a[i * n + j], b[j], s);
@@ -617,6 +628,20 @@ static void zlu_solve(int n, const zlu_t *L, double *br, double *bi) {
       }
     }
     br[i] = sr; bi[i] = si;
+  }
+  if (g_mirror && n == NYMAX) {   /* column-oriented, see rlu_solve */
+    for (int j = n - 1; j >= 0; j--) {
+      const double rr = L->rdre[j], ri = L->rdim[j];
+      const double xr = fma(-bi[j], ri, br[j] * rr), xi = fma(bi[j], rr, br[j] * ri);
+      br[j] = xr; bi[j] = xi;
+      for (int i = 0; i < j; i++) {
+        const double ur = ar[i * n + j], ui = ai[i * n + j];
+        const double nr = fma(ui, xi, fma(-ur, xr, br[i]));
+        bi[i] = fma(-ui, xr, fma(-ur, xi, bi[i]));
+        br[i] = nr;
+      }
+    }
+    return;
   }
   for (int i = n - 1; i >= 0; i--) {
     double sr = br[i], si = bi[i];
