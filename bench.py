@@ -357,6 +357,8 @@ def _traffic(a):
         t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         if a.M != 1 << 20:
             return None
+        if a.workload == "c4":
+            return None if a.fixed_order else t["c4_bytes_per_solve"]
         return t["fixed_bytes_per_solve"] if a.fixed_order else t["default_bytes_per_solve"]
     except Exception:
         return None

@@ -148,7 +148,8 @@ int jb200_last_launches(void* handle);
 int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void* stream);
 int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream);
 
-/* batched small dense LU factor + solve, n in {2,3,4}: A [M,n,n], b [M,n] -> x [M,n].
+/* batched small dense LU factor + solve, n in {2,3,4} (one thread per system) or 16 (16 lanes per
+ * system, one matrix row per lane): A [M,n,n], b [M,n] -> x [M,n].
  * Aim/bim/xim == NULL selects the real path, otherwise complex (separate re/im planes).    */
 int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre,
                    const double* bim, double* xre, double* xim, void* stream);

@@ -106,6 +106,9 @@ static const HamOps* ham_ops(int ham_id) {
 }
 #endif
 
+int lu16_solve_launch(long long M, const double* Are, const double* Aim, const double* bre, const double* bim, double* xre,
+                      double* xim, cudaStream_t st);   // tu_mlp.cu
+
 static int validate(const jb200_opts* o, int ny) {
   if (o->n_tol != 1 && o->n_tol != ny) return fail(JB200_EINVAL, "RelTol/AbsTol: vector of length 1 or Ny");
   for (int i = 0; i < o->n_tol; i++) {
@@ -451,7 +454,10 @@ int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const
     case 2: return launch_lu<2>(M, Are, Aim, bre, bim, xre, xim, st);
     case 3: return launch_lu<3>(M, Are, Aim, bre, bim, xre, xim, st);
     case 4: return launch_lu<4>(M, Are, Aim, bre, bim, xre, xim, st);
-    default: return fail(JB200_ENOTSUP, "jb200_lu_solve: n must be 2, 3 or 4");
+#if !defined(JB_USER_HAM_HEADER) && !defined(JB_FAST_BUILD)
+    case 16: return lu16_solve_launch(M, Are, Aim, bre, bim, xre, xim, st);   // 16 lanes per system (csrc/lu16.cuh)
+#endif
+    default: return fail(JB200_ENOTSUP, "jb200_lu_solve: n must be 2, 3, 4 or 16");
   }
 }
 

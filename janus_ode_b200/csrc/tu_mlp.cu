@@ -237,6 +237,39 @@ __global__ void output_kernel(const State S, double* __restrict__ y_out, double*
   if (work) work[i] = s.work;
 }
 
+// jb200_lu_solve for n = 16: factor + solve of M independent systems, 16 lanes per system
+template <bool CPLX>
+__global__ void __launch_bounds__(256) lu16_solve_kernel(long long M, const double* __restrict__ Are,
+                                                         const double* __restrict__ Aim, const double* __restrict__ bre,
+                                                         const double* __restrict__ bim, double* __restrict__ xre,
+                                                         double* __restrict__ xim) {
+  const long long m = blockIdx.x * 16LL + (threadIdx.x >> 4);
+  if (m >= M) return;
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  const int l = threadIdx.x & 15;
+  double re[16], im[16];
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    re[c] = Are[m * 256 + l * 16 + c];
+    im[c] = CPLX ? Aim[m * 256 + l * 16 + c] : 0.0;
+  }
+  int piv = 0;
+  if (CPLX) {
+    double rdre = 0.0, rdim = 0.0;
+    zlu16_factor(mask, l, re, im, rdre, rdim, piv);
+    double br = bre[m * 16 + l], bi = bim[m * 16 + l];
+    zlu16_solve(mask, l, re, im, rdre, rdim, piv, br, bi);
+    xre[m * 16 + l] = br;
+    xim[m * 16 + l] = bi;
+  } else {
+    double rd = 0.0;
+    rlu16_factor(mask, l, re, rd, piv);
+    double b = bre[m * 16 + l];
+    rlu16_solve(mask, l, re, rd, piv, b);
+    xre[m * 16 + l] = b;
+  }
+}
+
 static Ctx* ctx_of(Handle* H) { return (Ctx*)H->ext; }
 
 static void free_workspace(Ctx* C) {
@@ -472,6 +505,15 @@ static int st_read(Handle*, EpochWS&, double*, double*, double*, double*, int*, 
 }
 
 }  // namespace mlp
+
+int lu16_solve_launch(long long M, const double* Are, const double* Aim, const double* bre, const double* bim, double* xre,
+                      double* xim, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((M + 15) / 16);
+  if (Aim) mlp::lu16_solve_kernel<true><<<blocks, 256, 0, st>>>(M, Are, Aim, bre, bim, xre, xim);
+  else mlp::lu16_solve_kernel<false><<<blocks, 256, 0, st>>>(M, Are, nullptr, bre, nullptr, xre, nullptr);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern const HamOps jb_ops_mlp = HamOps{mlp::MN,       mlp::NPAR,     &mlp::solve,   &mlp::dyns,   &mlp::jac,
                                         &mlp::st_init, &mlp::st_step, &mlp::st_read, &mlp::create, &mlp::destroy};

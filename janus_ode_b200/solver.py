@@ -299,7 +299,7 @@ class RadauT:
 
 
 def lu_solve(A, b):
-    """Batched small dense LU factor + solve on CUDA tensors, A [M,n,n], b [M,n], n in {2,3,4};
+    """Batched small dense LU factor + solve on CUDA tensors, A [M,n,n], b [M,n], n in {2,3,4} or 16;
     real float64 or complex128 (the torch::linalg_lu_factor / lu_solve role on the Radau path,
     src/cpp/radaute_impl.hpp:1558,1754)."""
     if not A.is_cuda:

@@ -126,3 +126,33 @@ def test_unsupported_and_invalid():
     small = jb.Hamiltonian("mlp", 5, 8, (4.0, 128.0) + H.params[2:])
     with pytest.raises(jb.JanusB200Error, match="N = 8"):
         jb.RadauTe(jb.HamiltonianSystem(small, -1), None, tgrid[:, [0, 2]].contiguous(), y0, jb.OptionsTe()).solve()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("kind", ["radau", "random"])
+def test_lu16_bitwise(cplx, kind):
+    """16-lane LU factor + solve (csrc/lu16.cuh) == the scalar mirror, every bit; 'random' matrices are
+    not diagonally dominant, so the pivot search (first maximum), the row exchanges and the pivot
+    bookkeeping are all exercised."""
+    n, M = 16, 3001
+    rng = np.random.default_rng(7)
+    if kind == "radau":
+        J = rng.standard_normal((M, n, n)) * 10.0 ** rng.integers(-2, 3, (M, n, n))
+        h = 10.0 ** rng.uniform(-5, 1, M)
+        A = (3.6378 / h)[:, None, None] * np.eye(n) - J
+        if cplx:
+            A = A + 1j * (3.05 / h)[:, None, None] * np.eye(n)
+    else:
+        A = rng.standard_normal((M, n, n))
+        A[::7, 3, 0] = 5.0                          # exact tie for the first pivot: rows 3 and 9 ...
+        A[::7, 9, 0] = 5.0                          # ... the first maximum (row 3) must win
+        A[1::7, 12, 0] = -6.0                       # and a negative entry of larger modulus
+        if cplx:
+            A = A + 1j * rng.standard_normal((M, n, n))
+    b = rng.standard_normal((M, n)) + (1j * rng.standard_normal((M, n)) if cplx else 0)
+    x = jb.lu_solve(torch.from_numpy(A).to(DEV), torch.from_numpy(b).to(DEV)).cpu().numpy()
+    xo = c_oracle.lu_solve(A, b, "mirror")
+    assert np.array_equal(x, xo, equal_nan=True)
+    xt = torch.linalg.solve(torch.from_numpy(A), torch.from_numpy(b)).numpy()
+    err = np.abs(x - xt).max(1) / np.abs(xt).max(1)
+    assert (err < 1e-12 * np.maximum(np.linalg.cond(A), 10)).all()
