@@ -56,6 +56,24 @@ def parse():
     return ap.parse_args()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL with NCCL_DEBUG=VERSION/INFO, nvcc, ...) write to fd 1; the contract is ONE JSON line
+    on stdout.  Everything else goes to stderr, the JSON line to the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def make_cfg(a, M, lo=0, hi=None):
     from janus_ode_b200 import configs
     if a.workload == "c4":
@@ -186,7 +204,7 @@ def run_reference(a):
                                           f"structure; the reference itself cannot be built here (SURVEY.md 8c)"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
     from oracle import c_oracle
     c_oracle.build()
@@ -212,7 +230,7 @@ def run_reference(a):
                                       f"reference itself cannot be built here (SURVEY.md 8c)"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_ours(a):
@@ -346,7 +364,7 @@ def run_ours(a):
                                    "sample": f"first {brows} rows of the workload, {bdt:.1f} s; masked-tensor torch restatement "
                                              f"of RadauTe with the autograd Hamiltonian adaptor (oracle/radau_batched.py): "
                                              f"the reference's op structure (BASELINE.md section 3)"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -373,6 +391,7 @@ def _hbm_peak():
 
 if __name__ == "__main__":
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
