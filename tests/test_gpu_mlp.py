@@ -100,8 +100,8 @@ def test_solve_vs_reference_arithmetic():
     cfg = configs.c4_mlp(M=256)
     g, o = gpu_solve(cfg), oracle_solve(cfg, "reference")
     rel = np.abs(g["y"] - o["y"]).max(1) / np.abs(o["y"]).max(1)
-    assert rel.max() < 1e-8
-    assert (g["stats"][:, 5] == o["stats"][:, 5]).mean() >= 0.9
+    assert rel.max() < 1e-8                                               # BASELINE.json bar: 1e-8 relative
+    assert (g["stats"][:, 5] == o["stats"][:, 5]).mean() >= 0.999         # ... and >= 99.9 % equal accepted-step counts
 
 
 @pytest.mark.parametrize("tag", ["s3", "var"])

@@ -81,7 +81,7 @@ def test_mirror_vs_reference_arithmetic():
     b = c_oracle.solve("mlp", par, -1, cfg["y0"].numpy(), cfg["tspan"].numpy(), cfg["options"], arith="reference")
     rel = np.abs(a["y"] - b["y"]).max(1) / np.abs(b["y"]).max(1)
     assert rel.max() < 1e-8                                   # the 1e-8 bar of BASELINE.json
-    assert (a["stats"][:, 5] == b["stats"][:, 5]).mean() >= 0.9   # smooth problem: counts agree almost always
+    assert (a["stats"][:, 5] == b["stats"][:, 5]).mean() >= 0.999   # smooth problem: the count bar holds across arithmetics
 
 
 @pytest.mark.parametrize("tag", ["s3", "var"])
