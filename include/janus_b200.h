@@ -148,6 +148,18 @@ int jb200_last_launches(void* handle);
 int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void* stream);
 int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream);
 
+/* Explicit Dormand-Prince 8(5,3) step for non-stiff batches: replaces
+ * Dopri853Te.step(htry) of /root/reference/src/python/dopri853te.py:290-315 (+ dy :207-287, error :191-205,
+ * control :318-355) with derivs = the handle's Hamiltonian dynamics.  One call = one ACCEPTED step of every
+ * trajectory (rejected attempts retried inside).  All pointers are device arrays updated in place: x [M],
+ * y / dydx [M,Ny], errold [M] (initialise to 1e-4), hnext [M]; htry [M] in; hdid [M], nrej [M] (may be NULL) out.
+ * norm_M = the batch size of the reference's error norm (0: M); aliased = 0 for the first step of a stepper
+ * object, 1 afterwards (the reference's y / yout aliasing after its first step, :311); its float32
+ * coefficients, non-growing hnext and beta = 0 are reproduced as well (csrc/dopri853.cuh).                     */
+int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,
+                        double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
+                        void* stream);
+
 /* batched small dense LU factor + solve, n in {2,3,4} (one thread per system) or 16 (16 lanes per
  * system, one matrix row per lane): A [M,n,n], b [M,n] -> x [M,n].
  * Aim/bim/xim == NULL selects the real path, otherwise complex (separate re/im planes).    */

@@ -444,6 +444,21 @@ int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* 
   return ham_ops(H->ham_id)->jac(H, y, M, jac, (cudaStream_t)stream);
 }
 
+int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,
+                        double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
+                        void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  if (!x || !y || !dydx || !errold || !hnext || !htry || !hdid) return fail(JB200_EINVAL, "null buffer");
+  if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->dopri) return fail(JB200_ENOTSUP, "DOPRI853 is available for the thread-resident Hamiltonians only");
+  const dp::StepArgs a{(long long)M, (long long)(norm_M > 0 ? norm_M : M), atol, rtol, x, y, dydx, errold, hnext, aliased, htry, hdid,
+                       (int*)nrej};
+  return ops->dopri(H, a, (cudaStream_t)stream);
+}
+
 int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre, const double* bim,
                    double* xre, double* xim, void* stream) {
   if (M <= 0) return 0;

@@ -26,6 +26,7 @@
 
 #include "../../include/janus_b200.h"
 #include "radau_core.cuh"
+#include "dopri853.cuh"
 
 namespace jb {
 
@@ -592,6 +593,35 @@ int launch_jac(Handle* H, const double* y, long long M, double* J, cudaStream_t 
 }
 
 // one table of entry points per Hamiltonian: what capi.cu dispatches on
+// explicit DOPRI853: one call = one accepted step of every trajectory (dopri853.cuh)
+template <class Ham>
+__global__ void __launch_bounds__(128) dopri_kernel(const __grid_constant__ RadauParams P, const dp::StepArgs a) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
+    double y[NY], d[NY];
+    load_row<NY>(a.y, m, y);
+    load_row<NY>(a.dydx, m, d);
+    double x = a.x[m], errold = a.errold[m], hnext = a.hnext[m], hdid;
+    int nrej;
+    dp::dopri_step_one<Ham>(P.ham_par, P.sign, a.norm_M, a.atol, a.rtol, a.aliased != 0, x, y, d, errold, hnext, a.htry[m], hdid, nrej);
+    store_row<NY>(a.y, m, y);
+    store_row<NY>(a.dydx, m, d);
+    a.x[m] = x;
+    a.errold[m] = errold;
+    a.hnext[m] = hnext;
+    a.hdid[m] = hdid;
+    if (a.nrej) a.nrej[m] = nrej;
+  }
+}
+template <class Ham>
+int launch_dopri(Handle* H, const dp::StepArgs& a, cudaStream_t st) {
+  const long long blocks = std::max<long long>(1, std::min<long long>((a.M + 127) / 128, (long long)H->sm_count * 8));
+  dopri_kernel<Ham><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  return 0;
+}
+
 struct HamOps {
   int ny, npar;
   int (*solve)(Handle*, const double*, const double*, long long, double*, double*, double*, int*, long long*, int*,
@@ -603,11 +633,13 @@ struct HamOps {
   int (*st_read)(Handle*, EpochWS&, double*, double*, double*, double*, int*, long long*, int*, int*, cudaStream_t);
   int (*create)(Handle*, const double* par, int npar) = nullptr;   // optional: device-resident parameters
   void (*destroy)(Handle*) = nullptr;
+  int (*dopri)(Handle*, const dp::StepArgs&, cudaStream_t) = nullptr;   // explicit DOPRI853 step (thread-resident Hamiltonians)
 };
 template <class Ham>
 HamOps make_ops() {
   return HamOps{Ham::NV,           Ham::NPAR,         &dispatch_order<Ham>, &launch_dyns<Ham>,
-                &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>};
+                &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>,
+                nullptr,          nullptr,           &launch_dopri<Ham>};
 }
 
 }  // namespace jb

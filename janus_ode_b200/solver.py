@@ -334,3 +334,55 @@ def fp64_peak_tflops(iters=20000):
     v = C.c_double()
     _lib.check(_lib.lib().jb200_fp64_peak(int(iters), C.byref(v)))
     return v.value
+
+
+class Dopri853Te:
+    """Explicit Dormand-Prince 8(5,3) stepper for non-stiff batches with the reference's object shape
+    (/root/reference/src/python/dopri853te.py:4-5, 290-315):
+
+        s = Dopri853Te(yy, dydxx, xx, atoll, rtoll, dens, derivs);  s.step(htry)  ->  s.y, s.x, s.dydx, s.hnext, s.hdid
+
+    `derivs` must be a HamiltonianSystem (the device evaluates H's dynamics by dual numbers); `dydxx` is used as
+    given, like the reference (None: evaluated here).  One step() = one accepted step of every trajectory on the
+    GPU (`jb200_dopri853_step`); the reference's float32 coefficients, batch-size-dependent error norm and
+    non-growing hnext are reproduced (csrc/dopri853.cuh).  `norm_M`: batch size of the error norm (default M),
+    for sharded runs.  Dense output (`dens`) is not built."""
+
+    def __init__(self, yy, dydxx, xx, atoll, rtoll, dens=False, derivs=None, norm_M=None):
+        if not isinstance(derivs, HamiltonianSystem):
+            raise TypeError("derivs must be a janus_ode_b200.HamiltonianSystem")
+        if dens:
+            raise NotImplementedError("dense output of DOPRI853 is not built")
+        if not (isinstance(yy, torch.Tensor) and yy.is_cuda and yy.dtype == torch.float64 and yy.dim() == 2):
+            raise _lib.JanusB200Error("Dopri853Te runs on CUDA float64 tensors [M,Ny] only (no CPU fallback)")
+        self.derivs = derivs
+        self.M, self.D = yy.shape
+        if self.D != derivs.hamiltonian.Ny:
+            raise ValueError(f"y must be [M,{derivs.hamiltonian.Ny}]")
+        dev = yy.device
+        self.y = yy.contiguous().clone()
+        self.x = torch.as_tensor(xx, dtype=torch.float64, device=dev).expand(self.M).contiguous().clone()
+        self.dydx = (derivs(self.x, self.y) if dydxx is None else dydxx.to(dev, torch.float64)).contiguous().clone()
+        self.atol, self.rtol = float(atoll), float(rtoll)
+        self.norm_M = int(norm_M or self.M)
+        self.errold = torch.full((self.M,), 1.0e-4, dtype=torch.float64, device=dev)
+        self.hnext = torch.zeros(self.M, dtype=torch.float64, device=dev)
+        self.hdid = torch.zeros(self.M, dtype=torch.float64, device=dev)
+        self.xold = self.x.clone()
+        self.nrej = torch.zeros(self.M, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            self._handle = _get_handle(derivs.hamiltonian, OptionsTe(), derivs.costate_sign, dev)
+        self.gpu_launches = 0
+
+    def step(self, htry):
+        dev = self.y.device
+        h = torch.as_tensor(htry, dtype=torch.float64, device=dev).expand(self.M).contiguous()
+        self.xold = self.x.clone()
+        H = self._handle
+        with torch.cuda.device(dev):
+            _lib.check_h(H, H.L.jb200_dopri853_step(H.h, self.M, self.norm_M, self.atol, self.rtol,
+                                                   1 if self.gpu_launches else 0, _ptr(self.x),
+                                                   _ptr(self.y), _ptr(self.dydx), _ptr(self.errold), _ptr(self.hnext),
+                                                   _ptr(h), _ptr(self.hdid), _ptr(self.nrej), _stream_ptr(dev)))
+        self.gpu_launches += 1
+        return self
