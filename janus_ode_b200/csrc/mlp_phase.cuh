@@ -46,6 +46,7 @@ struct TrajS {   // per-trajectory scalars (array of structs)
   int NbrStg, Newt, ChangeNbr, res;
   unsigned flags;   // PF_* of radau_core.cuh
   int phase;
+  int nout;         // output points written so far (output at the tspan points, OutFlag 3)
 };
 
 // vector state: structure of arrays, element e of trajectory i at arr[e * M + i] (one thread per
@@ -60,6 +61,11 @@ struct State {
   double* LU;      // [i][lud]: L0a[256] L0rd[16] { re[256] im[256] rdre[16] rdim[16] } x (SM-1)/2
   int* LUpiv;      // [i][lui]: L0piv[16] { piv[16] } x (SM-1)/2
   int lud, lui;
+  // output at the interior points of tspan (radau.m:1150-1168, OutFlag 3); tout == nullptr: final state only
+  int ntspan;              // columns of tspan (>= 2)
+  const double* tspan;     // [M][ntspan]
+  double* tout;            // [M][ntspan]
+  double* yout;            // [M][ntspan][16]
   JB_HD double* L0a(long long i) const { return LU + (size_t)i * lud; }
   JB_HD double* L0rd(long long i) const { return LU + (size_t)i * lud + 256; }
   JB_HD int* L0piv(long long i) const { return LUpiv + (size_t)i * lui; }
@@ -214,14 +220,15 @@ JB_HD void zlu_solve_g(const double* re, const double* im, const double* rdre, c
 JB_HD void finish(TrajS& s) { s.phase = PH_FINISHED; }
 
 // radau.m:631-696 / radaute_impl.hpp:406-455 up to the first dynamics evaluation
-JB_HD void ph_init(const State& S, const RadauParams& P, long long i, const double* y0 /*[M][16]*/,
-                   const double* tspan /*[M][2]*/) {
+JB_HD void ph_init(const State& S, const RadauParams& P, long long i, const double* y0 /*[M][16]*/) {
+  const double* tspan = S.tspan + (size_t)i * S.ntspan;
   const long long M = S.M;
   TrajS s;
   for (int e = 0; e < MN; e++) S.y[(size_t)e * M + i] = y0[i * MN + e];
   for (int e = 0; e < S.SM * MN; e++) S.cont[(size_t)e * M + i] = 0.0;
   for (int k = 0; k < 8; k++) s.st[k] = 0;
-  const double t0 = tspan[2 * i], tfinal = tspan[2 * i + 1];
+  const double t0 = tspan[0], tfinal = tspan[S.ntspan - 1];
+  s.nout = 0;
   s.t = t0;
   s.t0 = t0;
   s.tfinal = tfinal;
@@ -455,6 +462,44 @@ JB_HD void ph_prep(const State& S, const RadauParams& P, long long i, bool defer
   S.sc[i] = s;
 }
 
+// after an accepted step: every requested time in (t - h, t] evaluated on the collocation polynomial
+// (ntrprad, radaute_impl.hpp:1413-1440; same loop as radau_core.cuh dense_output)
+template <int S_>
+JB_HD void dense_output_g(const State& S, TrajS& s, long long i) {
+  using Tab = RadauTab<S_>;
+  const long long M = S.M;
+  const double* tspan = S.tspan + (size_t)i * S.ntspan;
+  double* tout = S.tout + (size_t)i * S.ntspan;
+  double* yout = S.yout + (size_t)i * S.ntspan * MN;
+  while (s.nout < S.ntspan) {
+    const double tn = tspan[s.nout];
+    if (s.PosNeg * (s.t - tn) < 0) break;
+    if (s.t == tn) {
+      tout[s.nout] = s.t;
+      for (int e = 0; e < MN; e++) yout[s.nout * MN + e] = S.y[(size_t)e * M + i];
+      s.nout += 1;
+      break;
+    }
+    const double sg = (tn - s.t) / s.h_old;
+    for (int e = 0; e < MN; e++) {
+      double yi = (sg - (Tab::C(0) - 1.0)) * S.cont[(size_t)((S_ - 1) * MN + e) * M + i];
+#pragma unroll
+      for (int q = 1; q < S_; q++) yi = (sg - (Tab::C(q) - 1.0)) * (yi + S.cont[(size_t)((S_ - 1 - q) * MN + e) * M + i]);
+      yout[s.nout * MN + e] = yi + S.y[(size_t)e * M + i];
+    }
+    tout[s.nout] = tn;
+    s.nout += 1;
+  }
+}
+
+// radau.m:1267-1269: the last recorded point is overwritten with the final (t, y)
+JB_HD void dense_finish_g(const State& S, const TrajS& s, long long i) {
+  if (s.nout >= 1) {
+    S.tout[(size_t)i * S.ntspan + s.nout - 1] = s.t;
+    for (int e = 0; e < MN; e++) S.yout[((size_t)i * S.ntspan + s.nout - 1) * MN + e] = S.y[(size_t)e * S.M + i];
+  }
+}
+
 // new step size + accept / reject up to the dynamics evaluation at the new point (radau.m:1038-1253)
 template <int S_>
 JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long long i) {
@@ -512,6 +557,7 @@ JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long lon
 #pragma unroll
       for (int q = 0; q < S_; q++) S.cont[(size_t)(q * MN + e) * M + i] = cc[q];
     }
+    if (S.tout) dense_output_g<S_>(S, s, i);   // radau.m:1150-1168
     s.flags |= PF_NEED_JAC;
     if (JB_FLAG(s, PF_LAST)) {
       s.h = s.hopt;

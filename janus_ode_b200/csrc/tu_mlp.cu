@@ -37,10 +37,9 @@ struct Ctx {
 
 __device__ __forceinline__ int append(int* counter, int n) { return atomicAdd(counter, n); }
 
-__global__ void init_kernel(const State S, const __grid_constant__ RadauParams P, const double* __restrict__ y0,
-                            const double* __restrict__ tspan) {
+__global__ void init_kernel(const State S, const __grid_constant__ RadauParams P, const double* __restrict__ y0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < S.M) ph_init(S, P, i, y0, tspan);
+  if (i < S.M) ph_init(S, P, i, y0);
 }
 __global__ void init_b_kernel(const State S) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -224,10 +223,14 @@ __global__ void accept_b_kernel(const State S, const __grid_constant__ RadauPara
 }
 __global__ void output_kernel(const State S, double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
                               int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
-                              long long* __restrict__ work) {
+                              long long* __restrict__ work, int* __restrict__ nout) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= S.M) return;
   const TrajS s = S.sc[i];
+  if (S.tout) {
+    dense_finish_g(S, s, i);
+    nout[i] = s.nout;
+  }
   for (int e = 0; e < MN; e++) y_out[i * MN + e] = S.y[(size_t)e * S.M + i];
   t_out[i] = s.t;
   h_out[i] = s.h;
@@ -352,17 +355,20 @@ static int read_counters(Ctx* C, cudaStream_t st) {
 
 static int solve(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out, double* h_out,
                  int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  if (dense.tout) return fail(JB200_ENOTSUP, "MLP Hamiltonian path: output at tspan points is not available yet");
   int rc = ensure(H, M, true);
   if (rc) return rc;
   Ctx* C = ctx_of(H);
   State S = C->S;
   S.M = M;   // element stride = this batch (the pool was sized for cap >= M)
+  S.ntspan = dense.ntspan;
+  S.tspan = tspan;
+  S.tout = dense.tout;
+  S.yout = dense.yout;
   const RadauParams& P = H->P;
   H->launches = 0;
   const unsigned gb = (unsigned)((M + 127) / 128);
   auto blocks = [](int n) { return (unsigned)((n + 127) / 128); };
-  init_kernel<<<gb, 128, 0, st>>>(S, P, y0, tspan);
+  init_kernel<<<gb, 128, 0, st>>>(S, P, y0);
   GradIO g0{nullptr, nullptr, (int)M, S.y, 1, M, nullptr, 0, 0, nullptr, S.f0, 1, M, C->d_act, P.sign};
   if ((rc = launch_grad(H, g0, (int)M, st))) return rc;
   init_b_kernel<<<gb, 128, 0, st>>>(S);
@@ -416,7 +422,7 @@ static int solve(Handle* H, const double* y0, const double* tspan, long long M, 
       H->launches += 1;
     }
   }
-  output_kernel<<<gb, 128, 0, st>>>(S, y_out, t_out, h_out, res, stats, nstg, work);
+  output_kernel<<<gb, 128, 0, st>>>(S, y_out, t_out, h_out, res, stats, nstg, work, dense.nout);
   H->launches += 1;
   JB_CUDA(cudaGetLastError());
   return 0;

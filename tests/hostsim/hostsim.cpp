@@ -167,7 +167,8 @@ extern "C" int hostsim_mlp_solve(mlp_dyns_fn dyns, mlp_jac_fn jacf, const double
        rscal = dv(MN), temp = dv(MN), ev = dv(MN), errs = dv(1), LU = dv(lu_doubles(SM));
   std::vector<int> LUpiv((size_t)lu_ints(SM) * M);
   State S{M, SM, sc.data(), y.data(), f0.data(), cont.data(), z.data(), w.data(), F.data(), rscal.data(),
-          temp.data(), ev.data(), errs.data(), Jac.data(), LU.data(), LUpiv.data(), lu_doubles(SM), lu_ints(SM)};
+          temp.data(), ev.data(), errs.data(), Jac.data(), LU.data(), LUpiv.data(), lu_doubles(SM), lu_ints(SM),
+          2, tspan, nullptr, nullptr};
   double yy[MN], ff[MN], JJ[MN * MN];
   auto eval_at = [&](long long i, const double* add /*SoA offset or null*/, double scalar, double* out) {
     for (int e = 0; e < MN; e++) {
@@ -180,7 +181,7 @@ extern "C" int hostsim_mlp_solve(mlp_dyns_fn dyns, mlp_jac_fn jacf, const double
     for (int e = 0; e < MN; e++) out[(size_t)e * M + i] = ff[e];
   };
   for (long long i = 0; i < M; i++) {
-    ph_init(S, P, i, y0, tspan);
+    ph_init(S, P, i, y0);
     eval_at(i, nullptr, 0.0, S.f0);
     ph_init_b(S, i);
   }

@@ -113,13 +113,35 @@ def test_golden_c4(tag):
     assert np.allclose(g["y"], gd["ref_y"], rtol=1e-8, atol=1e-12)
 
 
+@pytest.mark.parametrize("fixed", [True, False])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_output_at_tspan_points_bitwise(fixed, reverse):
+    """OutFlag 3 (radau.m:1150-1168): tout / yout / nout at interior tspan points, forward and reverse time."""
+    cfg = configs.c4_mlp(M=70, fixed_order=fixed)
+    grid = torch.linspace(0.0, 1.0, 9, dtype=torch.float64)
+    if reverse:
+        grid = torch.flip(grid, [0]) * 0.7 + 0.1
+    ts = grid.repeat(70, 1)
+    ts[:, 1:-1] += 0.01 * torch.rand(70, 7, dtype=torch.float64, generator=torch.Generator().manual_seed(3))   # per-row grids
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    r = jb.RadauTe(dyn, None, ts.to(DEV), cfg["y0"].to(DEV), cfg["options"])
+    r.solve()
+    torch.cuda.synchronize()
+    o = c_oracle.solve_dense("mlp", np.array(cfg["ham"].params), cfg["sign"], cfg["y0"].numpy(), ts.numpy(), cfg["options"],
+                             arith="mirror")
+    assert (o["nout"] >= 8).all()      # (a final point missed by one ulp is overwritten with (tfinal, y): radau.m:1267-1269)
+    assert np.array_equal(r.nout.cpu().numpy(), o["nout"]) and np.array_equal(r.tout.cpu().numpy(), o["tout"])
+    assert np.array_equal(r.yout.cpu().numpy(), o["yout"]) and np.array_equal(r.y.cpu().numpy(), o["y"])
+    assert np.array_equal(r.stats.raw.cpu().numpy(), o["stats"])
+
+
 def test_unsupported_and_invalid():
     H = jb.MlpHamiltonian(8, 128, 0)
     dyn = jb.HamiltonianSystem(H, -1)
     y0 = torch.zeros(4, 16, dtype=torch.float64, device=DEV)
     tgrid = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64, device=DEV).repeat(4, 1)
     with pytest.raises(jb.JanusB200Error, match="not available"):
-        jb.RadauTe(dyn, None, tgrid, y0, jb.OptionsTe()).solve()
+        jb.RadauT(jb.OptionsTe()).step(0.01, dyn, 1.0, jb.RadauState(y0, torch.zeros(4, dtype=torch.float64, device=DEV), ft=1.0))
     bad = jb.Hamiltonian("mlp", 5, 8, H.params[:100])
     with pytest.raises(ValueError, match="parameters"):
         jb.RadauTe(jb.HamiltonianSystem(bad, -1), None, tgrid[:, [0, 2]].contiguous(), y0, jb.OptionsTe()).solve()
