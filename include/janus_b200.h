@@ -148,6 +148,15 @@ int jb200_last_launches(void* handle);
 int jb200_eval_dyns(void* handle, const double* y, int64_t M, double* ydot, void* stream);
 int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* stream);
 
+/* Solve with forward sensitivities: replaces RadauTeD(OdeFcnDual, JacFnDual, tspan, y0 (TensorDual), Op, params).solve()
+ * (/root/reference/src/cpp/radauted.hpp, radauted_impl.hpp:620-1645) for Hamiltonian dynamics, the dual part of y0
+ * being S0 [M,Ny,Ny] (NULL: identity = d y / d y0).  S_out [M,Ny,Ny] = the dual part of the final state (row i,
+ * column d = d y_i(tfinal) / d direction d); sens_iters [M] (may be NULL) = sensitivity Newton iterations spent.
+ * States, step sizes and counters are those of jb200_solve, bit for bit (step control looks at the real part only). */
+int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const double* S0, int64_t M, double* y_out,
+                     double* S_out, double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
+                     int64_t* work, int32_t* sens_iters, void* stream);
+
 /* Explicit Dormand-Prince 8(5,3) step for non-stiff batches: replaces
  * Dopri853Te.step(htry) of /root/reference/src/python/dopri853te.py:290-315 (+ dy :207-287, error :191-205,
  * control :318-355) with derivs = the handle's Hamiltonian dynamics.  One call = one ACCEPTED step of every

@@ -444,6 +444,20 @@ int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* 
   return ham_ops(H->ham_id)->jac(H, y, M, jac, (cudaStream_t)stream);
 }
 
+int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const double* S0, int64_t M, double* y_out,
+                     double* S_out, double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
+                     int64_t* work, int32_t* sens_iters, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (M == 0) return 0;
+  if (!y0 || !tspan || !y_out || !S_out || !t_out || !h_out || !res || !stats) return fail(JB200_EINVAL, "null buffer");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->sens) return fail(JB200_ENOTSUP, "forward sensitivities are available for the thread-resident Hamiltonians only");
+  return ops->sens(H, y0, tspan, S0, (long long)M, y_out, S_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
+                   (long long*)work, (int*)sens_iters, (cudaStream_t)stream);
+}
+
 int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,
                         double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
                         void* stream) {

@@ -216,8 +216,126 @@ JB_HD void dense_finish(const Traj<NY, SM>& T, const DenseOut& out) {
   }
 }
 
+// ------------------------------------------------------------------ forward sensitivities
+// S = d y / d y0 (or d y / d any ND parameters of the initial state), carried through every accepted
+// step (the reference carries TensorDual numbers through RadauTeD::solve,
+// /root/reference/src/cpp/radauted_impl.hpp:620-1645, with evalDynsDual / evalJacDual,
+// src/cpp/janus_ode_common.hpp:2075-2158,2302-2416).  The dual part of the converged stage equations is
+// LINEAR:   Zs_i = h sum_j a_ij J(y + z_j) (S + Zs_j),   y_{n+1}' = S + Zs_s,
+// and is solved here by the same simplified-Newton iteration as the state -- same transformed system,
+// same real + complex LU factors (the dual part of the iteration matrix only changes the convergence rate, not
+// the fixed point, so no third derivatives of H are needed), with the Jacobians J(y + z_j) evaluated by
+// hyper-dual numbers at the CONVERGED stage points.  The real part of the integration is untouched: states,
+// step sizes and counters are bit-identical to a solve without sensitivities.
+template <int NY>
+struct Sens {
+  static constexpr int ND = NY;
+  double S[NY * NY];   // S[i * ND + d] = d y_i / d (direction d)
+  int iters;           // sensitivity Newton iterations spent (all directions, all steps)
+};
+
 template <class Ham, int NY, int S, int SM>
-JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
+JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, const double* rscal, Sens<NY>& sn) {
+  using Tab = RadauTab<S>;
+  constexpr int ND = Sens<NY>::ND;
+  constexpr int si = (S - 1) / 2;
+  const int Nit = nit_of(S, P.MaxNbrNewton) + 10;
+  const double tol = 0.1 * P.FNewt[si];
+  const double rh = 1.0 / T.h;
+  double Jq[S * NY * NY];
+#pragma unroll
+  for (int q = 0; q < S; q++) {
+    double yq[NY];
+#pragma unroll
+    for (int i = 0; i < NY; i++) yq[i] = T.y[i] + z[q * NY + i];
+    ham_jac<Ham>(yq, P.ham_par, P.sign, &Jq[q * NY * NY]);
+  }
+  T.work += (long long)S * Ham::FLOPS_J;
+  for (int d = 0; d < ND; d++) {
+    double Sd[NY], smax = 1.0;
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      Sd[i] = sn.S[i * ND + d];
+      smax = fmax(smax, fabs(Sd[i]));
+    }
+    const double rs = 1.0 / smax;
+    double Zs[S * NY], Ws[S * NY];
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) Zs[k] = Ws[k] = 0.0;
+    for (int it = 0; it < Nit; it++) {
+      double zz[S * NY];
+      {  // F_q = J_q (S_d + Zs_q);  zz = TI F
+        double Fq[S * NY];
+#pragma unroll
+        for (int q = 0; q < S; q++)
+#pragma unroll
+          for (int i = 0; i < NY; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NY; j++) acc = fma(Jq[q * NY * NY + i * NY + j], Sd[j] + Zs[q * NY + j], acc);
+            Fq[q * NY + i] = acc;
+          }
+#pragma unroll
+        for (int j = 0; j < S; j++)
+#pragma unroll
+          for (int i = 0; i < NY; i++) {
+            double acc = Tab::TI(j, 0) * Fq[i];
+#pragma unroll
+            for (int q = 1; q < S; q++) acc = fma(Tab::TI(j, q), Fq[q * NY + i], acc);
+            zz[j * NY + i] = acc;
+          }
+      }
+      {  // Solvrad with the factors of this step
+        const double valp0 = Tab::ValP(0) * rh;
+#pragma unroll
+        for (int i = 0; i < NY; i++) zz[i] = fma(-valp0, Ws[i], zz[i]);
+        rlu_solve<NY>(T.L0, &zz[0]);
+#pragma unroll
+        for (int q = 1; q <= (S - 1) / 2; q++) {
+          const int q2 = 2 * q - 1, q3 = 2 * q;
+          const double v2 = Tab::ValP(q2) * rh, v3 = Tab::ValP(q3) * rh;
+#pragma unroll
+          for (int i = 0; i < NY; i++) {
+            const double a = fma(v3, Ws[q3 * NY + i], fma(-v2, Ws[q2 * NY + i], zz[q2 * NY + i]));
+            const double b = fma(-v2, Ws[q3 * NY + i], fma(-v3, Ws[q2 * NY + i], zz[q3 * NY + i]));
+            zz[q2 * NY + i] = a;
+            zz[q3 * NY + i] = b;
+          }
+          constexpr int NS = LcPlace<NY, SM>::NS;
+          if ((q - 1) < NS) zlu_solve(T.LcS[(q - 1) < NS ? (q - 1) : 0], &zz[q2 * NY], &zz[q3 * NY]);
+          else zlu_solve<NY>(T.Lc[(q - 1 - NS) > 0 ? (q - 1 - NS) : 0], &zz[q2 * NY], &zz[q3 * NY]);
+        }
+      }
+      // Ws += dW;  Zs = T Ws;  size of the increment in Z space
+      double nrm = 0.0;
+#pragma unroll
+      for (int k = 0; k < S * NY; k++) Ws[k] = Ws[k] + zz[k];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          double acc = Tab::T(j, 0) * Ws[i], dz = Tab::T(j, 0) * zz[i];
+#pragma unroll
+          for (int q = 1; q < S; q++) {
+            acc = fma(Tab::T(j, q), Ws[q * NY + i], acc);
+            dz = fma(Tab::T(j, q), zz[q * NY + i], dz);
+          }
+          Zs[j * NY + i] = acc;
+          const double v = dz * rscal[i] * rs;
+          nrm = fma(v, v, nrm);
+        }
+      nrm = ::sqrt(nrm) * P.inv_sqrt_sn[si];
+      sn.iters += 1;
+      T.work += W_newt(S, NY, 2 * NY * NY);
+      if (!(nrm > tol)) break;
+    }
+#pragma unroll
+    for (int i = 0; i < NY; i++) sn.S[i * ND + d] = Sd[i] + Zs[(S - 1) * NY + i];
+  }
+}
+
+template <class Ham, int NY, int S, int SM>
+JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr, Sens<NY>* sens = nullptr) {
   using Tab = RadauTab<S>;
   constexpr int si = (S - 1) / 2;
   const int Nit = nit_of(S, P.MaxNbrNewton);
@@ -481,6 +599,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* o
       T.hacc = T.h;
       T.erracc = fmax(1.0e-2, err);
     }
+    if (sens) sens_step<Ham, NY, S, SM>(T, P, z, rscal, *sens);   // before y moves: needs y_n, z, the LU of this step
     T.h_old = T.h;
     T.t = T.t + T.h;
 #pragma unroll
@@ -595,14 +714,14 @@ JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
 // whole integration of one trajectory.  VAR = false: fixed order S = SM (host guarantees
 // MinNbrStg == MaxNbrStg == NbrStg == SM); VAR = true: orders 1..SM selected at run time.
 template <class Ham, int NY, int SM, bool VAR>
-JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
+JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr, Sens<NY>* sens = nullptr) {
   if (!pass_head<Ham, NY, SM, VAR>(T, P)) return true;
-  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P, out);
+  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P, out, sens);
   switch (T.NbrStg) {
-    case 1: return attempt_step<Ham, NY, 1, SM>(T, P, out);
-    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P, out);
-    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P, out);
-    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P, out);
+    case 1: return attempt_step<Ham, NY, 1, SM>(T, P, out, sens);
+    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P, out, sens);
+    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P, out, sens);
+    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P, out, sens);
   }
 }
 
@@ -611,10 +730,10 @@ JB_HD bool traj_active(double PosNeg, double t, double tfinal, int steps, long l
 }
 
 template <class Ham, int NY, int SM, bool VAR>
-JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr) {
+JB_HD void integrate(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr, Sens<NY>* sens = nullptr) {
   if (T.res != 0) return;
   while (traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
-    if (one_pass<Ham, NY, SM, VAR>(T, P, out)) return;
+    if (one_pass<Ham, NY, SM, VAR>(T, P, out, sens)) return;
   }
   if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;  // MaxNbrStep exceeded
 }

@@ -622,6 +622,59 @@ int launch_dopri(Handle* H, const dp::StepArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// forward sensitivities (radau_core.cuh: Sens / sens_step): one thread = one trajectory with its Ny x Ny
+// sensitivity matrix, all stage counts inside one kernel (order selection at run time)
+template <class Ham>
+__global__ void __launch_bounds__(JB_THREADS, 1) sens_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
+                                                             const double* __restrict__ tspan, const double* __restrict__ S0,
+                                                             long long M, double* __restrict__ y_out, double* __restrict__ S_out,
+                                                             double* __restrict__ t_out, double* __restrict__ h_out,
+                                                             int* __restrict__ res, long long* __restrict__ stats,
+                                                             int* __restrict__ nstg, long long* __restrict__ work,
+                                                             int* __restrict__ sens_iters) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    Traj<NY, 7> T;
+    double y[NY];
+    load_row<NY>(y0, m, y);
+    traj_init<Ham, NY, 7>(T, P, y, tspan[2 * m], tspan[2 * m + 1]);
+    Sens<NY> sn;
+    sn.iters = 0;
+#pragma unroll
+    for (int k = 0; k < NY * NY; k++) sn.S[k] = S0 ? S0[m * NY * NY + k] : ((k / NY == k % NY) ? 1.0 : 0.0);
+    integrate<Ham, NY, 7, true>(T, P, nullptr, &sn);
+    store_row<NY>(y_out, m, T.y);
+#pragma unroll
+    for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = sn.S[k];
+    t_out[m] = T.t;
+    h_out[m] = T.h;
+    res[m] = T.res;
+#pragma unroll
+    for (int k = 0; k < 8; k++) stats[m * 8 + k] = T.st[k];
+    if (nstg) nstg[m] = T.NbrStg;
+    if (work) work[m] = T.work;
+    if (sens_iters) sens_iters[m] = sn.iters;
+  }
+}
+template <class Ham>
+int launch_sens(Handle* H, const double* y0, const double* tspan, const double* S0, long long M, double* y_out, double* S_out,
+                double* t_out, double* h_out, int* res, long long* stats, int* nstg, long long* work, int* sens_iters,
+                cudaStream_t st) {
+#ifdef JB_SLIM
+  return fail(JB200_ENOTSUP, "this plugin was built without the sensitivity kernel");
+#else
+  auto kern = sens_kernel<Ham>;
+  const size_t smem = lc_smem_bytes<Ham::NV, 7>(JB_THREADS);
+  if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = std::max<long long>(1, std::min<long long>((M + JB_THREADS - 1) / JB_THREADS, (long long)H->sm_count * 2));
+  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
+                                                  sens_iters);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  return 0;
+#endif
+}
+
 struct HamOps {
   int ny, npar;
   int (*solve)(Handle*, const double*, const double*, long long, double*, double*, double*, int*, long long*, int*,
@@ -634,12 +687,14 @@ struct HamOps {
   int (*create)(Handle*, const double* par, int npar) = nullptr;   // optional: device-resident parameters
   void (*destroy)(Handle*) = nullptr;
   int (*dopri)(Handle*, const dp::StepArgs&, cudaStream_t) = nullptr;   // explicit DOPRI853 step (thread-resident Hamiltonians)
+  int (*sens)(Handle*, const double*, const double*, const double*, long long, double*, double*, double*, double*, int*,
+              long long*, int*, long long*, int*, cudaStream_t) = nullptr;   // solve with forward sensitivities
 };
 template <class Ham>
 HamOps make_ops() {
   return HamOps{Ham::NV,           Ham::NPAR,         &dispatch_order<Ham>, &launch_dyns<Ham>,
                 &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>,
-                nullptr,          nullptr,           &launch_dopri<Ham>};
+                nullptr,          nullptr,           &launch_dopri<Ham>,   &launch_sens<Ham>};
 }
 
 }  // namespace jb

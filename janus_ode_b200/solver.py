@@ -386,3 +386,50 @@ class Dopri853Te:
                                                    _ptr(h), _ptr(self.hdid), _ptr(self.nrej), _stream_ptr(dev)))
         self.gpu_launches += 1
         return self
+
+
+class RadauTeD(RadauTe):
+    """Radau IIA with forward sensitivities, shaped like the reference's dual-number solver
+    (`RadauTeD r(dyns_dual, jac_dual, tspan, y, options, params); r.solve(); r.y.r, r.y.d`,
+    /root/reference/src/cpp/radauted.hpp, tests/cpp/ode_solver_test.cpp:620-770):
+
+        r = RadauTeD(dyns, dyns.jacobian, tspan, y0, options, y0d=None);  r.solve()  ->  r.y [M,Ny], r.yd [M,Ny,Ny]
+
+    y0d [M,Ny,Ny] is the dual part of the initial state (None: identity, i.e. yd = d y(tfinal) / d y0).  The
+    sensitivity of the final state to the final time is the dynamics there: `r.dydtf = dyns(t, r.y)`.  CUDA tensors
+    only; thread-resident Hamiltonians (built-in or user plugins with N <= 2)."""
+
+    def __init__(self, dyns, jac, tspan, y0, options=None, y0d=None):
+        super().__init__(dyns, jac, tspan, y0, options)
+        if not y0.is_cuda:
+            raise _lib.JanusB200Error("RadauTeD runs on CUDA tensors only (no CPU fallback)")
+        if self.ntspan != 2:
+            raise NotImplementedError("RadauTeD: tspan must be [M,2]")
+        if y0d is not None and tuple(y0d.shape) != (self.M, self.Ny, self.Ny):
+            raise ValueError(f"y0d must be [M,{self.Ny},{self.Ny}]")
+        self.y0d = None if y0d is None else y0d.to(y0.device, torch.float64).contiguous()
+        self.yd = None
+        self.sens_iters = None
+
+    def solve(self):
+        H, M, ny, dev = self._handle, self.M, self.Ny, self.device
+        y_out = torch.empty(M, ny, dtype=torch.float64, device=dev)
+        S_out = torch.empty(M, ny, ny, dtype=torch.float64, device=dev)
+        t_out = torch.empty(M, dtype=torch.float64, device=dev)
+        h_out = torch.empty(M, dtype=torch.float64, device=dev)
+        res = torch.empty(M, dtype=torch.int32, device=dev)
+        stats = torch.empty(M, 8, dtype=torch.int64, device=dev)
+        nstg = torch.empty(M, dtype=torch.int32, device=dev)
+        work = torch.empty(M, dtype=torch.int64, device=dev)
+        it = torch.empty(M, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check_h(H, H.L.jb200_solve_sens(H.h, _ptr(self.y), _ptr(self.tspan), _ptr(self.y0d), M, _ptr(y_out),
+                                                _ptr(S_out), _ptr(t_out), _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg),
+                                                _ptr(work), _ptr(it), _stream_ptr(dev)))
+        self.y, self.yd, self.t, self.h, self.nstg, self.work, self.sens_iters = y_out, S_out, t_out, h_out, nstg, work, it
+        self.stats = StatsTe.from_tensor(stats)
+        self.gpu_launches = 1
+        self.count = int(stats[:, 4].max().item()) if M else 0
+        self.res = res.to(torch.float64)
+        self.dydtf = self.dyns(self.t, self.y)
+        return self.res

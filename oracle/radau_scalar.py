@@ -108,6 +108,8 @@ class RadauResult:
     y_accept: list = field(default_factory=list)
     nstg_accept: list = field(default_factory=list)
     newt_accept: list = field(default_factory=list)
+    sens: np.ndarray | None = None     # forward sensitivities d y / d (directions of sens0), [Ny, Nd]
+    sens_iters: int = 0
 
 
 STAT_NAMES = ("FcnNbr", "JacNbr", "DecompNbr", "SolveNbr", "StepNbr", "AccptNbr",
@@ -176,7 +178,37 @@ def estrad(z, Dd, h, lus, Scal, f0, First, Reject, f, t, y, stats):
     return err
 
 
-def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record=False):
+def sens_step(jac, t, y, z, h, C, T, TI, ValP, lus, Scal, Sm, Nit, FNewt):
+    """Forward sensitivities across one accepted step (csrc/radau_core.cuh sens_step; the dual part of
+    RadauTeD's stage equations, src/cpp/radauted_impl.hpp:1746-1936): the linear system
+        Zs_i = h sum_j a_ij J(y + z_j) (S + Zs_j)
+    solved by the state's simplified-Newton iteration with the same factors, J at the converged stage points.
+    Sm [Ny, Nd] -> returns the updated Sm and the iterations spent."""
+    Ny, s = z.shape
+    Jq = [np.asarray(jac(t + C[q] * h, y + z[:, q]), dtype=np.float64) for q in range(s)]
+    out = Sm.copy()
+    iters = 0
+    for d in range(Sm.shape[1]):
+        Sd = Sm[:, d]
+        rs = 1.0 / max(1.0, float(np.max(np.abs(Sd))))
+        Zs = np.zeros((Ny, s))
+        Ws = np.zeros((Ny, s))
+        for _ in range(Nit + 10):
+            F = np.stack([Jq[q] @ (Sd + Zs[:, q]) for q in range(s)], axis=1)
+            zz = F @ TI.T                                        # zz_j = sum_q TI[j,q] F_q
+            dW = solvrad(zz, Ws, ValP, h, lus)
+            Ws = Ws + dW
+            Zs = Ws @ T.T
+            dZ = dW @ T.T
+            nrm = math.sqrt(float(np.sum((dZ / Scal[:, None] * rs) ** 2))) / math.sqrt(s * Ny)
+            iters += 1
+            if not nrm > 0.1 * FNewt:
+                break
+        out[:, d] = Sd + Zs[:, s - 1]
+    return out, iters
+
+
+def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record=False, sens0=None):
     """Integrate y' = f(t,y) from t0 to tfinal for ONE trajectory.
 
     f(t, y) -> ndarray[Ny];  jac(t, y) -> ndarray[Ny, Ny].
@@ -195,6 +227,8 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
     AbsTol = np.broadcast_to(np.asarray(op.AbsTol, dtype=np.float64), (Ny,)).copy()
     stats = {k: 0 for k in STAT_NAMES}
     out = RadauResult(y=y, t=t, h=0.0, res=0, stats=stats, nstg=op.NbrStg)
+    Sm = None if sens0 is None else np.array(sens0, dtype=np.float64).copy()   # forward sensitivities [Ny, Nd]
+    out.sens, out.sens_iters = Sm, 0
 
     Thet = op.JacRecompute
     Safe, Quot1, Quot2 = op.Safe, op.Quot1, op.Quot2
@@ -434,6 +468,9 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
                     hnew = h / quot
                 hacc = h
                 erracc = max(1.0e-2, err)
+            if Sm is not None:
+                Sm, its = sens_step(jac, t, y, z, h, C, T, TI, ValP, lus, Scal, Sm, Nit, FNewt)
+                out.sens, out.sens_iters = Sm, out.sens_iters + its
             h_old = h
             t = t + h
             Scal = AbsTol1 + RelTol1 * np.abs(y)    # :1080 (y before the update; dead value)

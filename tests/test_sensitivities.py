@@ -1,0 +1,129 @@
+"""Forward sensitivities (the reference's RadauTeD, tests/cpp/ode_solver_test.cpp:620-770).
+The reference's own check is central finite differences of the solver (rtol 1e-3 ... 1e-4): the same check is applied
+to the oracle (CPU) and to the GPU path, plus the exact answer for the harmonic oscillator and GPU == oracle."""
+import numpy as np
+import pytest
+import torch
+
+import janus_ode_b200 as jb
+from janus_ode_b200 import configs
+from oracle import problems
+from oracle.radau_scalar import RadauOptions, radau_solve
+
+
+def fd_sens(f, j, t0, tf, y0, op, rel=1e-7):
+    n = len(y0)
+    S = np.zeros((n, n))
+    for d in range(n):
+        hh = rel * max(abs(y0[d]), 1.0)
+        yp, ym = y0.copy(), y0.copy()
+        yp[d] += hh
+        ym[d] -= hh
+        S[:, d] = (radau_solve(f, j, t0, tf, yp, op).y - radau_solve(f, j, t0, tf, ym, op).y) / (2 * hh)
+    return S
+
+
+def test_oracle_sensitivities_harmonic_exact():
+    f, j = problems.harmonic(1.0, -1)
+    op = RadauOptions(RelTol=1e-9, AbsTol=1e-12)
+    y0 = np.array([0.3, -0.7])
+    r = radau_solve(f, j, 0.0, 2.0, y0, op, sens0=np.eye(2))
+    r0 = radau_solve(f, j, 0.0, 2.0, y0, op)
+    assert np.array_equal(r.y, r0.y) and r.stats == r0.stats            # the real part is untouched
+    c, s = np.cos(2.0), np.sin(2.0)
+    assert np.allclose(r.sens, np.array([[c, -s], [s, c]]), atol=1e-8)   # y = [p, x]: p' = -x, x' = p
+
+
+@pytest.mark.parametrize("mu,tf", [(1.0, 6.0), (30.0, 20.0)])
+def test_oracle_sensitivities_vs_finite_differences(mu, tf):
+    """the reference's test: vdP, tf = 6, sensitivities vs central differences at 1e-3 ... 1e-4 (here 2e-4)"""
+    f, j = problems.vdp(mu, +1)
+    op = RadauOptions(RelTol=1e-9, AbsTol=1e-12, MaxNbrStep=100000)
+    y0 = np.array([1.0, 1.0, 2.0, 0.0])
+    r = radau_solve(f, j, 0.0, tf, y0, op, sens0=np.eye(4))
+    S = fd_sens(f, j, 0.0, tf, y0, op)
+    assert r.res == 0 and r.sens_iters > 0
+    assert np.allclose(r.sens, S, rtol=2e-4, atol=2e-4 * np.abs(S).max())
+
+
+# ------------------------------------------------------------------ GPU
+DEV = "cuda:0"
+
+
+def gpu_sens(cfg, y0d=None):
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    r = jb.RadauTeD(dyn, dyn.jacobian, cfg["tspan"].to(DEV), cfg["y0"].to(DEV), cfg["options"], y0d=y0d)
+    r.solve()
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixed", [True, False])
+def test_gpu_real_part_is_bitwise_the_plain_solve(fixed):
+    cfg = configs.c2_vdp(M=512, fixed_order=fixed)
+    r = gpu_sens(cfg)
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    p = jb.RadauTe(dyn, dyn.jacobian, cfg["tspan"].to(DEV), cfg["y0"].to(DEV), cfg["options"])
+    p.solve()
+    assert torch.equal(r.y, p.y) and torch.equal(r.stats.raw, p.stats.raw) and torch.equal(r.h, p.h) and torch.equal(r.nstg, p.nstg)
+    assert bool((r.sens_iters > 0).all()) and bool(torch.isfinite(r.yd).all())
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_harmonic_exact_and_chain_rule():
+    cfg = configs.c1_harmonic(M=256)
+    r = gpu_sens(cfg)
+    tf = 10.0
+    c, s = np.cos(tf), np.sin(tf)
+    exact = torch.tensor([[c, -s], [s, c]], dtype=torch.float64, device=DEV)
+    assert torch.allclose(r.yd, exact.expand_as(r.yd), atol=1e-7)
+    # a non-identity dual part of y0 is propagated linearly: yd(S0) = yd(I) S0
+    S0 = torch.randn(256, 2, 2, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(0))
+    r2 = gpu_sens(cfg, y0d=S0)
+    assert torch.allclose(r2.yd, r.yd @ S0, rtol=1e-9, atol=1e-10)
+    assert torch.allclose(r.dydtf, torch.stack([-r.y[:, 1], r.y[:, 0]], 1), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mu,tf", [(1.0, 6.0), (30.0, 20.0)])
+def test_gpu_sensitivities_vs_oracle_and_finite_differences(mu, tf):
+    M = 32
+    g = torch.Generator().manual_seed(1)
+    y0 = torch.tensor([1.0, 1.0, 2.0, 0.0], dtype=torch.float64).repeat(M, 1)
+    y0[:, 2] += 0.5 * torch.rand(M, generator=g, dtype=torch.float64)
+    op = jb.OptionsTe(RelTol=1e-9, AbsTol=1e-12, MaxNbrStep=100000)
+    cfg = dict(ham=jb.VanDerPol(mu), sign=+1, y0=y0, tspan=torch.tensor([0.0, tf], dtype=torch.float64).repeat(M, 1), options=op)
+    r = gpu_sens(cfg)
+    assert bool((r.res == 0).all())
+    # oracle (same algorithm, numpy): tolerance-level agreement
+    f, j = problems.vdp(mu, +1)
+    for m in (0, 7, 31):
+        o = radau_solve(f, j, 0.0, tf, y0[m].numpy(), op, sens0=np.eye(4))
+        assert np.allclose(r.yd[m].cpu().numpy(), o.sens, rtol=1e-6, atol=1e-6 * np.abs(o.sens).max())
+    # finite differences of the GPU solver itself, all 2 * Ny * M perturbed solves in one batch
+    rel = 1e-7
+    yp = y0.repeat_interleave(8, 0).clone()
+    hh = torch.zeros(M * 8, dtype=torch.float64)
+    for d in range(4):
+        step = rel * torch.clamp(y0[:, d].abs(), min=1.0)
+        yp[2 * d::8, d] += step
+        yp[2 * d + 1::8, d] -= step
+        hh[2 * d::8] = step
+    dyn = jb.HamiltonianSystem(cfg["ham"], +1)
+    pb = jb.RadauTe(dyn, None, cfg["tspan"].repeat_interleave(8, 0).to(DEV), yp.to(DEV), op)
+    pb.solve()
+    Y = pb.y.cpu().reshape(M, 4, 2, 4)                      # [m, direction, +/-, component]
+    fd = (Y[:, :, 0, :] - Y[:, :, 1, :]) / (2 * hh.reshape(M, 4, 2)[:, :, 0:1])
+    fd = fd.permute(0, 2, 1)                                # [m, component, direction]
+    S = r.yd.cpu()
+    assert torch.allclose(S, fd, rtol=5e-4, atol=5e-4 * float(fd.abs().max()))
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_unsupported():
+    dyn = jb.HamiltonianSystem(jb.MlpHamiltonian(), -1)
+    y0 = torch.zeros(2, 16, dtype=torch.float64, device=DEV)
+    ts = torch.tensor([0.0, 1.0], dtype=torch.float64, device=DEV).repeat(2, 1)
+    with pytest.raises(jb.JanusB200Error, match="thread-resident"):
+        jb.RadauTeD(dyn, None, ts, y0, jb.OptionsTe()).solve()
