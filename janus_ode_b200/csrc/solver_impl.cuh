@@ -624,8 +624,8 @@ int launch_dopri(Handle* H, const dp::StepArgs& a, cudaStream_t st) {
 
 // forward sensitivities (radau_core.cuh: Sens / sens_step): one thread = one trajectory with its Ny x Ny
 // sensitivity matrix, all stage counts inside one kernel (order selection at run time)
-template <class Ham>
-__global__ void __launch_bounds__(JB_THREADS, 1) sens_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
+template <class Ham, int SM, bool VAR>
+__global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
                                                              const double* __restrict__ tspan, const double* __restrict__ S0,
                                                              long long M, double* __restrict__ y_out, double* __restrict__ S_out,
                                                              double* __restrict__ t_out, double* __restrict__ h_out,
@@ -634,15 +634,15 @@ __global__ void __launch_bounds__(JB_THREADS, 1) sens_kernel(const __grid_consta
                                                              int* __restrict__ sens_iters) {
   constexpr int NY = Ham::NV;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    Traj<NY, 7> T;
+    Traj<NY, SM> T;
     double y[NY];
     load_row<NY>(y0, m, y);
-    traj_init<Ham, NY, 7>(T, P, y, tspan[2 * m], tspan[2 * m + 1]);
+    traj_init<Ham, NY, SM>(T, P, y, tspan[2 * m], tspan[2 * m + 1]);
     Sens<NY> sn;
     sn.iters = 0;
 #pragma unroll
     for (int k = 0; k < NY * NY; k++) sn.S[k] = S0 ? S0[m * NY * NY + k] : ((k / NY == k % NY) ? 1.0 : 0.0);
-    integrate<Ham, NY, 7, true>(T, P, nullptr, &sn);
+    integrate<Ham, NY, SM, VAR>(T, P, nullptr, &sn);
     store_row<NY>(y_out, m, T.y);
 #pragma unroll
     for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = sn.S[k];
@@ -663,10 +663,14 @@ int launch_sens(Handle* H, const double* y0, const double* tspan, const double* 
 #ifdef JB_SLIM
   return fail(JB200_ENOTSUP, "this plugin was built without the sensitivity kernel");
 #else
-  auto kern = sens_kernel<Ham>;
-  const size_t smem = lc_smem_bytes<Ham::NV, 7>(JB_THREADS);
+  // fixed 3 stages (the common fixed-order configuration): its own lean instantiation; everything else -- other
+  // fixed stage counts, variable order -- runs the all-orders kernel with the order chosen at run time
+  const bool fixed3 = H->P.MinNbrStg == 3 && H->P.MaxNbrStg == 3;
+  auto kern = fixed3 ? sens_kernel<Ham, 3, false> : sens_kernel<Ham, 7, true>;
+  const size_t smem = fixed3 ? lc_smem_bytes<Ham::NV, 3>(JB_THREADS) : lc_smem_bytes<Ham::NV, 7>(JB_THREADS);
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long blocks = std::max<long long>(1, std::min<long long>((M + JB_THREADS - 1) / JB_THREADS, (long long)H->sm_count * 2));
+  // many small blocks in flight: trajectories differ in length by up to 5x, the block scheduler balances them
+  const long long blocks = std::max<long long>(1, (M + JB_THREADS - 1) / JB_THREADS);
   kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
                                                   sens_iters);
   JB_CUDA(cudaGetLastError());
