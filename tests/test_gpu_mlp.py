@@ -135,6 +135,18 @@ def test_output_at_tspan_points_bitwise(fixed, reverse):
     assert np.array_equal(r.stats.raw.cpu().numpy(), o["stats"])
 
 
+def test_failure_codes_rowwise():
+    """a NaN initial state fails only its own row (res = 2, radaute_impl.hpp:873-877); MaxNbrStep exhaustion gives 3"""
+    cfg = configs.c4_mlp(M=40)
+    cfg["y0"][7, 3] = float("nan")
+    cfg["y0"][21] = float("inf")
+    g = gpu_solve(cfg)
+    o = oracle_solve(cfg, "mirror")
+    assert np.array_equal(g["res"], o["res"]) and g["res"][7] == 2 and g["res"][21] == 2
+    ok = g["res"] == 0
+    assert ok.sum() == 38 and np.array_equal(g["y"][ok], o["y"][ok]) and np.array_equal(g["stats"], o["stats"])
+
+
 def test_unsupported_and_invalid():
     H = jb.MlpHamiltonian(8, 128, 0)
     dyn = jb.HamiltonianSystem(H, -1)
