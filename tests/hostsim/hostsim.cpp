@@ -146,6 +146,36 @@ extern "C" int hostsim_solve_epochs(int ham_id, const RadauParams* P, const doub
   return -1;
 }
 
+
+// ---- forward sensitivities (radau_core.cuh Sens / sens_step) on the CPU: the all-orders instantiation the GPU's
+// sens_kernel<Ham, 7, true> runs
+template <class Ham>
+static void run_sens(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out, double* S_out,
+                     long long* stats, int* iters) {
+  constexpr int NY = Ham::NV;
+  for (long long m = 0; m < M; m++) {
+    Traj<NY, 7> T;
+    traj_init<Ham, NY, 7>(T, P, y0 + m * NY, tspan[2 * m], tspan[2 * m + 1]);
+    Sens<NY> sn;
+    sn.iters = 0;
+    for (int k = 0; k < NY * NY; k++) sn.S[k] = (k / NY == k % NY) ? 1.0 : 0.0;
+    integrate<Ham, NY, 7, true>(T, P, nullptr, &sn);
+    for (int i = 0; i < NY; i++) y_out[m * NY + i] = T.y[i];
+    for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = sn.S[k];
+    for (int k = 0; k < 8; k++) stats[m * 8 + k] = T.st[k];
+    iters[m] = sn.iters;
+  }
+}
+
+extern "C" int hostsim_solve_sens(int ham_id, const RadauParams* P, const double* y0, const double* tspan, long long M,
+                                  double* y_out, double* S_out, long long* stats, int* iters) {
+  switch (ham_id) {
+    case HAM_HARMONIC: run_sens<HamHarmonic>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
+    case HAM_VDP: run_sens<HamVdp>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
+  }
+  return -1;
+}
+
 // ---- MLP Hamiltonian path (csrc/mlp_phase.cuh): the same phase functions the GPU kernels wrap,
 // driven by the same pass protocol; the stage / Jacobian evaluations (tile GEMMs on the GPU) are
 // delegated to callbacks (the mirror oracle's scalar evaluation, passed in from the test).

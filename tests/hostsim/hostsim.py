@@ -66,6 +66,25 @@ def solve_mlp(par, sign, y0, tspan, opts, oracle_lib):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, work=work)
 
 
+def solve_sens(ham, par, sign, y0, tspan, opts):
+    """forward sensitivities d y / d y0 by the CUDA core's sens_step, on the CPU"""
+    build()
+    lib = C.CDLL(_SO)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, ny = y0.shape
+    P = _params(lib, opts, ny, sign, par)
+    y = np.empty_like(y0)
+    S = np.empty((M, ny, ny))
+    stats = np.empty((M, 8), dtype=np.int64)
+    iters = np.empty(M, dtype=np.int32)
+    rc = lib.hostsim_solve_sens(C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(S),
+                                stats.ctypes.data_as(C.POINTER(C.c_longlong)), iters.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return dict(y=y, sens=S, stats=stats, iters=iters)
+
+
 def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
     """epochs_K > 0: emulate the variable-order epoch scheme (park / regroup / resume every K passes)."""
     build()

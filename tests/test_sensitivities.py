@@ -46,6 +46,28 @@ def test_oracle_sensitivities_vs_finite_differences(mu, tf):
     assert np.allclose(r.sens, S, rtol=2e-4, atol=2e-4 * np.abs(S).max())
 
 
+def test_cuda_core_sens_step_on_host_vs_oracle():
+    """the device code itself (csrc/radau_core.cuh sens_step, compiled for the host by tests/hostsim) against the numpy
+    oracle: same algorithm -> tolerance-level agreement; the real part equals the plain host-sim solve bit for bit"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import hostsim
+    op = jb.OptionsTe(RelTol=1e-9, AbsTol=1e-12, MaxNbrStep=100000)
+    y0 = np.array([[1.0, 1.0, 2.0, 0.0], [1.0, 1.0, 2.3, 0.0], [0.5, -1.0, 1.7, 0.2]])
+    ts = np.tile(np.array([0.0, 6.0]), (3, 1))
+    h = hostsim.solve_sens("vdp", [3.0], +1, y0, ts, op)
+    p = hostsim.solve("vdp", [3.0], +1, y0, ts, op)
+    assert np.array_equal(h["y"], p["y"]) and np.array_equal(h["stats"], p["stats"])
+    f, j = problems.vdp(3.0, +1)
+    for m in range(3):
+        o = radau_solve(f, j, 0.0, 6.0, y0[m], op, sens0=np.eye(4))
+        assert np.allclose(h["sens"][m], o.sens, rtol=1e-6, atol=1e-6 * np.abs(o.sens).max())
+    hh = hostsim.solve_sens("harmonic", [1.0], -1, np.array([[0.3, -0.7]]), np.array([[0.0, 2.0]]), op)
+    c, s = np.cos(2.0), np.sin(2.0)
+    assert np.allclose(hh["sens"][0], np.array([[c, -s], [s, c]]), atol=1e-8)
+
+
 # ------------------------------------------------------------------ GPU
 DEV = "cuda:0"
 
