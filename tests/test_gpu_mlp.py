@@ -135,6 +135,32 @@ def test_output_at_tspan_points_bitwise(fixed, reverse):
     assert np.array_equal(r.stats.raw.cpu().numpy(), o["stats"])
 
 
+def test_full_size_properties():
+    """config 4 at BASELINE.json's full size (2^20 trajectories): size-independent properties -- every trajectory ends at
+    tfinal with res = 0, H is conserved along the flow (canonical sign), integrating back returns to y0 -- plus bit
+    parity with the oracle on a strided sample."""
+    from oracle import ham as oham
+    M = 1 << 20
+    cfg = configs.c4_mlp(M=M)
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    y0, ts = cfg["y0"].to(DEV), cfg["tspan"].to(DEV)
+    r = jb.RadauTe(dyn, None, ts, y0, cfg["options"])
+    res = r.solve()
+    assert bool((res == 0).all()) and bool((r.t == 1.0).all())
+    idx = torch.arange(0, M, 257)[:2048]
+    o = c_oracle.solve("mlp", np.array(cfg["ham"].params), -1, cfg["y0"][idx].numpy(), cfg["tspan"][idx].numpy(),
+                       cfg["options"], arith="mirror")
+    assert np.array_equal(r.y[idx.to(DEV)].cpu().numpy(), o["y"]) and np.array_equal(r.stats.raw[idx.to(DEV)].cpu().numpy(), o["stats"])
+    H = oham.MLPHamiltonian(N=8, width=128, seed=0)
+    ya, yb = cfg["y0"][idx], r.y[idx.to(DEV)].cpu()
+    Ha, Hb = H(ya[:, 8:], ya[:, :8]), H(yb[:, 8:], yb[:, :8])          # y = [p, x]
+    assert float((Hb - Ha).abs().max()) < 1e-6
+    back = jb.RadauTe(dyn, None, torch.flip(ts, [1]).contiguous(), r.y, cfg["options"])
+    back.solve()
+    assert bool((back.res == 0).all())
+    assert float((back.y - y0).abs().max()) < 1e-5
+
+
 def test_failure_codes_rowwise():
     """a NaN initial state fails only its own row (res = 2, radaute_impl.hpp:873-877); MaxNbrStep exhaustion gives 3"""
     cfg = configs.c4_mlp(M=40)
