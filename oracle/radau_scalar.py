@@ -3,13 +3,20 @@
 TEST INFRASTRUCTURE ONLY.  Nothing in janus_ode_b200/ may import this module; only
 tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
 
-PARITY STATUS: "parity unpinned" for final states / step counts -- the reference
-(optstat/janus-ode) cannot be compiled or imported in this environment (it needs the
-un-vendored janus-tensor-dual / janus-linear headers, Eigen3, SUNDIALS, PETSc) and it
-ships no golden vectors for a solve.  What IS pinned: the coefficient tables
-(oracle/tools/gen_tables.py), the closed-form Hamiltonian fixtures of the reference's
-GTest file (tests/test_oracle_ham.py) and tolerance-level agreement with SciPy Radau on
-the reference's own cross-check scripts (tests/test_oracle_scipy.py).
+PARITY STATUS: "parity unpinned" for final states / step counts of a WHOLE Radau solve --
+the reference's RadauTe / RadauTeD cannot be compiled or imported in this environment (they
+need the un-vendored janus-tensor-dual / janus-linear headers, Eigen3, SUNDIALS, PETSc) and
+the reference ships no golden vectors for a solve.  What IS pinned:
+  * against LIVE reference code run in the build container (tests/golden/make_reference_pins.py,
+    tests/test_reference_pins.py): solvrad() == the reference's Python solve_radau, estrad() ==
+    its estrad incl. the First-step retry, the C / Dd literals and gamma, alpha +- i beta ==
+    its radau_tables (src/python/odesolvers/src/odesolvers/{solvrad,estrad,radau_tables}.py);
+  * the coefficient tables across radau.m and radaute_impl.hpp (oracle/tools/gen_tables.py), the
+    closed-form Hamiltonian fixtures of the reference's GTest file (tests/test_oracle_ham.py),
+    tolerance-level agreement with SciPy Radau on the reference's own cross-check scripts
+    (tests/test_oracle_scipy.py);
+  * sens_step(): the reference's own criterion for RadauTeD (finite differences of the solver,
+    tests/cpp/ode_solver_test.cpp:620-770) and the exact harmonic-oscillator sensitivities.
 
 What is restated, line by line:
   control flow      /root/reference/src/matlab/radau.m:630-1256 (the scalar truth the C++
