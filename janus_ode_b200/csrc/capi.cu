@@ -397,7 +397,8 @@ int jb200_state_create(void* handle, const double* y0, const double* tspan, int6
   if (M > 0) {
     int rc = ops->st_init(H, S->ws, y0, tspan, 2, (long long)M, (cudaStream_t)stream);
     if (rc) {
-      ws_free(S->ws);
+      if (ops->st_free) ops->st_free(S->ws);
+      else ws_free(S->ws);
       delete S;
       return rc;
     }
@@ -424,7 +425,9 @@ int jb200_state_read(void* state, double* y, double* t, double* hnext, double* h
 void jb200_state_destroy(void* state) {
   State* S = (State*)state;
   if (!S) return;
-  ws_free(S->ws);
+  const HamOps* ops = ham_ops(S->H->ham_id);
+  if (ops && ops->st_free) ops->st_free(S->ws);
+  else ws_free(S->ws);
   delete S;
 }
 

@@ -47,6 +47,7 @@ struct TrajS {   // per-trajectory scalars (array of structs)
   unsigned flags;   // PF_* of radau_core.cuh
   int phase;
   int nout;         // output points written so far (output at the tspan points, OutFlag 3)
+  int acc_mark;     // incremental protocol: accepted-step count when the current step() call began
 };
 
 // vector state: structure of arrays, element e of trajectory i at arr[e * M + i] (one thread per
@@ -257,6 +258,7 @@ JB_HD void ph_init(const State& S, const RadauParams& P, long long i, const doub
   s.hacc = 0.0;
   s.erracc = 0.0;
   s.hnew = s.err = s.NewNrm = s.OldNrm = s.thqold = 0.0;
+  s.acc_mark = 0;
   s.phase = PH_F0_EVAL;
   S.sc[i] = s;
 }
@@ -273,10 +275,30 @@ JB_HD void ph_init_b(const State& S, long long i) {
   s.phase = nanf ? PH_FINISHED : PH_IDLE;
 }
 
-// run_epoch's loop guard + the first lines of pass_head (radau.m:712, :733-735)
-JB_HD void ph_head(const State& S, const RadauParams& P, long long i) {
+// incremental protocol (RadauT.step(htry, ...), src/python/seulext.py:158-581): start of a step() call -- an optional
+// trial step chosen by the caller (like radau.m:645-655; same rule as rearm_kernel of the thread-resident path)
+JB_HD void ph_rearm(const State& S, long long i, const double* htry) {
   TrajS& s = S.sc[i];
   if (s.phase == PH_FINISHED) return;
+  if (htry && htry[i] != s.h) {
+    double h = s.PosNeg * fmin(fabs(htry[i]), fabs(s.tfinal - s.t0));
+    s.flags |= PF_NEED_LU;
+    if ((s.t + h * 1.0001 - s.tfinal) * s.PosNeg >= 0) {
+      h = s.tfinal - s.t;
+      s.flags |= PF_LAST;
+    } else {
+      s.flags &= ~PF_LAST;
+    }
+    s.h = h;
+  }
+  s.acc_mark = s.st[ST_ACC];
+}
+
+// run_epoch's loop guard + the first lines of pass_head (radau.m:712, :733-735)
+JB_HD void ph_head(const State& S, const RadauParams& P, long long i, bool stop_on_accept = false) {
+  TrajS& s = S.sc[i];
+  if (s.phase == PH_FINISHED) return;
+  if (stop_on_accept && s.st[ST_ACC] != s.acc_mark) return;   // incremental protocol: this call's step is done
   if (!(s.res == 0 && traj_active(s.PosNeg, s.t, s.tfinal, s.st[ST_STEP], P.MaxNbrStep))) {
     if (s.res == 0 && s.PosNeg * s.t < s.PosNeg * s.tfinal) s.res = 3;
     s.phase = PH_FINISHED;

@@ -693,6 +693,7 @@ struct HamOps {
   int (*dopri)(Handle*, const dp::StepArgs&, cudaStream_t) = nullptr;   // explicit DOPRI853 step (thread-resident Hamiltonians)
   int (*sens)(Handle*, const double*, const double*, const double*, long long, double*, double*, double*, double*, int*,
               long long*, int*, long long*, int*, cudaStream_t) = nullptr;   // solve with forward sensitivities
+  void (*st_free)(EpochWS&) = nullptr;   // optional: the state of the incremental protocol is not a plain EpochWS
 };
 template <class Ham>
 HamOps make_ops() {

@@ -22,10 +22,8 @@ namespace mlp {
 constexpr int NPAR = 2 + WD * NV + WD + 2 * (WD * WD + WD) + WD + 1;
 enum { C_ACTIVE = 0, C_JAC, C_ROWS_A, C_TRAJ_A, C_ROWS_B, C_TRAJ_B, C_ERR, C_F0, C_LU, C_N };
 
-struct Ctx {
-  double* d_w = nullptr;   // all weight matrices, both orientations
-  Weights W{};
-  long long cap = 0;       // trajectories the workspace holds
+struct Work {              // the phase workspace of one batch (a solve, or a state of the incremental protocol)
+  long long cap = 0;       // trajectories it holds
   int cap_SM = 0;
   State S{};
   void* pool = nullptr;
@@ -33,6 +31,15 @@ struct Ctx {
   int *d_rows[2] = {nullptr, nullptr}, *d_trajs[2] = {nullptr, nullptr};
   int *d_jac = nullptr, *d_err = nullptr, *d_f0 = nullptr, *d_lu = nullptr, *d_cnt = nullptr;
   int* h_cnt = nullptr;    // pinned
+};
+struct Ctx {
+  double* d_w = nullptr;   // all weight matrices, both orientations
+  Weights W{};
+  Work w;                  // workspace of jb200_solve / jb200_eval_jac
+};
+struct StepObj {           // jb200_state_*: a batch parked between step() calls
+  Work w;
+  long long M = 0;
 };
 
 __device__ __forceinline__ int append(int* counter, int n) { return atomicAdd(counter, n); }
@@ -45,13 +52,32 @@ __global__ void init_b_kernel(const State S) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < S.M) ph_init_b(S, i);
 }
-__global__ void head_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* jac_list) {
+__global__ void head_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* jac_list, int stop_on_accept) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= S.M) return;
-  ph_head(S, P, i);
+  ph_head(S, P, i, stop_on_accept != 0);
   const int ph = S.sc[i].phase;
-  if (ph != PH_FINISHED) atomicAdd(&cnt[C_ACTIVE], 1);
+  if (ph == PH_WANT_JAC || ph == PH_PREP) atomicAdd(&cnt[C_ACTIVE], 1);   // takes part in this pass
   if (ph == PH_WANT_JAC) jac_list[append(&cnt[C_JAC], 1)] = (int)i;
+}
+__global__ void rearm_kernel_mlp(const State S, const double* __restrict__ htry) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < S.M) ph_rearm(S, i, htry);
+}
+__global__ void state_read_kernel_mlp(const State S, double* __restrict__ y, double* __restrict__ t, double* __restrict__ hnext,
+                                      double* __restrict__ hdid, int* __restrict__ res, long long* __restrict__ stats,
+                                      int* __restrict__ nstg, int* __restrict__ done) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= S.M) return;
+  const TrajS s = S.sc[i];
+  for (int e = 0; e < MN; e++) y[i * MN + e] = S.y[(size_t)e * S.M + i];
+  t[i] = s.t;
+  hnext[i] = s.h;
+  hdid[i] = s.h_old;
+  res[i] = s.res;
+  for (int k = 0; k < 8; k++) stats[i * 8 + k] = s.st[k];
+  if (nstg) nstg[i] = s.NbrStg;
+  if (done) done[i] = s.phase == PH_FINISHED ? 1 : 0;
 }
 __device__ __forceinline__ void enqueue(const State& S, long long i, int* cnt, int c_rows, int c_traj, int* rows, int* trajs,
                                         int* err_list, int* f0_list) {
@@ -275,32 +301,30 @@ __global__ void __launch_bounds__(256) lu16_solve_kernel(long long M, const doub
 
 static Ctx* ctx_of(Handle* H) { return (Ctx*)H->ext; }
 
-static void free_workspace(Ctx* C) {
-  cudaFree(C->pool);
-  cudaFree(C->d_act);
-  for (int k = 0; k < 2; k++) { cudaFree(C->d_rows[k]); cudaFree(C->d_trajs[k]); }
-  cudaFree(C->d_jac); cudaFree(C->d_err); cudaFree(C->d_f0); cudaFree(C->d_lu);
-  C->pool = nullptr; C->d_act = nullptr; C->d_rows[0] = C->d_rows[1] = C->d_trajs[0] = C->d_trajs[1] = nullptr;
-  C->d_jac = C->d_err = C->d_f0 = C->d_lu = nullptr;
-  C->cap = 0;
+static void free_workspace(Work& C) {
+  cudaFree(C.pool);
+  cudaFree(C.d_act);
+  for (int k = 0; k < 2; k++) { cudaFree(C.d_rows[k]); cudaFree(C.d_trajs[k]); }
+  cudaFree(C.d_jac); cudaFree(C.d_err); cudaFree(C.d_f0); cudaFree(C.d_lu); cudaFree(C.d_cnt);
+  if (C.h_cnt) cudaFreeHost(C.h_cnt);
+  C = Work();
 }
 
-static int ensure(Handle* H, long long M, bool need_state) {
-  Ctx* C = ctx_of(H);
+static int ensure(Handle* H, Work& C, long long M, bool need_state) {
   const int SM = H->P.MaxNbrStg;
-  if (M <= C->cap && SM <= C->cap_SM && (C->pool || !need_state)) return 0;
+  if (M <= C.cap && SM <= C.cap_SM && (C.pool || !need_state)) return 0;
   if (M > (1LL << 27)) return fail(JB200_EINVAL, "MLP Hamiltonian path: M must be <= 2^27 per GPU");
   free_workspace(C);
-  const int nq = (SM - 1) / 2 > 0 ? (SM - 1) / 2 : 1;
-  JB_CUDA(cudaMalloc(&C->d_act, sizeof(double) * 5 * WD * (size_t)M));
+  JB_CUDA(cudaMalloc(&C.d_act, sizeof(double) * 5 * WD * (size_t)M));
+  JB_CUDA(cudaMalloc(&C.d_cnt, sizeof(int) * C_N));
+  JB_CUDA(cudaMallocHost(&C.h_cnt, sizeof(int) * C_N));
   if (need_state) {
-    (void)nq;
     const size_t per_d = MN * 5 + MN * MN + (size_t)SM * MN * 4 + 1 + (size_t)lu_doubles(SM);
     const size_t per_i = (size_t)lu_ints(SM);
     const size_t bytes = sizeof(TrajS) * (size_t)M + 1024 + sizeof(double) * per_d * (size_t)M + sizeof(int) * per_i * (size_t)M;
-    JB_CUDA(cudaMalloc(&C->pool, bytes));
-    char* p = (char*)C->pool;
-    State& S = C->S;
+    JB_CUDA(cudaMalloc(&C.pool, bytes));
+    char* p = (char*)C.pool;
+    State& S = C.S;
     S.M = M;
     S.SM = SM;
     S.sc = (TrajS*)p;
@@ -315,16 +339,16 @@ static int ensure(Handle* H, long long M, bool need_state) {
     S.LU = take(S.lud);
     S.LUpiv = (int*)d;
     for (int k = 0; k < 2; k++) {
-      JB_CUDA(cudaMalloc(&C->d_rows[k], sizeof(int) * (size_t)SM * M));
-      JB_CUDA(cudaMalloc(&C->d_trajs[k], sizeof(int) * (size_t)M));
+      JB_CUDA(cudaMalloc(&C.d_rows[k], sizeof(int) * (size_t)SM * M));
+      JB_CUDA(cudaMalloc(&C.d_trajs[k], sizeof(int) * (size_t)M));
     }
-    JB_CUDA(cudaMalloc(&C->d_jac, sizeof(int) * (size_t)M));
-    JB_CUDA(cudaMalloc(&C->d_err, sizeof(int) * (size_t)M));
-    JB_CUDA(cudaMalloc(&C->d_f0, sizeof(int) * (size_t)M));
-    JB_CUDA(cudaMalloc(&C->d_lu, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C.d_jac, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C.d_err, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C.d_f0, sizeof(int) * (size_t)M));
+    JB_CUDA(cudaMalloc(&C.d_lu, sizeof(int) * (size_t)M));
   }
-  C->cap = M;
-  C->cap_SM = SM;
+  C.cap = M;
+  C.cap_SM = SM;
   return 0;
 }
 
@@ -347,35 +371,36 @@ static int launch_hess(Handle* H, const HessIO& io, int n, cudaStream_t st) {
   return 0;
 }
 
-static int read_counters(Ctx* C, cudaStream_t st) {
+static int read_counters(Work* C, cudaStream_t st) {
   JB_CUDA(cudaMemcpyAsync(C->h_cnt, C->d_cnt, sizeof(int) * C_N, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
-static int solve(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out, double* h_out,
-                 int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
-  int rc = ensure(H, M, true);
-  if (rc) return rc;
-  Ctx* C = ctx_of(H);
-  State S = C->S;
-  S.M = M;   // element stride = this batch (the pool was sized for cap >= M)
-  S.ntspan = dense.ntspan;
-  S.tspan = tspan;
-  S.tout = dense.tout;
-  S.yout = dense.yout;
-  const RadauParams& P = H->P;
-  H->launches = 0;
+// initial state of every trajectory: ph_init, f(t0, y0) (activations saved for the first Jacobian), NaN check
+static int begin(Handle* H, Work* C, State& S, const double* y0, long long M, cudaStream_t st) {
   const unsigned gb = (unsigned)((M + 127) / 128);
-  auto blocks = [](int n) { return (unsigned)((n + 127) / 128); };
-  init_kernel<<<gb, 128, 0, st>>>(S, P, y0);
-  GradIO g0{nullptr, nullptr, (int)M, S.y, 1, M, nullptr, 0, 0, nullptr, S.f0, 1, M, C->d_act, P.sign};
-  if ((rc = launch_grad(H, g0, (int)M, st))) return rc;
+  init_kernel<<<gb, 128, 0, st>>>(S, H->P, y0);
+  GradIO g0{nullptr, nullptr, (int)M, S.y, 1, M, nullptr, 0, 0, nullptr, S.f0, 1, M, C->d_act, H->P.sign};
+  const int rc = launch_grad(H, g0, (int)M, st);
+  if (rc) return rc;
   init_b_kernel<<<gb, 128, 0, st>>>(S);
   H->launches += 2;
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// passes (one attempted step of every participating trajectory each) until nobody is left; stop_on_accept:
+// a trajectory stops participating once it has accepted a step in this call (incremental protocol)
+static int run_passes(Handle* H, Work* C, State& S, bool stop_on_accept, cudaStream_t st) {
+  const long long M = S.M;
+  const RadauParams& P = H->P;
+  const unsigned gb = (unsigned)((M + 127) / 128);
+  auto blocks = [](int n) { return (unsigned)((n + 127) / 128); };
+  int rc = 0;
   for (;;) {
     JB_CUDA(cudaMemsetAsync(C->d_cnt, 0, sizeof(int) * C_N, st));
-    head_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_jac);
+    head_kernel<<<gb, 128, 0, st>>>(S, P, C->d_cnt, C->d_jac, stop_on_accept ? 1 : 0);
     H->launches += 1;
     if ((rc = read_counters(C, st))) return rc;
     if (C->h_cnt[C_ACTIVE] == 0) break;
@@ -422,7 +447,30 @@ static int solve(Handle* H, const double* y0, const double* tspan, long long M, 
       H->launches += 1;
     }
   }
-  output_kernel<<<gb, 128, 0, st>>>(S, y_out, t_out, h_out, res, stats, nstg, work, dense.nout);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static State bind(Work* C, long long M, const double* tspan, const DenseArgs& dense) {
+  State S = C->S;
+  S.M = M;   // element stride = this batch (the pool was sized for cap >= M)
+  S.ntspan = dense.ntspan;
+  S.tspan = tspan;
+  S.tout = dense.tout;
+  S.yout = dense.yout;
+  return S;
+}
+
+static int solve(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out, double* h_out,
+                 int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  Work* C = &ctx_of(H)->w;
+  int rc = ensure(H, *C, M, true);
+  if (rc) return rc;
+  State S = bind(C, M, tspan, dense);
+  H->launches = 0;
+  if ((rc = begin(H, C, S, y0, M, st))) return rc;
+  if ((rc = run_passes(H, C, S, false, st))) return rc;
+  output_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(S, y_out, t_out, h_out, res, stats, nstg, work, dense.nout);
   H->launches += 1;
   JB_CUDA(cudaGetLastError());
   return 0;
@@ -434,9 +482,9 @@ static int dyns(Handle* H, const double* y, long long M, double* ydot, cudaStrea
 }
 
 static int jac(Handle* H, const double* y, long long M, double* J, cudaStream_t st) {
-  int rc = ensure(H, M, false);
+  Work* C = &ctx_of(H)->w;
+  int rc = ensure(H, *C, M, false);
   if (rc) return rc;
-  Ctx* C = ctx_of(H);
   double* tmp = nullptr;
   JB_CUDA(cudaMalloc(&tmp, sizeof(double) * MN * (size_t)M));
   const GradIO io{nullptr, nullptr, (int)M, y, MN, 1, nullptr, 0, 0, nullptr, tmp, MN, 1, C->d_act, H->P.sign};
@@ -482,8 +530,6 @@ static int create(Handle* H, const double* par, int npar) {
   JB_CUDA(cudaMemcpy(C->d_w, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
   C->W = Weights{C->d_w + oW1t, C->d_w + oW2t, C->d_w + oW3t, C->d_w + oW3, C->d_w + oW2, C->d_w + oW1,
                  C->d_w + ob1,  C->d_w + ob2,  C->d_w + ob3,  C->d_w + oW4};
-  JB_CUDA(cudaMalloc(&C->d_cnt, sizeof(int) * C_N));
-  JB_CUDA(cudaMallocHost(&C->h_cnt, sizeof(int) * C_N));
   JB_CUDA(cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   JB_CUDA(cudaFuncSetAttribute(mlp_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   return 0;
@@ -492,22 +538,54 @@ static int create(Handle* H, const double* par, int npar) {
 static void destroy(Handle* H) {
   Ctx* C = ctx_of(H);
   if (!C) return;
-  free_workspace(C);
+  free_workspace(C->w);
   cudaFree(C->d_w);
-  cudaFree(C->d_cnt);
-  if (C->h_cnt) cudaFreeHost(C->h_cnt);
   delete C;
   H->ext = nullptr;
 }
 
-static int st_init(Handle*, EpochWS&, const double*, const double*, int, long long, cudaStream_t) {
-  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+// ---- incremental protocol (jb200_state_*): the batch lives in its own workspace between step() calls; the
+// EpochWS of the generic State only carries the pointer (parked) and the batch size
+static int st_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int ntspan, long long M, cudaStream_t st) {
+  if (ntspan != 2) return fail(JB200_EINVAL, "state protocol: tspan must be [M,2]");
+  StepObj* o = new StepObj();
+  o->M = M;
+  ws.parked = o;
+  ws.M = M;
+  int rc = ensure(H, o->w, M, true);
+  if (rc) return rc;
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
+  // tspan is only read here (t0, tfinal go into the per-trajectory scalars): the caller may free it afterwards
+  State S = bind(&o->w, M, tspan, none);
+  H->launches = 0;
+  return begin(H, &o->w, S, y0, M, st);
 }
-static int st_step(Handle*, EpochWS&, const double*, cudaStream_t) {
-  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+static int st_step(Handle* H, EpochWS& ws, const double* htry, cudaStream_t st) {
+  StepObj* o = (StepObj*)ws.parked;
+  if (!o || o->M <= 0) return 0;
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
+  State S = bind(&o->w, o->M, nullptr, none);
+  H->launches = 1;
+  rearm_kernel_mlp<<<(unsigned)((o->M + 127) / 128), 128, 0, st>>>(S, htry);
+  return run_passes(H, &o->w, S, true, st);
 }
-static int st_read(Handle*, EpochWS&, double*, double*, double*, double*, int*, long long*, int*, int*, cudaStream_t) {
-  return fail(JB200_ENOTSUP, "MLP Hamiltonian path: the incremental step protocol is not available yet");
+static int st_read(Handle*, EpochWS& ws, double* y, double* t, double* hnext, double* hdid, int* res, long long* stats, int* nstg,
+                   int* done, cudaStream_t st) {
+  StepObj* o = (StepObj*)ws.parked;
+  if (!o || o->M <= 0) return 0;
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
+  State S = bind(&o->w, o->M, nullptr, none);
+  state_read_kernel_mlp<<<(unsigned)((o->M + 127) / 128), 128, 0, st>>>(S, y, t, hnext, hdid, res, stats, nstg, done);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+static void st_free(EpochWS& ws) {
+  StepObj* o = (StepObj*)ws.parked;
+  if (o) {
+    free_workspace(o->w);
+    delete o;
+  }
+  ws = EpochWS();
 }
 
 }  // namespace mlp
@@ -522,6 +600,7 @@ int lu16_solve_launch(long long M, const double* Are, const double* Aim, const d
 }
 
 extern const HamOps jb_ops_mlp = HamOps{mlp::MN,       mlp::NPAR,     &mlp::solve,   &mlp::dyns,   &mlp::jac,
-                                        &mlp::st_init, &mlp::st_step, &mlp::st_read, &mlp::create, &mlp::destroy};
+                                        &mlp::st_init, &mlp::st_step, &mlp::st_read, &mlp::create, &mlp::destroy,
+                                        nullptr,       nullptr,       &mlp::st_free};
 
 }  // namespace jb

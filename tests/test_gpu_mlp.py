@@ -161,6 +161,31 @@ def test_full_size_properties():
     assert float((back.y - y0).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("fixed", [True, False])
+def test_step_protocol_reproduces_solve_bit_for_bit(fixed):
+    """state = RadauState(...); state = RadauT(opts).step(htry, dyns, ft, state) -- one accepted step per trajectory and
+    call (src/python/seulext.py:158-581); looping it is the same integration as solve(), bit for bit"""
+    cfg = configs.c4_mlp(M=100, fixed_order=fixed)
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    ft = cfg["tspan"][:, 1].to(DEV)
+    state = jb.RadauState(cfg["y0"].to(DEV), cfg["tspan"][:, 0].to(DEV), atol=1e-9, rtol=1e-6, ft=ft)
+    solver = jb.RadauT(cfg["options"])
+    htry, n = cfg["options"].InitialStep, 0
+    x_prev = state.x.clone()
+    while not bool(state.done.all()):
+        state = solver.step(htry, dyn, ft, state)
+        htry = state.hnext
+        live = ~state.done
+        assert torch.equal((x_prev + state.hdid)[live], state.x[live])
+        x_prev = state.x.clone()
+        n += 1
+        assert n < 200
+    o = oracle_solve(cfg, "mirror")
+    assert np.array_equal(state.y.cpu().numpy(), o["y"]) and np.array_equal(state.x.cpu().numpy(), o["t"])
+    assert np.array_equal(state.stats.raw.cpu().numpy(), o["stats"]) and bool((state.res == 0).all())
+    assert n == int(o["stats"][:, 5].max())
+
+
 def test_failure_codes_rowwise():
     """a NaN initial state fails only its own row (res = 2, radaute_impl.hpp:873-877); MaxNbrStep exhaustion gives 3"""
     cfg = configs.c4_mlp(M=40)
@@ -178,8 +203,8 @@ def test_unsupported_and_invalid():
     dyn = jb.HamiltonianSystem(H, -1)
     y0 = torch.zeros(4, 16, dtype=torch.float64, device=DEV)
     tgrid = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64, device=DEV).repeat(4, 1)
-    with pytest.raises(jb.JanusB200Error, match="not available"):
-        jb.RadauT(jb.OptionsTe()).step(0.01, dyn, 1.0, jb.RadauState(y0, torch.zeros(4, dtype=torch.float64, device=DEV), ft=1.0))
+    with pytest.raises(jb.JanusB200Error, match="thread-resident"):
+        jb.Dopri853Te(y0, None, 0.0, 1e-6, 1e-6, False, dyn).step(0.1)
     bad = jb.Hamiltonian("mlp", 5, 8, H.params[:100])
     with pytest.raises(ValueError, match="parameters"):
         jb.RadauTe(jb.HamiltonianSystem(bad, -1), None, tgrid[:, [0, 2]].contiguous(), y0, jb.OptionsTe()).solve()
