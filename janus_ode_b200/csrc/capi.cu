@@ -300,6 +300,8 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
   }
   if (const char* ep = std::getenv("JB200_EPOCH_PASSES")) H->epoch_passes = std::max(1, atoi(ep));
   if (const char* fe = std::getenv("JB200_FIXED_EPOCHS")) H->fixed_epochs = atoi(fe) != 0;
+  if (const char* ps = std::getenv("JB200_PRESORT")) H->presort = atoi(ps) != 0;
+  if (const char* eh = std::getenv("JB200_EPOCH_HORDER")) H->epoch_horder = atoi(eh);
   *handle = H;
   return 0;
 }

@@ -16,6 +16,8 @@
 // see radau_core.cuh).
 #pragma once
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED)
                                                     double* __restrict__ h_out, int* __restrict__ res,
                                                     long long* __restrict__ stats, int* __restrict__ nstg,
                                                     long long* __restrict__ work, const DenseArgs dense,
-                                                    unsigned long long* __restrict__ counter) {
+                                                    unsigned long long* __restrict__ counter,
+                                                    const int* __restrict__ order) {
   constexpr int NY = Ham::NV;
   Traj<NY, SM> T;
   long long m = -1;
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED)
     if (!have) {
       m = (long long)atomicAdd(counter, 1ull);
       if (m >= M) break;
+      if (order) m = order[m];   // trajectories pre-sorted by H(y0): the lanes of a warp start as phase-space neighbours
       double y[NY];
       load_row<NY>(y0, m, y);
       traj_init<Ham, NY, SM>(T, P, y, __ldg(tspan + m * nts), __ldg(tspan + m * nts + nts - 1));
@@ -205,6 +209,32 @@ static __global__ void scatter_kernel(const unsigned short* __restrict__ tag, lo
 #ifndef JB_THREADS_HI
 #define JB_THREADS_HI 128
 #endif
+// ---- pre-sort of a batch by the value of the Hamiltonian at the initial state (a scheduling hint only).
+// Trajectories that start as neighbours in phase space take nearly the same step sequence, so a warp built from
+// 32 neighbours iterates Newton the same number of times, accepts / rejects together and finishes together.
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_bits(unsigned long long u) {
+  const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double((long long)b);
+}
+template <class Ham>
+__global__ void hkey_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0, long long M,
+                            unsigned long long* __restrict__ key, int* __restrict__ idx) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    double y[NY];
+    load_row<NY>(y0, m, y);
+    const double u = Ham::HAS_CONTROL ? Ham::control(y, P.ham_par) : 0.0;
+    double v = ham_eval1<Ham>(y, P.ham_par, u, std::make_index_sequence<NY>{}).v;
+    if (!(v - v == 0.0)) v = 0.0;
+    key[m] = ordered_bits(v);
+    idx[m] = (int)m;
+  }
+}
+
 template <int S>
 struct EpochCfg {
   static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
@@ -283,25 +313,40 @@ __global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* 
 // incremental-stepping state (jb200_state_*)
 struct EpochWS {
   long long cap = 0, M = 0;
+  size_t rec_bytes = 0;
   void* parked = nullptr;
   unsigned short* tag = nullptr;
-  int* lists = nullptr;
+  int* lists = nullptr;    // [4][cap]: one region per stage count when `order` is in use, else one list [cap]
   int* counts = nullptr;
+  int* order = nullptr;    // [cap] rows sorted by H(y0) (phase-space neighbours adjacent)
+  bool use_order = false;  // epochs take their lists from `order` (else: regime-key counting sort)
+  bool have_order = false;
+  int* nsel = nullptr;     // [4] device counts of the per-stage selections
+  void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
 };
 inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
   ws.M = M;
-  if (M <= ws.cap) return 0;
+  if (M <= ws.cap && parked_bytes <= ws.rec_bytes) return 0;
   cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
+  cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp);
+  ws.order = nullptr; ws.nsel = nullptr; ws.sort_tmp = nullptr; ws.sort_tmp_bytes = 0;
   ws.cap = 0;
+  ws.rec_bytes = parked_bytes;
   JB_CUDA(cudaMalloc(&ws.parked, parked_bytes * M));
   JB_CUDA(cudaMalloc(&ws.tag, sizeof(unsigned short) * M));
-  JB_CUDA(cudaMalloc(&ws.lists, sizeof(int) * M));
+  JB_CUDA(cudaMalloc(&ws.lists, sizeof(int) * 4 * M));
+  JB_CUDA(cudaMalloc(&ws.order, sizeof(int) * M));
+  JB_CUDA(cudaMalloc(&ws.nsel, sizeof(int) * 4));
+  ws.sort_tmp_bytes = 48 * (size_t)M + (1 << 20);
+  JB_CUDA(cudaMalloc(&ws.sort_tmp, ws.sort_tmp_bytes));
   JB_CUDA(cudaMalloc(&ws.counts, sizeof(int) * NKEYS));
   ws.cap = M;
   return 0;
 }
 inline void ws_free(EpochWS& ws) {
   cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
+  cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp);
   ws = EpochWS();
 }
 
@@ -317,6 +362,8 @@ struct Handle {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // the per-order epoch kernels of one epoch overlap
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool fixed_epochs = false;
+  bool presort = true;     // fused fixed-order kernel: batch pre-sorted by H(y0) (JB200_PRESORT=0 disables)
+  int epoch_horder = 2;    // epoch lists: 0 regime-key sort, 1 stage count then H(y0) order, 2 regime key then H(y0) order
   int epoch_passes = 12;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
   // workspace of jb200_solve_host
   long long cap = 0;
@@ -333,6 +380,42 @@ template <int NY, int S>
 inline size_t lc_smem_bytes(int threads) {
   return sizeof(double) * (size_t)LcPlace<NY, S>::NS * (size_t)ZLUS<NY>::WORDS * (size_t)threads;
 }
+
+// rows sorted by H(y0): radix sort (CUB) of the order-preserving bit pattern of H, payload = row index
+template <class Ham>
+int build_order(Handle* H, EpochWS& ws, const double* y0, long long M, cudaStream_t st, bool& ok) {
+  ok = false;
+  const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
+  unsigned long long* kin = (unsigned long long*)ws.sort_tmp;
+  unsigned long long* kout = kin + M;
+  int* vin = (int*)(kout + M);
+  void* tmp = (void*)(vin + M + (M & 1));
+  const size_t tmp_bytes = ws.sort_tmp_bytes - (size_t)((char*)tmp - (char*)ws.sort_tmp);
+  size_t need_tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need_tmp, kin, kout, vin, ws.order, (int)M, 0, 64, st);
+  if (need_tmp > tmp_bytes) return 0;
+  hkey_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, M, kin, vin);
+  JB_CUDA(cudaGetLastError());
+  JB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need_tmp, kin, kout, vin, ws.order, (int)M, 0, 64, st));
+  ok = true;
+  return 0;
+}
+
+static __global__ void gather_tag_kernel(const unsigned short* __restrict__ tag, const int* __restrict__ order, long long M,
+                                         unsigned short* __restrict__ keys) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x)
+    keys[m] = tag[order[m]];
+}
+
+// live rows of one stage-count bucket, taken in H-order (stable selection)
+struct StagePred {
+  const unsigned short* tag;
+  int k;
+  __device__ __forceinline__ bool operator()(const int& idx) const {
+    const int t = tag[idx];
+    return t != 0 && ((t - 1) >> 8) == k;
+  }
+};
 
 template <class Ham, int SM, bool VAR>
 int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
@@ -353,9 +436,19 @@ int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, 
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
-  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense, H->d_counter);
+  // pre-sort by H(y0) (large batches)
+  const int* order = nullptr;
+  if (H->presort && M >= (1 << 16) && M <= 2000000000LL) {
+    int rc = ws_reserve(H->ws, M, sizeof(double));
+    if (rc) return rc;
+    bool ok = false;
+    if ((rc = build_order<Ham>(H, H->ws, y0, M, st, ok))) return rc;
+    if (ok) order = H->ws.order;
+  }
+  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense,
+                                                  H->d_counter, order);
   JB_CUDA(cudaGetLastError());
-  H->launches = 1;
+  H->launches = order ? 2 : 1;   // + the CUB radix-sort passes (library kernels)
   return 0;
 }
 
@@ -369,7 +462,7 @@ struct OutArgs {
 };
 
 template <class Ham, int S, bool VAR>
-int launch_epoch(Handle* H, EpochWS& ws, int k, int base, int count, int max_passes, int stop_on_accept,
+int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int max_passes, int stop_on_accept,
                  const OutArgs& o, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
   // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
   cudaStream_t st = main_st;
@@ -415,6 +508,28 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
   const long long M = ws.M;
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
   std::vector<int> hist(NKEYS);
+  for (long long epoch = 0; ws.use_order && H->epoch_horder == 1; epoch++) {
+    // H-ordered epochs: per stage count, the live rows in the order of H(y0) (stable CUB selection from ws.order)
+    JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
+    for (int k = 0; k < 4; k++) {
+      size_t bytes = ws.sort_tmp_bytes;
+      JB_CUDA(cub::DeviceSelect::If(ws.sort_tmp, bytes, ws.order, ws.lists + (size_t)k * M, ws.nsel + k, (int)M,
+                                    StagePred{ws.tag, k}, st));
+    }
+    int cnt[4];
+    JB_CUDA(cudaMemcpyAsync(cnt, ws.nsel, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    H->launches += 1;
+    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] == 0) return 0;
+    int rc = 0, used = 0;
+    JB_CUDA(cudaEventRecord(H->ev_fork, st));
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, ws, 3, 3 * M, cnt[3], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, ws, 2, 2 * M, cnt[2], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, ws, 1, 1 * M, cnt[1], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, ws, 0, 0, cnt[0], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (rc) return rc;
+  }
+  const bool key_then_h = H->epoch_horder == 2 && ws.have_order;   // regime key major, H(y0) minor (stable radix sort)
   for (long long epoch = 0;; epoch++) {
     JB_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
@@ -432,8 +547,19 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     }
     H->launches += 1;
     if (run == 0) break;
-    JB_CUDA(cudaMemcpyAsync(ws.counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
-    scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, ws.lists);
+    if (key_then_h) {
+      unsigned short* kin = (unsigned short*)ws.sort_tmp;
+      unsigned short* kout = kin + M + (M & 1);
+      void* tmp = (void*)(kout + M + (M & 1) + 8);
+      size_t bytes = ws.sort_tmp_bytes - (size_t)((char*)tmp - (char*)ws.sort_tmp);
+      gather_tag_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, ws.order, M, kin);
+      JB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, ws.order, ws.lists, (int)M, 0, 11, st));
+      const int n0 = (int)(M - run);   // finished rows (key 0) sort to the front
+      for (int k = 0; k < 4; k++) base[k] += n0;
+    } else {
+      JB_CUDA(cudaMemcpyAsync(ws.counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
+      scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, ws.lists);
+    }
     JB_CUDA(cudaGetLastError());
     H->launches += 1;
     int rc = 0, used = 0;
@@ -457,6 +583,12 @@ int ws_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int n
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
   init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, ntspan, M, (Parked<NY>*)ws.parked, ws.tag);
   JB_CUDA(cudaGetLastError());
+  ws.use_order = ws.have_order = false;
+  if (H->epoch_horder && M >= (1 << 16)) {
+    bool ok = false;
+    if ((rc = build_order<Ham>(H, ws, y0, M, st, ok))) return rc;
+    ws.use_order = ws.have_order = ok;
+  }
   return 0;
 }
 
@@ -631,9 +763,10 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
                                                              double* __restrict__ t_out, double* __restrict__ h_out,
                                                              int* __restrict__ res, long long* __restrict__ stats,
                                                              int* __restrict__ nstg, long long* __restrict__ work,
-                                                             int* __restrict__ sens_iters) {
+                                                             int* __restrict__ sens_iters, const int* __restrict__ order) {
   constexpr int NY = Ham::NV;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = order ? order[i] : i;   // rows in H(y0) order: the lanes of a warp are phase-space neighbours
     Traj<NY, SM> T;
     double y[NY];
     load_row<NY>(y0, m, y);
@@ -671,8 +804,16 @@ int launch_sens(Handle* H, const double* y0, const double* tspan, const double* 
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // many small blocks in flight: trajectories differ in length by up to 5x, the block scheduler balances them
   const long long blocks = std::max<long long>(1, (M + JB_THREADS - 1) / JB_THREADS);
+  const int* order = nullptr;
+  if (H->presort && M >= (1 << 16) && M <= 2000000000LL) {
+    int rc = ws_reserve(H->ws, M, sizeof(double));
+    if (rc) return rc;
+    bool ok = false;
+    if ((rc = build_order<Ham>(H, H->ws, y0, M, st, ok))) return rc;
+    if (ok) order = H->ws.order;
+  }
   kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
-                                                  sens_iters);
+                                                  sens_iters, order);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
