@@ -69,7 +69,8 @@ __device__ __forceinline__ void store_row(double* __restrict__ dst, long long m,
 }
 
 #ifndef JB_MINB_FIXED
-#define JB_MINB_FIXED 2   // resident CTAs/SM targeted for the fixed-order kernels (register budget)
+#define JB_MINB_FIXED 3   // resident CTAs/SM of the fused fixed-order kernels (168 registers; with H(y0)-ordered rows the
+                          // extra warps pay: 55.7 -> 49.5 ms on config 2; the epoch kernels are faster with 2, measured)
 #endif
 #ifndef JB_MINB_VAR
 #define JB_MINB_VAR 2
@@ -87,7 +88,7 @@ struct DenseArgs {
 };
 
 template <class Ham, int SM, bool VAR, bool DENSE>
-__global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : JB_MINB_FIXED) radau_kernel(const __grid_constant__ RadauParams P,
+__global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : (SM <= 3 ? JB_MINB_FIXED : 2)) radau_kernel(const __grid_constant__ RadauParams P,
                                                     const double* __restrict__ y0,
                                                     const double* __restrict__ tspan, long long M,
                                                     double* __restrict__ y_out, double* __restrict__ t_out,
@@ -203,6 +204,9 @@ static __global__ void scatter_kernel(const unsigned short* __restrict__ tag, lo
   }
 }
 
+#ifndef JB_MINB_EPOCH
+#define JB_MINB_EPOCH 2   // resident CTAs/SM for the 1- and 3-stage epoch kernels
+#endif
 #ifndef JB_MINB_HI
 #define JB_MINB_HI 2      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
 #endif
@@ -238,7 +242,7 @@ __global__ void hkey_kernel(const __grid_constant__ RadauParams P, const double*
 template <int S>
 struct EpochCfg {
   static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
-  static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_FIXED;
+  static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_EPOCH;
 };
 
 template <class Ham, int S, bool VAR, bool DENSE>
