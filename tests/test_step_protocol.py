@@ -50,3 +50,26 @@ def test_step_with_user_chosen_trial_step():
     exact = np.stack([y0[:, 0] * np.cos(10) - y0[:, 1] * np.sin(10), y0[:, 1] * np.cos(10) + y0[:, 0] * np.sin(10)], 1)
     assert np.abs(state.y.cpu().numpy() - exact).max() < 5e-9 and (state.x == 10.0).all()
     assert (state.hdid <= 0.05 + 1e-15).all()
+
+
+def test_step_loop_on_a_large_batch_uses_the_ordered_lists():
+    """>= 65,536 rows: the epoch lists are sorted by regime key, then H(y0) (csrc/solver_impl.cuh build_order); the step loop
+    must still be the same integration as solve(), bit for bit"""
+    cfg = configs.c2_vdp(M=70000)
+    cfg["tspan"][:, 1] = 40.0
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    ft = cfg["tspan"][:, 1].cuda()
+    state = jb.RadauState(cfg["y0"].cuda(), cfg["tspan"][:, 0].cuda(), atol=1e-9, rtol=1e-6, ft=ft)
+    solver = jb.RadauT(cfg["options"])
+    htry, n = cfg["options"].InitialStep, 0
+    while not bool(state.done.all()):
+        state = solver.step(htry, dyn, ft, state)
+        htry = state.hnext
+        n += 1
+        assert n < 500
+    r = jb.RadauTe(dyn, None, cfg["tspan"].cuda(), cfg["y0"].cuda(), cfg["options"])
+    r.solve()
+    assert torch.equal(state.y, r.y) and torch.equal(state.stats.raw, r.stats.raw) and torch.equal(state.x, r.t)
+    idx = torch.arange(0, 70000, 97)
+    o = c_oracle.solve("vdp", [1000.0], 1, cfg["y0"][idx].numpy(), cfg["tspan"][idx].numpy(), cfg["options"], arith="mirror")
+    assert np.array_equal(r.y[idx.cuda()].cpu().numpy(), o["y"])
