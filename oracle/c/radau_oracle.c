@@ -783,6 +783,9 @@ static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t
   return err;
 }
 
+/* per-pass log of oracle_radau_trace2 (single-threaded diagnostic): rows of 8 doubles =
+ * [StepNbr, t, h of the attempt, NbrStg, Newt, Theta, err (-1: Newton failed), FacConv] */
+static double *g_plog = 0; static int g_plog_cap = 0, g_plog_n = 0;
 /* one trajectory; returns res code */
 /* dense output rows of one trajectory (radau.m:1150-1168 OutFlag 3); tsp == NULL: final state only */
 typedef struct { const double *tsp; int ntspan; double *tout, *yout; int nout; } dense_t;
@@ -915,6 +918,7 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
     FacConv = POW(fmax(FacConv, EPS), 0.8);
     Theta = fabs(Thet);
     Newt = 0;
+    const double h_attempt = h;
     int newton_failed = 0, nan_fail = 0;
     double NewNrm = 0.0;
     for (;;) {
@@ -987,9 +991,14 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
       break;
     }
     if (nan_fail) { res = 2; break; }
+    if (g_plog && g_plog_n < g_plog_cap) {
+      double *L = g_plog + 8 * g_plog_n++;
+      L[0] = (double)st[ST_STEP]; L[1] = t; L[2] = h_attempt; L[3] = NbrStg; L[4] = Newt; L[5] = Theta; L[6] = -1.0; L[7] = FacConv;
+    }
     if (newton_failed) continue;
 
     double err = estrad(pb, &tb, h, &lu, z, Scal, f0, First, Reject, t, y, st);
+    if (g_plog && g_plog_n >= 1) g_plog[8 * (g_plog_n - 1) + 6] = err;
     if (!isfinite(err)) { res = 2; break; }
     double fac = fmin(Safe, (2.0 * tb.Nit + 1.0) / (2.0 * tb.Nit + Newt));
     double exponent = 1.0 / s + 1.0;
@@ -1153,6 +1162,15 @@ int oracle_radau_trace(int problem, const double *par, int sign, int Ny, const d
 }
 
 /* batched dynamics / Jacobian (checks the stage-eval kernel) */
+int oracle_radau_trace2(int problem, const double *par, int sign, int Ny, const double *y0, const double *tspan,
+                        const oracle_opts *op, double *y_out, long long *stats, double *plog, int cap, int *n) {
+  g_plog = plog; g_plog_cap = cap; g_plog_n = 0;
+  double t; int rn = 0;
+  int rc = oracle_radau_trace(problem, par, sign, Ny, y0, tspan, op, y_out, &t, stats, 0, 0, &rn);
+  *n = g_plog_n; g_plog = 0;
+  return rc;
+}
+
 int oracle_eval_dyns(int problem, const double *par, int sign, int Ny, long long M, const double *y, double *f) {
   problem_t pb; pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
 #pragma omp parallel for

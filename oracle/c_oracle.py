@@ -159,6 +159,25 @@ def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     return dict(y=y, t=t.value, res=res, stats=stats, h_accept=rec[:n.value].copy())
 
 
+def trace_passes(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
+    """one trajectory; per attempted step [StepNbr, t, h, NbrStg, Newt, Theta, err (-1 = Newton failed), FacConv]."""
+    set_arith(arith)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    Ny = y0.shape[0]
+    y = np.empty(Ny)
+    stats = np.empty(8, dtype=np.int64)
+    log = np.zeros((cap, 8))
+    n = C.c_int()
+    o = _opts(opts, Ny)
+    res = lib().oracle_radau_trace2(
+        C.c_int(PB[problem] if isinstance(problem, str) else problem), _dp(par), C.c_int(sign),
+        C.c_int(Ny), _dp(y0), _dp(tspan), C.byref(o), _dp(y), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+        _dp(log), C.c_int(cap), C.byref(n))
+    return dict(y=y, res=res, stats=stats, log=log[:n.value].copy())
+
+
 def eval_dyns(problem, par, sign, y, arith="reference"):
     set_arith(arith)
     y = np.ascontiguousarray(y, dtype=np.float64)
