@@ -86,7 +86,11 @@ typedef struct jb200_opts {
   double Vitu, Vitd, hhou, hhod;/* 0.002, 0.8, 1.2, 0.8 */
   int Gustafsson;               /* 1 */
   int costate_sign;             /* +1: pdot=+dH/dx (reference), -1: canonical */
+  int radaute_quirks;           /* bit mask of RadauTe deviations from its MATLAB twin to reproduce (default: all):
+                                   JB200_Q8_GUSTAFSSON_UNGATED -- the Gustafsson limiter also acts on accepted steps whose
+                                   order just changed (src/cpp/radaute_impl.hpp:1092-1100 vs src/matlab/radau.m:1066-1076) */
 } jb200_opts;
+#define JB200_Q8_GUSTAFSSON_UNGATED 1
 
 /* fill *o with the reference defaults (src/cpp/radaute.hpp:52-96) */
 int jb200_opts_default(jb200_opts* o);

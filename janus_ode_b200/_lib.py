@@ -20,7 +20,8 @@ class jb200_opts(C.Structure):
                 ("MinNbrStg", C.c_int), ("MaxNbrStg", C.c_int), ("MaxNbrStep", C.c_int64),
                 ("Safe", C.c_double), ("Quot1", C.c_double), ("Quot2", C.c_double), ("FacL", C.c_double),
                 ("FacR", C.c_double), ("Vitu", C.c_double), ("Vitd", C.c_double), ("hhou", C.c_double),
-                ("hhod", C.c_double), ("Gustafsson", C.c_int), ("costate_sign", C.c_int)]
+                ("hhod", C.c_double), ("Gustafsson", C.c_int), ("costate_sign", C.c_int),
+                ("radaute_quirks", C.c_int)]
 
 
 class JanusB200Error(RuntimeError):

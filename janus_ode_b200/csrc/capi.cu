@@ -176,7 +176,7 @@ static void fill_params(RadauParams& P, const jb200_opts* o, int ny, const doubl
   P.NbrStg = o->NbrStg;
   P.MinNbrStg = o->MinNbrStg;
   P.MaxNbrStg = o->MaxNbrStg;
-  P.Gustafsson = o->Gustafsson;
+  P.Gustafsson = o->Gustafsson ? (1 | ((o->radaute_quirks & JB200_Q8_GUSTAFSSON_UNGATED) ? 2 : 0)) : 0;
   for (int i = 0; i < nhp && i < JB200_MAX_HAM_PARAMS; i++) P.ham_par[i] = hp[i];
 }
 
@@ -259,6 +259,7 @@ int jb200_opts_default(jb200_opts* o) {
   o->hhod = 0.8;
   o->Gustafsson = 1;
   o->costate_sign = 1;
+  o->radaute_quirks = JB200_Q8_GUSTAFSSON_UNGATED;
   return 0;
 }
 

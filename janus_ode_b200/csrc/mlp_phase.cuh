@@ -540,7 +540,9 @@ JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long lon
   if (err < 1.0) {
     s.flags &= ~PF_FIRST;
     s.st[ST_ACC] += 1;
-    if (P.Gustafsson && !JB_FLAG(s, PF_CHANGE)) {
+    const bool gus_upd = (P.Gustafsson & 1) && !JB_FLAG(s, PF_CHANGE);   // see radau_core.cuh (quirk Q8)
+    const bool gus_lim = (P.Gustafsson & 2) ? true : gus_upd;
+    if (gus_lim) {
       if (s.st[ST_ACC] > 1) {
         const double ratio = err * err / s.erracc;
         double root;
@@ -553,6 +555,8 @@ JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long lon
         quot = fmax(quot, facgus);
         hnew = s.h / quot;
       }
+    }
+    if (gus_upd) {
       s.hacc = s.h;
       s.erracc = fmax(1.0e-2, err);
     }

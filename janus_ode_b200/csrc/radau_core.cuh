@@ -41,7 +41,8 @@ struct RadauParams {
   double Vitu, Vitd, hhou, hhod;
   double sign;
   long long MaxNbrStep;
-  int Start_Newt, MaxNbrNewton, NbrStg, MinNbrStg, MaxNbrStg, Gustafsson;
+  int Start_Newt, MaxNbrNewton, NbrStg, MinNbrStg, MaxNbrStg;
+  int Gustafsson;            // bit 0: on; bit 1: limiter not gated by ChangeFlag (RadauTe, quirk Q8)
   double ham_par[8];
 };
 
@@ -75,7 +76,10 @@ struct DenseOut {
 
 template <int NY, int SM>
 struct Traj {
-  double y[NY], f0[NY], Jac[NY * NY], cont[SM * NY];
+  // The Jacobian itself is NOT part of the persistent state: it is a deterministic function of the state it was
+  // evaluated at (yJ), so a factorisation that needs a Jacobian older than this pass re-evaluates it (same code,
+  // same bits).  That keeps Ny^2 doubles out of the registers across the Newton loop and out of the parked record.
+  double y[NY], f0[NY], yJ[NY], cont[SM * NY];
   double t, tfinal, h, h_old, hopt, hacc, erracc, FacConv, Theta, Thetat, PosNeg, hmaxn;
   int NbrStg, Newt, ChangeNbr, nout;
   bool Last, First, Reject, Keep, ChangeFlag, UnExpStepRej, UnExpNewtRej, NeedNewJac, NeedNewLU;
@@ -103,7 +107,7 @@ template <class Ham, int NY, int SM>
 JB_HD void traj_init(Traj<NY, SM>& T, const RadauParams& P, const double* y0, double t0, double tfinal) {
   // radau.m:631-696 / radaute_impl.hpp:406-455
 #pragma unroll
-  for (int i = 0; i < NY; i++) T.y[i] = y0[i];
+  for (int i = 0; i < NY; i++) T.y[i] = T.yJ[i] = y0[i];
 #pragma unroll
   for (int i = 0; i < 8; i++) T.st[i] = 0;
 #pragma unroll
@@ -148,14 +152,14 @@ JB_HD void traj_init(Traj<NY, SM>& T, const RadauParams& P, const double* y0, do
 
 // gamma/h I - J and (alpha_q + i beta_q)/h I - J, factored (radaute_impl.hpp:1502-1625)
 template <int NY, int S, int SM>
-JB_HD void decomrc(Traj<NY, SM>& T) {
+JB_HD void decomrc(Traj<NY, SM>& T, const double* Jac) {
   using Tab = RadauTab<S>;
   const double rh = 1.0 / T.h;
   const double valp0 = Tab::ValP(0) * rh;
 #pragma unroll
   for (int i = 0; i < NY; i++)
 #pragma unroll
-    for (int j = 0; j < NY; j++) T.L0.a[i * NY + j] = (i == j) ? (valp0 - T.Jac[i * NY + j]) : -T.Jac[i * NY + j];
+    for (int j = 0; j < NY; j++) T.L0.a[i * NY + j] = (i == j) ? (valp0 - Jac[i * NY + j]) : -Jac[i * NY + j];
   rlu_factor<NY>(T.L0);
 #pragma unroll
   for (int q = 1; q <= (S - 1) / 2; q++) {
@@ -168,7 +172,7 @@ JB_HD void decomrc(Traj<NY, SM>& T) {
     for (int i = 0; i < NY; i++)
 #pragma unroll
       for (int j = 0; j < NY; j++) {
-        Z.re[i * NY + j] = (i == j) ? (al - T.Jac[i * NY + j]) : -T.Jac[i * NY + j];
+        Z.re[i * NY + j] = (i == j) ? (al - Jac[i * NY + j]) : -Jac[i * NY + j];
         Z.im[i * NY + j] = (i == j) ? be : 0.0;
       }
     zlu_factor<NY>(Z);
@@ -335,14 +339,16 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
 }
 
 template <class Ham, int NY, int S, int SM>
-JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr, Sens<NY>* sens = nullptr) {
+JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool jac_fresh, const DenseOut* out = nullptr,
+                        Sens<NY>* sens = nullptr) {
   using Tab = RadauTab<S>;
   constexpr int si = (S - 1) / 2;
   const int Nit = nit_of(S, P.MaxNbrNewton);
   double z[S * NY], w[S * NY];  // [stage][component]
 
   if (T.NeedNewLU) {  // radau.m:827-844
-    decomrc<NY, S, SM>(T);
+    if (!jac_fresh) ham_jac<Ham>(T.yJ, P.ham_par, P.sign, Jac);  // the Jacobian kept from an earlier pass
+    decomrc<NY, S, SM>(T, Jac);
     T.st[ST_DEC] += 1;
     T.work += W_lu(S, NY);
     T.NeedNewLU = false;
@@ -583,7 +589,13 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* o
   if (err < 1.0) {  // ------- accepted (radau.m:1054-1232)
     T.First = false;
     T.st[ST_ACC] += 1;
-    if (P.Gustafsson && !T.ChangeFlag) {
+    // P.Gustafsson: bit 0 = predictive controller on; bit 1 = RadauTe's gate: the limiter is applied on
+    // every accepted step with AccptNbr > 1, also when the order just changed (radaute_impl.hpp:1092-1100: the inner
+    // mask m1_12_1_1_1 lacks `& ~ChangeFlag`), while hacc / erracc are only refreshed under `Gustafsson & ~ChangeFlag`
+    // (:1101-1102).  Bit 1 clear = radau.m:1066-1076, which gates both.
+    const bool gus_upd = (P.Gustafsson & 1) && !T.ChangeFlag;
+    const bool gus_lim = (P.Gustafsson & 2) ? true : gus_upd;
+    if (gus_lim) {
       if (T.st[ST_ACC] > 1) {
         const double ratio = err * err / T.erracc;
         double root;
@@ -596,6 +608,8 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* o
         quot = fmax(quot, facgus);
         hnew = T.h / quot;
       }
+    }
+    if (gus_upd) {
       T.hacc = T.h;
       T.erracc = fmax(1.0e-2, err);
     }
@@ -672,14 +686,17 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* o
 // head of a pass: Jacobian refresh + order selection (radau.m:733-824); returns false if the
 // trajectory must stop (NaN in the Jacobian)
 template <class Ham, int NY, int SM, bool VAR>
-JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
+JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool& jac_fresh) {
   T.st[ST_STEP] += 1;
   T.FacConv = det_pow(fmax(T.FacConv, EPS), 0.8);
   if (T.NeedNewJac) {
-    ham_jac<Ham>(T.y, P.ham_par, P.sign, T.Jac);
+    ham_jac<Ham>(T.y, P.ham_par, P.sign, Jac);
+    jac_fresh = true;
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.yJ[i] = T.y[i];
     bool nanf = false;
 #pragma unroll
-    for (int k = 0; k < NY * NY; k++) nanf = nanf || (T.Jac[k] != T.Jac[k]);
+    for (int k = 0; k < NY * NY; k++) nanf = nanf || (Jac[k] != Jac[k]);
     if (nanf) {
       T.res = 2;
       return false;
@@ -715,13 +732,15 @@ JB_HD bool pass_head(Traj<NY, SM>& T, const RadauParams& P) {
 // MinNbrStg == MaxNbrStg == NbrStg == SM); VAR = true: orders 1..SM selected at run time.
 template <class Ham, int NY, int SM, bool VAR>
 JB_HD bool one_pass(Traj<NY, SM>& T, const RadauParams& P, const DenseOut* out = nullptr, Sens<NY>* sens = nullptr) {
-  if (!pass_head<Ham, NY, SM, VAR>(T, P)) return true;
-  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P, out, sens);
+  double Jac[NY * NY];
+  bool jf = false;
+  if (!pass_head<Ham, NY, SM, VAR>(T, P, Jac, jf)) return true;
+  if (!VAR) return attempt_step<Ham, NY, SM, SM>(T, P, Jac, jf, out, sens);
   switch (T.NbrStg) {
-    case 1: return attempt_step<Ham, NY, 1, SM>(T, P, out, sens);
-    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P, out, sens);
-    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P, out, sens);
-    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P, out, sens);
+    case 1: return attempt_step<Ham, NY, 1, SM>(T, P, Jac, jf, out, sens);
+    case 3: return attempt_step<Ham, NY, (SM >= 3 ? 3 : 1), SM>(T, P, Jac, jf, out, sens);
+    case 5: return attempt_step<Ham, NY, (SM >= 5 ? 5 : 1), SM>(T, P, Jac, jf, out, sens);
+    default: return attempt_step<Ham, NY, (SM >= 7 ? 7 : 1), SM>(T, P, Jac, jf, out, sens);
   }
 }
 
@@ -752,7 +771,7 @@ enum : unsigned {
 
 template <int NY>
 struct alignas(16) Parked {
-  double y[NY], f0[NY], Jac[NY * NY], cont[7 * NY];
+  double y[NY], f0[NY], yJ[NY], cont[7 * NY];
   double t, t0, tfinal, h, h_old, hopt, hacc, erracc, FacConv, Theta, Thetat;
   long long work;
   int st[8];
@@ -764,9 +783,7 @@ struct alignas(16) Parked {
 template <int NY, int SM>
 JB_HD void park(const Traj<NY, SM>& T, double t0, bool head_done, bool finished, Parked<NY>& p) {
 #pragma unroll
-  for (int i = 0; i < NY; i++) { p.y[i] = T.y[i]; p.f0[i] = T.f0[i]; }
-#pragma unroll
-  for (int i = 0; i < NY * NY; i++) p.Jac[i] = T.Jac[i];
+  for (int i = 0; i < NY; i++) { p.y[i] = T.y[i]; p.f0[i] = T.f0[i]; p.yJ[i] = T.yJ[i]; }
 #pragma unroll
   for (int i = 0; i < SM * NY; i++) p.cont[i] = T.cont[i];
   p.t = T.t; p.t0 = t0; p.tfinal = T.tfinal; p.h = T.h; p.h_old = T.h_old; p.hopt = T.hopt;
@@ -785,9 +802,7 @@ JB_HD void park(const Traj<NY, SM>& T, double t0, bool head_done, bool finished,
 template <int NY, int SM>
 JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_done) {
 #pragma unroll
-  for (int i = 0; i < NY; i++) { T.y[i] = p.y[i]; T.f0[i] = p.f0[i]; }
-#pragma unroll
-  for (int i = 0; i < NY * NY; i++) T.Jac[i] = p.Jac[i];
+  for (int i = 0; i < NY; i++) { T.y[i] = p.y[i]; T.f0[i] = p.f0[i]; T.yJ[i] = p.yJ[i]; }
 #pragma unroll
   for (int i = 0; i < SM * NY; i++) T.cont[i] = p.cont[i];
   T.t = p.t; t0 = p.t0; T.tfinal = p.tfinal; T.h = p.h; T.h_old = p.h_old; T.hopt = p.hopt;
@@ -813,22 +828,27 @@ JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_d
 template <class Ham, int NY, int S, bool VAR = true>
 JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes,
                      const DenseOut* out = nullptr, bool stop_on_accept = false, bool* stepped = nullptr) {
-  if (!T.NeedNewLU) decomrc<NY, S, S>(T);  // rebuild the factors this trajectory was parked with
+  double Jac[NY * NY];
+  if (!T.NeedNewLU) {  // rebuild the factors this trajectory was parked with
+    ham_jac<Ham>(T.yJ, P.ham_par, P.sign, Jac);
+    decomrc<NY, S, S>(T, Jac);
+  }
   const int acc0 = T.st[ST_ACC];
   for (int passes = 0;;) {
+    bool jf = false;
     if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
       if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
       return true;
     }
     if (!head_done) {
-      if (!pass_head<Ham, NY, S, VAR>(T, P)) return true;
+      if (!pass_head<Ham, NY, S, VAR>(T, P, Jac, jf)) return true;
     }
     if (T.NbrStg != S) {
       head_done = true;
       return false;
     }
     head_done = false;
-    if (attempt_step<Ham, NY, S, S>(T, P, out)) return true;
+    if (attempt_step<Ham, NY, S, S>(T, P, Jac, jf, out)) return true;
     if (stop_on_accept && T.st[ST_ACC] != acc0) {
       *stepped = true;
       return false;

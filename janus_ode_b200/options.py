@@ -40,6 +40,9 @@ class OptionsTe:
     hhou: float = 1.2
     hhod: float = 0.8
     Gustafsson: bool = True
+    # RadauTe deviations from its MATLAB twin that are reproduced (bit mask; 0 = radau.m semantics).  Bit 0 (quirk Q8):
+    # the Gustafsson limiter also acts on accepted steps whose order just changed, src/cpp/radaute_impl.hpp:1092-1100.
+    RadauTeQuirks: int = 1
     Complex: bool = False
     Refine: int = 1
     MassFcn: object = None
@@ -75,6 +78,7 @@ class OptionsTe:
         o.Start_Newt = int(bool(self.Start_Newt))
         o.Gustafsson = int(bool(self.Gustafsson))
         o.costate_sign = int(costate_sign)
+        o.radaute_quirks = int(self.RadauTeQuirks)
         return o
 
 

@@ -34,17 +34,26 @@ def _get_handle(ham: Hamiltonian, options: OptionsTe, costate_sign: int, device)
     """Solver objects are one-shot like the reference's (construct per solve), but the native handle
     behind them -- device workspace of the host-buffer and variable-order paths -- is reused for the
     same (Hamiltonian, options, device)."""
+    import threading
+
     import numpy as np
-    key = (ham, costate_sign, str(device),
-           tuple((k, tuple(np.atleast_1d(np.asarray(v, dtype=float)).tolist()) if k in ("RelTol", "AbsTol") else v)
-                 for k, v in sorted(vars(options).items())))
+
+    from .options import _to_np
     try:
+        # one native handle per (Hamiltonian, options, device, stream, thread): the C ABI allows one call at a time per
+        # handle (include/janus_b200.h), so concurrent streams / threads never share one
+        stream = torch.cuda.current_stream(device).cuda_stream if isinstance(device, torch.device) else 0
+        key = (ham, costate_sign, str(device), stream, threading.get_ident(),
+               tuple((k, tuple(np.atleast_1d(np.asarray(_to_np(v), dtype=float)).tolist()) if k in ("RelTol", "AbsTol") else v)
+                     for k, v in sorted(vars(options).items())))
         h = _HANDLE_CACHE.get(key)
     except TypeError:
         return _Handle(ham, options, costate_sign)
     if h is None:
         if len(_HANDLE_CACHE) >= 8:
-            _HANDLE_CACHE.pop(next(iter(_HANDLE_CACHE))).close()
+            # evict the oldest entry from the cache only: solver / state objects that still reference it keep it
+            # alive, _Handle.__del__ destroys the native handle when the last of them goes away
+            _HANDLE_CACHE.pop(next(iter(_HANDLE_CACHE)))
         h = _HANDLE_CACHE[key] = _Handle(ham, options, costate_sign)
     return h
 

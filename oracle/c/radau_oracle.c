@@ -785,6 +785,11 @@ static double estrad(const problem_t *pb, const tab_t *tb, double h, const lus_t
 
 /* per-pass log of oracle_radau_trace2 (single-threaded diagnostic): rows of 8 doubles =
  * [StepNbr, t, h of the attempt, NbrStg, Newt, Theta, err (-1: Newton failed), FacConv] */
+/* reference-variant switches, see oracle_set_quirks */
+static int g_quirks = 1;
+#define Q8_GUS_UNGATED 1   /* RadauTe applies the Gustafsson limiter on every accepted step with AccptNbr > 1, also when the
+                              order just changed (radaute_impl.hpp:1092-1100: m1_12_1_1_1 lacks `& ~ChangeFlag`); hacc / erracc
+                              are still only updated under `Gustafsson & ~ChangeFlag`.  MATLAB radau.m:1066-1076 gates both. */
 static double *g_plog = 0; static int g_plog_cap = 0, g_plog_n = 0;
 /* one trajectory; returns res code */
 /* dense output rows of one trajectory (radau.m:1150-1168 OutFlag 3); tsp == NULL: final state only */
@@ -1007,7 +1012,9 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
     if (err < 1.0) {
       First = 0;
       st[ST_ACC] += 1;
-      if (op->Gustafsson && !ChangeFlag) {
+      const int gus_upd = op->Gustafsson && !ChangeFlag;
+      const int gus_lim = (g_quirks & Q8_GUS_UNGATED) ? op->Gustafsson : gus_upd;
+      if (gus_lim) {
         if (st[ST_ACC] > 1) {
           double ratio = err * err / erracc, root;
           if (!g_mirror) root = pow(ratio, 1.0 / (s + 1.0));
@@ -1020,6 +1027,8 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
           quot = fmax(quot, facgus);
           hnew = h / quot;
         }
+      }
+      if (gus_upd) {
         hacc = h;
         erracc = fmax(1.0e-2, err);
       }
@@ -1108,6 +1117,8 @@ done:
 /* ------------------------------------------------------------------ public entry points */
 /* y0 [M][Ny] row-major, tspan [M][2]; outputs y_out [M][Ny], t_out[M], h_out[M], res[M],
  * stats [M][8], nstg[M].  nthreads <= 0 -> all.  Returns 0.                               */
+void oracle_set_quirks(int q) { g_quirks = q; }
+int oracle_get_quirks(void) { return g_quirks; }
 void oracle_set_arith(int mirror) { g_mirror = mirror ? 1 : 0; }
 int oracle_get_arith(void) { return g_mirror; }
 

@@ -80,6 +80,15 @@ def set_arith(mode):
     lib().oracle_set_arith(C.c_int(1 if mode == "mirror" else 0))
 
 
+Q8_GUS_UNGATED = 1
+
+
+def set_quirks(q):
+    """bit 0 (default on): RadauTe's Gustafsson limiter also on order-change steps (radaute_impl.hpp:1092-1100);
+    0 = MATLAB radau.m:1066-1076 gating."""
+    lib().oracle_set_quirks(C.c_int(int(q)))
+
+
 def det_pow(x, y):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
@@ -91,6 +100,7 @@ def det_pow(x, y):
 def solve(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
     """y0 [M,Ny], tspan [M,2] -> dict(y, t, h, res, stats[M,8], nstg)."""
     set_arith(arith)
+    set_quirks(getattr(opts, "RadauTeQuirks", 1))
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
@@ -114,6 +124,7 @@ def solve(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
 def solve_dense(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
     """tspan [M, ntspan] with interior output points -> additionally tout [M,ntspan], yout [M,ntspan,Ny], nout."""
     set_arith(arith)
+    set_quirks(getattr(opts, "RadauTeQuirks", 1))
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
@@ -142,6 +153,7 @@ def solve_dense(problem, par, sign, y0, tspan, opts, nthreads=0, arith="referenc
 def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     """one trajectory, with the accepted step sizes."""
     set_arith(arith)
+    set_quirks(getattr(opts, "RadauTeQuirks", 1))
     y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
     par = np.ascontiguousarray(par, dtype=np.float64)
@@ -162,6 +174,7 @@ def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
 def trace_passes(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     """one trajectory; per attempted step [StepNbr, t, h, NbrStg, Newt, Theta, err (-1 = Newton failed), FacConv]."""
     set_arith(arith)
+    set_quirks(getattr(opts, "RadauTeQuirks", 1))
     y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
     tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
     par = np.ascontiguousarray(par, dtype=np.float64)

@@ -310,7 +310,8 @@ class RadauBatched:
             qa = quot[acc]
             if op.Gustafsson:
                 gm = ~self.ChangeFlag[a]
-                gg2 = gm & (self.stats[a, ST["Acc"]] > 1)
+                lim = torch.ones_like(gm) if (getattr(op, "RadauTeQuirks", 1) & 1) else gm   # quirk Q8
+                gg2 = lim & (self.stats[a, ST["Acc"]] > 1)
                 if bool(gg2.any()):
                     ag = a[gg2]
                     fg = (self.hacc[ag] / self.h[ag]) * (ea[gg2] ** 2 / self.erracc[ag]) ** (1.0 / (s + 1.0)) / op.Safe

@@ -34,7 +34,8 @@ Deliberate deviations from RadauTe's batch-coupled behaviour (SURVEY.md section 
   Q4  Newt > Nit breaks out of the Newton loop (radau.m:915-925)
   Q6  no |h| <= hmin abort (C++ has none); "0.1|h| <= |t| eps" -> res = 1 is kept
   Q7  MaxStep ignored: hmax = tfinal - t0 (radaute_impl.hpp:227)
-  Q8  Gustafsson gate nested per trajectory (radau.m:1066-1076)
+  Q8  Gustafsson: per trajectory; by default RadauTe's gate (limiter also on order-change steps,
+      radaute_impl.hpp:1092-1100), RadauTeQuirks=0 -> radau.m:1066-1076
   Q9  Reject is cleared at the top of every Newton iteration (radau.m:913) -- reproduced,
       so Estrad's retry fires on First only and the Reject limiter on accept is dead code.
 Counters (defined here, the reference is inconsistent between files): MATLAB semantics,
@@ -76,6 +77,7 @@ class RadauOptions:
     hhou: float = 1.2
     hhod: float = 0.8
     Gustafsson: bool = True
+    RadauTeQuirks: int = 1      # bit 0: quirk Q8, Gustafsson limiter not gated by ChangeFlag (radaute_impl.hpp:1092-1100)
 
     def validate(self):
         """Option checks of the constructor, src/cpp/radaute_impl.hpp:65-214 (raise, not exit)."""
@@ -467,12 +469,15 @@ def radau_solve(f, jac, t0, tfinal, y0, opts: RadauOptions | None = None, record
         if err < 1:                                 # ------- accepted  :1054
             First = False
             stats["AccptNbr"] += 1
-            if op.Gustafsson and not ChangeFlag:    # :1066-1076
+            gus_upd = op.Gustafsson and not ChangeFlag          # radau.m:1066-1076
+            gus_lim = op.Gustafsson if (op.RadauTeQuirks & 1) else gus_upd   # radaute_impl.hpp:1092-1100 (Q8)
+            if gus_lim:
                 if stats["AccptNbr"] > 1:
                     facgus = (hacc / h) * (err * err / erracc) ** (1.0 / (NbrStg + 1.0)) / Safe
                     facgus = max(FacR, min(FacL, facgus))
                     quot = max(quot, facgus)
                     hnew = h / quot
+            if gus_upd:
                 hacc = h
                 erracc = max(1.0e-2, err)
             if Sm is not None:

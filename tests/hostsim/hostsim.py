@@ -25,6 +25,11 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def _gus(opts):
+    """RadauParams::Gustafsson bit mask: bit 0 on, bit 1 limiter not gated by ChangeFlag (quirk Q8)."""
+    return (1 | (2 if getattr(opts, "RadauTeQuirks", 1) & 1 else 0)) if opts.Gustafsson else 0
+
+
 def _params(lib, opts, ny, sign, par):
     P = (C.c_char * lib.hostsim_params_size())()
     rt = np.ascontiguousarray(np.broadcast_to(np.asarray(opts.RelTol, dtype=np.float64), (ny,)))
@@ -34,7 +39,7 @@ def _params(lib, opts, ny, sign, par):
                             d(opts.Safe), d(opts.Quot1), d(opts.Quot2), d(opts.FacL), d(opts.FacR), d(opts.Vitu),
                             d(opts.Vitd), d(opts.hhou), d(opts.hhod), C.c_int(sign), C.c_longlong(opts.MaxNbrStep),
                             C.c_int(int(opts.Start_Newt)), C.c_int(opts.MaxNbrNewton), C.c_int(opts.NbrStg),
-                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(int(opts.Gustafsson)),
+                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(_gus(opts)),
                             _dp(par[:8]), C.c_int(min(par.size, 8)))
     return P
 
@@ -101,7 +106,7 @@ def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
                             d(opts.Safe), d(opts.Quot1), d(opts.Quot2), d(opts.FacL), d(opts.FacR), d(opts.Vitu),
                             d(opts.Vitd), d(opts.hhou), d(opts.hhod), C.c_int(sign), C.c_longlong(opts.MaxNbrStep),
                             C.c_int(int(opts.Start_Newt)), C.c_int(opts.MaxNbrNewton), C.c_int(opts.NbrStg),
-                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(int(opts.Gustafsson)),
+                            C.c_int(opts.MinNbrStg), C.c_int(opts.MaxNbrStg), C.c_int(_gus(opts)),
                             _dp(par), C.c_int(par.size))
     y = np.empty_like(y0)
     t = np.empty(M)
