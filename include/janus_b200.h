@@ -129,6 +129,14 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
                      double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                      int64_t* work);
 
+/* jb200_solve_host with a compact result set for the PCIe link: counters as int32 [M,8] (they are bounded by
+ * MaxNbrStep * 17 * 7 < 2^31 for MaxNbrStep <= 1e6), and t_out / h_out / nstg / work optional (NULL = not copied):
+ * 68 B per trajectory device->host for Ny = 4 instead of 128.  Same reference interface as jb200_solve_host
+ * (RadauTe::solve() + the public result fields, src/cpp/radaute.hpp:296,253,98-108).                       */
+int jb200_solve_host_compact(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
+                             double* t_out, double* h_out, int32_t* res, int32_t* stats32, int32_t* nstg,
+                             int64_t* work);
+
 /* Incremental stepping: the state / step(htry, dyns, ft, state) protocol of the reference's Python
  * steppers (src/python/seulext.py:8-148 SeulexState, :158-581 step; src/python/seulex_dual_example_vdp.py:
  * 136-175 driver loop), carried by the Radau stepper.  A state holds M trajectories parked on the

@@ -205,12 +205,26 @@ static int launch_lu(long long M, const double* Are, const double* Aim, const do
   return 0;
 }
 
+static __global__ void narrow_stats_kernel(const long long* __restrict__ s64, long long n, int* __restrict__ s32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s32[i] = (int)s64[i];
+}
+
+static void free_workspace(Handle* H) {
+  cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work); cudaFree(H->d_stats32);
+  H->d_y0 = H->d_ts = H->d_y = H->d_t = H->d_h = nullptr;
+  H->d_res = H->d_nstg = H->d_stats32 = nullptr;
+  H->d_stats = H->d_work = nullptr;
+  H->cap = 0;
+}
+
 static int ensure_workspace(Handle* H, long long M) {
   if (M <= H->cap) return 0;
-  cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
-  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
-  H->cap = 0;
+  free_workspace(H);   // pointers are nulled: a failed allocation below leaves nothing dangling
   const int ny = H->ny;
+  struct Guard { Handle* H; bool ok = false; ~Guard() { if (!ok) { free_workspace(H); cudaGetLastError(); } } } guard{H};
+  JB_CUDA(cudaMalloc(&H->d_stats32, sizeof(int) * M * 8));
   JB_CUDA(cudaMalloc(&H->d_y0, sizeof(double) * M * ny));
   JB_CUDA(cudaMalloc(&H->d_ts, sizeof(double) * M * 2));
   JB_CUDA(cudaMalloc(&H->d_y, sizeof(double) * M * ny));
@@ -221,6 +235,7 @@ static int ensure_workspace(Handle* H, long long M) {
   JB_CUDA(cudaMalloc(&H->d_stats, sizeof(long long) * M * 8));
   JB_CUDA(cudaMalloc(&H->d_work, sizeof(long long) * M));
   H->cap = M;
+  guard.ok = true;
   return 0;
 }
 
@@ -315,7 +330,7 @@ void jb200_destroy(void* handle) {
   cudaFree(H->d_counter);
   ws_free(H->ws);
   cudaFree(H->d_y0); cudaFree(H->d_ts); cudaFree(H->d_y); cudaFree(H->d_t); cudaFree(H->d_h);
-  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work);
+  cudaFree(H->d_res); cudaFree(H->d_nstg); cudaFree(H->d_stats); cudaFree(H->d_work); cudaFree(H->d_stats32);
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
   for (int i = 0; i < 3; i++) {
     if (H->aux[i]) cudaStreamDestroy(H->aux[i]);
@@ -379,6 +394,42 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   JB_CUDA(cudaMemcpyAsync(h_out, H->d_h, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaMemcpyAsync(res, H->d_res, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaMemcpyAsync(stats, H->d_stats, sizeof(long long) * M * 8, cudaMemcpyDeviceToHost, st));
+  if (nstg) JB_CUDA(cudaMemcpyAsync(nstg, H->d_nstg, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+  if (work) JB_CUDA(cudaMemcpyAsync(work, H->d_work, sizeof(long long) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int jb200_solve_host_compact(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
+                             double* h_out, int32_t* res, int32_t* stats32, int32_t* nstg, int64_t* work) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (M == 0) {
+    H->launches = 0;
+    return 0;
+  }
+  if (!y0 || !tspan || !y_out || !res || !stats32) return fail(JB200_EINVAL, "null buffer");
+  for (int64_t m = 0; m < M; m++)
+    if (!(tspan[2 * m + 1] != tspan[2 * m])) return fail(JB200_EINVAL, "Time vector must be strictly monotonic");
+  int rc = ensure_workspace(H, M);
+  if (rc) return rc;
+  cudaStream_t st = H->own_stream;
+  const int ny = H->ny;
+  JB_CUDA(cudaMemcpyAsync(H->d_y0, y0, sizeof(double) * M * ny, cudaMemcpyHostToDevice, st));
+  JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
+  const DenseArgs none{2, nullptr, nullptr, nullptr};
+  rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, work ? H->d_work : nullptr,
+                 none, st);
+  if (rc) return rc;
+  JB_CUDA(cudaMemcpyAsync(y_out, H->d_y, sizeof(double) * M * ny, cudaMemcpyDeviceToHost, st));
+  narrow_stats_kernel<<<(unsigned)std::min<long long>((M * 8 + 255) / 256, 148 * 16), 256, 0, st>>>(H->d_stats, M * 8, H->d_stats32);
+  JB_CUDA(cudaGetLastError());
+  H->launches += 1;
+  JB_CUDA(cudaMemcpyAsync(res, H->d_res, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
+  JB_CUDA(cudaMemcpyAsync(stats32, H->d_stats32, sizeof(int) * M * 8, cudaMemcpyDeviceToHost, st));
+  if (t_out) JB_CUDA(cudaMemcpyAsync(t_out, H->d_t, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+  if (h_out) JB_CUDA(cudaMemcpyAsync(h_out, H->d_h, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
   if (nstg) JB_CUDA(cudaMemcpyAsync(nstg, H->d_nstg, sizeof(int) * M, cudaMemcpyDeviceToHost, st));
   if (work) JB_CUDA(cudaMemcpyAsync(work, H->d_work, sizeof(long long) * M, cudaMemcpyDeviceToHost, st));
   JB_CUDA(cudaStreamSynchronize(st));

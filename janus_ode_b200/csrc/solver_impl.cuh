@@ -330,12 +330,18 @@ struct EpochWS {
   size_t sort_tmp_bytes = 0;
 };
 inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
-  ws.M = M;
-  if (M <= ws.cap && parked_bytes <= ws.rec_bytes) return 0;
+  if (M <= ws.cap && parked_bytes <= ws.rec_bytes) {
+    ws.M = M;
+    return 0;
+  }
   cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
   cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp);
-  ws.order = nullptr; ws.nsel = nullptr; ws.sort_tmp = nullptr; ws.sort_tmp_bytes = 0;
-  ws.cap = 0;
+  ws = EpochWS();   // every pointer nulled, cap = 0: a failed allocation below leaves nothing dangling
+  struct Guard {
+    EpochWS& ws; bool ok = false;
+    ~Guard() { if (!ok) { cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts); cudaFree(ws.order);
+                          cudaFree(ws.nsel); cudaFree(ws.sort_tmp); ws = EpochWS(); cudaGetLastError(); } }
+  } guard{ws};
   ws.rec_bytes = parked_bytes;
   JB_CUDA(cudaMalloc(&ws.parked, parked_bytes * M));
   JB_CUDA(cudaMalloc(&ws.tag, sizeof(unsigned short) * M));
@@ -346,6 +352,8 @@ inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
   JB_CUDA(cudaMalloc(&ws.sort_tmp, ws.sort_tmp_bytes));
   JB_CUDA(cudaMalloc(&ws.counts, sizeof(int) * NKEYS));
   ws.cap = M;
+  ws.M = M;
+  guard.ok = true;
   return 0;
 }
 inline void ws_free(EpochWS& ws) {
@@ -372,7 +380,7 @@ struct Handle {
   // workspace of jb200_solve_host
   long long cap = 0;
   double *d_y0 = nullptr, *d_ts = nullptr, *d_y = nullptr, *d_t = nullptr, *d_h = nullptr;
-  int *d_res = nullptr, *d_nstg = nullptr;
+  int *d_res = nullptr, *d_nstg = nullptr, *d_stats32 = nullptr;
   long long* d_stats = nullptr;
   long long* d_work = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -534,7 +542,11 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     if (rc) return rc;
   }
   const bool key_then_h = H->epoch_horder == 2 && ws.have_order;   // regime key major, H(y0) minor (stable radix sort)
+  static const bool trace = std::getenv("JB200_EPOCH_TRACE") != nullptr;   // developer aid: per-epoch timeline on stderr
+  cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+  if (trace) for (auto& e : tev) cudaEventCreate(&e);
   for (long long epoch = 0;; epoch++) {
+    if (trace) cudaEventRecord(tev[0], st);
     JB_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
     hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts);
@@ -567,14 +579,28 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     JB_CUDA(cudaGetLastError());
     H->launches += 1;
     int rc = 0, used = 0;
+    if (trace) cudaEventRecord(tev[1], st);
     JB_CUDA(cudaEventRecord(H->ev_fork, st));
+    // Stragglers: once the live set no longer fills the GPU (one thread per trajectory), an epoch boundary buys no
+    // regrouping, only a sort + a host round trip -- let every trajectory run until it finishes or changes order.
+    const int mp = (run < H->sm_count * 2 * JB_THREADS) ? (1 << 30) : max_passes;
     // largest stage count first: its kernel is the longest-running per trajectory
-    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, ws, 3, base[3], cnt[3], max_passes, stop_on_accept, o, tspan, dense, st, used);
-    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, ws, 2, base[2], cnt[2], max_passes, stop_on_accept, o, tspan, dense, st, used);
-    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, ws, 1, base[1], cnt[1], max_passes, stop_on_accept, o, tspan, dense, st, used);
-    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, ws, 0, base[0], cnt[0], max_passes, stop_on_accept, o, tspan, dense, st, used);
+    if (cnt[3]) rc = launch_epoch<Ham, 7, VAR>(H, ws, 3, base[3], cnt[3], mp, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[2]) rc = launch_epoch<Ham, 5, VAR>(H, ws, 2, base[2], cnt[2], mp, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[1]) rc = launch_epoch<Ham, 3, VAR>(H, ws, 1, base[1], cnt[1], mp, stop_on_accept, o, tspan, dense, st, used);
+    if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, ws, 0, base[0], cnt[0], mp, stop_on_accept, o, tspan, dense, st, used);
     if (rc) return rc;
+    if (trace) {
+      cudaEventRecord(tev[2], st);
+      cudaEventSynchronize(tev[2]);
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev[0], tev[1]);
+      cudaEventElapsedTime(&b, tev[1], tev[2]);
+      fprintf(stderr, "[epoch %lld] live %d  s1 %d s3 %d s5 %d s7 %d  sort %.3f ms  kernels %.3f ms\n", epoch, run, cnt[0], cnt[1],
+              cnt[2], cnt[3], a, b);
+    }
   }
+  if (trace) for (auto& e : tev) cudaEventDestroy(e);
   return 0;
 }
 

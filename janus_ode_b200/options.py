@@ -91,7 +91,8 @@ def _to_np(v):
 
 @dataclass
 class StatsTe:
-    """Per-trajectory int64 counters, one tensor per field (src/cpp/radaute.hpp:98-108)."""
+    """Per-trajectory counters, one tensor per field (src/cpp/radaute.hpp:98-108): int64 like the reference for device
+    solves; solves on host tensors carry them as int32 over the PCIe link (jb200_solve_host_compact)."""
     FcnNbr: object = None
     JacNbr: object = None
     DecompNbr: object = None

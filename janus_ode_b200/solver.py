@@ -181,21 +181,23 @@ class RadauTe:
         self.h = torch.zeros(self.M, dtype=torch.float64, device=self.device)
         self.stats = None
         self.nstg = None
-        self.count = 0
-        self.res = None
+        self._res = self._res32 = None
+        self.want_work = False     # host path: also fetch the per-trajectory FLOP counts (roofline accounting)
 
     def solve(self):
         H = self._handle
         M, ny, dev = self.M, self.Ny, self.device
         # host path: page-locked result buffers so the D2H copies of jb200_solve_host are direct DMA
         kw = dict(device=dev) if self.y.is_cuda else dict(device=dev, pin_memory=True)
+        host = not self.y.is_cuda
         y_out = torch.empty(M, ny, dtype=torch.float64, **kw)
         t_out = torch.empty(M, dtype=torch.float64, **kw)
         h_out = torch.empty(M, dtype=torch.float64, **kw)
         res = torch.empty(M, dtype=torch.int32, **kw)
-        stats = torch.empty(M, 8, dtype=torch.int64, **kw)
+        # host path: int32 counters on the PCIe link (jb200_solve_host_compact); StatsTe widens lazily
+        stats = torch.empty(M, 8, dtype=torch.int32 if host else torch.int64, **kw)
         nstg = torch.empty(M, dtype=torch.int32, **kw)
-        work = torch.empty(M, dtype=torch.int64, **kw)
+        work = None if (host and not self.want_work) else torch.empty(M, dtype=torch.int64, **kw)
         if self.y.is_cuda and self.ntspan > 2:
             # output at the requested tspan points (radau.m OutFlag 3): tout, yout, nout like the reference
             self.tout = torch.zeros(M, self.ntspan, dtype=torch.float64, **kw)
@@ -211,16 +213,34 @@ class RadauTe:
                 _lib.check_h(H, H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
                                            _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work), _stream_ptr(dev)))
         else:
-            _lib.check_h(H, H.L.jb200_solve_host(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
-                                            _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work)))
+            _lib.check_h(H, H.L.jb200_solve_host_compact(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),
+                                                         _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work)))
         self.y, self.t, self.h = y_out, t_out, h_out
         self.stats = StatsTe.from_tensor(stats)
         self.nstg = nstg
         self.work = work           # algorithmic FLOPs per trajectory (roofline accounting)
-        self.res = res.to(torch.float64)
+        self._res32 = res
+        self._res = None
         self.gpu_launches = int(H.L.jb200_last_launches(H.h))
-        self.count = int(stats[:, 4].max().item()) if M > 0 else 0   # passes of the reference's loop
         return self.res
+
+    @property
+    def res(self):
+        """[M] fp64 result codes like the reference's `Tensor solve()` (widened from int32 on first use)."""
+        if self._res is None and self._res32 is not None:
+            self._res = self._res32.to(torch.float64)
+        return self._res
+
+    @res.setter
+    def res(self, v):
+        self._res, self._res32 = v, None
+
+    @property
+    def count(self):
+        """passes of the reference's outer loop (radaute.hpp:417): the largest StepNbr of the batch"""
+        if self.stats is None or self.M == 0:
+            return 0
+        return int(self.stats.raw[:, 4].max().item())
 
 
 class RadauState:
@@ -438,7 +458,6 @@ class RadauTeD(RadauTe):
         self.y, self.yd, self.t, self.h, self.nstg, self.work, self.sens_iters = y_out, S_out, t_out, h_out, nstg, work, it
         self.stats = StatsTe.from_tensor(stats)
         self.gpu_launches = 1
-        self.count = int(stats[:, 4].max().item()) if M else 0
         self.res = res.to(torch.float64)
         self.dydtf = self.dyns(self.t, self.y)
         return self.res

@@ -72,6 +72,7 @@ def evaluate(problem, par, sign, y, adaptor=True):
 
 def _solve_chunk(args):
     (problem, par, sign, adaptor, batch, y0, tspan, rtol, atol, h0, stg, max_steps) = args
+    import time
     M, Ny = y0.shape
     y = np.empty_like(y0)
     t = np.empty(M)
@@ -80,6 +81,8 @@ def _solve_chunk(args):
     stats = np.empty((M, 8), dtype=np.int64)
     nstg = np.empty(M, dtype=np.int64)
     passes = np.empty(M, dtype=np.int64)
+    lib()
+    t_start = time.perf_counter()
     rc = lib().ref_radau_solve(
         C.c_int(PB[problem]), C.c_double(par), C.c_int(sign), C.c_int(int(adaptor)), C.c_int(int(batch)),
         C.c_int64(M), C.c_int(Ny), _dp(y0), _dp(tspan), C.c_double(rtol), C.c_double(atol), C.c_double(h0),
@@ -88,7 +91,8 @@ def _solve_chunk(args):
     if rc != 0:
         lib().ref_last_error.restype = C.c_char_p
         raise RuntimeError(f"reference solver failed ({rc}): {lib().ref_last_error().decode()[:400]}")
-    return dict(y=y, t=t, h=h, res=res.astype(np.int32), stats=stats, nstg=nstg.astype(np.int32), passes=passes)
+    secs = np.full(M, (time.perf_counter() - t_start) / max(M, 1))   # solver seconds per row (no process start-up)
+    return dict(y=y, t=t, h=h, res=res.astype(np.int32), stats=stats, nstg=nstg.astype(np.int32), passes=passes, secs=secs)
 
 
 def trace(problem, par, sign, y0, tspan, rtol, atol, h0=1e-2, stages=(3, 3, 7), max_steps=100000, adaptor=False,
@@ -126,7 +130,7 @@ def solve(problem, par, sign, y0, tspan, rtol, atol, h0=1e-2, stages=(3, 3, 7), 
     import sys
     import tempfile
     lib()                                            # build before starting workers
-    edges = np.linspace(0, M, procs * 4 + 1).astype(int)
+    edges = np.linspace(0, M, procs * 2 + 1).astype(int)
     chunks = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
     parts = [None] * len(chunks)
     with tempfile.TemporaryDirectory() as td:

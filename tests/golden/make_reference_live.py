@@ -53,13 +53,13 @@ JOBS = {
     "c2_vdp_var_adaptor": lambda: run("c2_vdp_var_adaptor", "vdp", 1000.0, configs.c2_vdp(), 256, True, adaptor=True),
     "c2_vdp_s3_ulp": lambda: run("c2_vdp_s3_ulp", "vdp", 1000.0, configs.c2_vdp(fixed_order=True), 256, False, ulp=True),
     "c2_vdp_var_ulp": lambda: run("c2_vdp_var_ulp", "vdp", 1000.0, configs.c2_vdp(), 256, True, ulp=True),
-    "c3_pmp_bang_var": lambda: run("c3_pmp_bang_var", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang"), 1024, True),
-    "c3_pmp_bang_s3": lambda: run("c3_pmp_bang_s3", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang", fixed_order=True), 1024, False),
+    "c3_pmp_bang_var": lambda: run("c3_pmp_bang_var", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang"), 256, True),
+    "c3_pmp_bang_s3": lambda: run("c3_pmp_bang_s3", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang", fixed_order=True), 256, False),
     "c3_pmp_smooth_var": lambda: run("c3_pmp_smooth_var", "vdp_pmp_smooth", 1.0, configs.c3_pmp(1024, "smooth"), 1024, True),
     "c3_pmp_smooth_s3": lambda: run("c3_pmp_smooth_s3", "vdp_pmp_smooth", 1.0, configs.c3_pmp(1024, "smooth", fixed_order=True), 1024, False),
     "c1_harmonic_var_ulp": lambda: run("c1_harmonic_var_ulp", "harmonic", 1.0, configs.c1_harmonic(1024), 256, True, ulp=True),
     "c1_harmonic_s3_ulp": lambda: run("c1_harmonic_s3_ulp", "harmonic", 1.0, configs.c1_harmonic(1024, fixed_order=True), 256, False, ulp=True),
-    "c3_pmp_bang_var_ulp": lambda: run("c3_pmp_bang_var_ulp", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang"), 256, True, ulp=True),
+    "c3_pmp_bang_var_ulp": lambda: run("c3_pmp_bang_var_ulp", "vdp_pmp_bang", 1.0, configs.c3_pmp(1024, "bangbang"), 128, True, ulp=True),
 }
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ def gpu_solve(cfg, host=False):
     torch.cuda.synchronize()
     return dict(y=r.y.cpu().numpy(), t=r.t.cpu().numpy(), h=r.h.cpu().numpy(), res=res.cpu().numpy().astype(np.int32),
                 stats=r.stats.raw.cpu().numpy(), nstg=r.nstg.cpu().numpy(), launches=r.gpu_launches,
-                work=r.work.cpu().numpy())
+                work=r.work.cpu().numpy() if r.work is not None else None)
 
 
 def oracle_solve(cfg, arith):
