@@ -129,6 +129,18 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
                      double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                      int64_t* work);
 
+/* SEULEX (semi-implicit extrapolation) behind the same boundary: one call = one `SeulexT.step(htry, dyns, state)` of the
+ * reference's Python stepper for every trajectory (src/python/seulext.py:158-581, dy_batch :593-667; state fields
+ * of SeulexState :8-70).  Device pointers, updated in place: y [M,Ny], x [M] (time), theta [M], k_targ [M], hnext [M],
+ * flags [M] (bit 0 first_step, 1 last_step, 2 reject, 3 prev_reject), yjac [M,Ny] (the state the kept Jacobian
+ * `state.dfdy` was evaluated at); outputs hdid [M], k_out / nrej [M] (table rows used, rejected attempts; may be NULL).
+ * quirks bit 0: the clock advances by htry even after an in-step reduction, like the reference (seulext.py:483-485);
+ * 0 = advance by the step actually taken.  jb200_seulex_init gives the initial theta / k_targ of a SeulexState.   */
+int jb200_seulex_step(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry,
+                      double* y, double* x, double* theta, int32_t* k_targ, double* hnext, double* hdid,
+                      int32_t* flags, double* yjac, int32_t* k_out, int32_t* nrej, void* stream);
+int jb200_seulex_init(double atol, double rtol, int KMAXX, double* theta0, int32_t* k_targ0);
+
 /* jb200_solve_host with a compact result set for the PCIe link: counters as int32 [M,8] (they are bounded by
  * MaxNbrStep * 17 * 7 < 2^31 for MaxNbrStep <= 1e6), and t_out / h_out / nstg / work optional (NULL = not copied):
  * 68 B per trajectory device->host for Ny = 4 instead of 128.  Same reference interface as jb200_solve_host

@@ -530,6 +530,33 @@ int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, do
   return ops->dopri(H, a, (cudaStream_t)stream);
 }
 
+int jb200_seulex_step(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry, double* y,
+                      double* x, double* theta, int32_t* k_targ, double* hnext, double* hdid, int32_t* flags, double* yjac,
+                      int32_t* k_out, int32_t* nrej, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  if (!htry || !y || !x || !theta || !k_targ || !hnext || !hdid || !flags || !yjac) return fail(JB200_EINVAL, "null buffer");
+  if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");
+  if (KMAXX < 2 || KMAXX + 1 > sx::IMAXX_CAP) return fail(JB200_EINVAL, "KMAXX must be in [2, 15]");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->seulex) return fail(JB200_ENOTSUP, "SEULEX is available for the thread-resident Hamiltonians only");
+  const sx::StepArgs a{(long long)M, atol, rtol, KMAXX, quirks, htry, y, x, theta, (int*)k_targ, hnext, hdid, (int*)flags, yjac,
+                       (int*)k_out, (int*)nrej};
+  return ops->seulex(H, a, (cudaStream_t)stream);
+}
+
+int jb200_seulex_init(double atol, double rtol, int KMAXX, double* theta0, int32_t* k_targ0) {
+  if (!theta0 || !k_targ0) return fail(JB200_EINVAL, "null argument");
+  if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");
+  // SeulexState.__init__ (src/python/seulext.py:44-46, 66-70): theta = 2 jac_redo, k_targ from the tolerances
+  const double jac_redo = std::fmin(1.0e-4, rtol);
+  *theta0 = 2.0 * jac_redo;
+  const double logfact = -std::log10(rtol + atol) * 0.6 + 0.5;
+  *k_targ0 = (int)std::floor(std::fmax(1.0, std::fmin((double)(KMAXX - 1), std::nearbyint(logfact))));
+  return 0;
+}
+
 int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const double* bre, const double* bim,
                    double* xre, double* xim, void* stream) {
   if (M <= 0) return 0;

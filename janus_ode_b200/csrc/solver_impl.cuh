@@ -29,6 +29,7 @@
 #include "../../include/janus_b200.h"
 #include "radau_core.cuh"
 #include "dopri853.cuh"
+#include "seulex.cuh"
 
 namespace jb {
 
@@ -784,6 +785,43 @@ int launch_dopri(Handle* H, const dp::StepArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// SEULEX: one call = one step() of every trajectory (seulex.cuh)
+template <class Ham>
+__global__ void __launch_bounds__(128) seulex_kernel(const __grid_constant__ RadauParams P, const sx::StepArgs a) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
+    double y[NY], yj[NY];
+    load_row<NY>(a.y, m, y);
+    load_row<NY>(a.yjac, m, yj);
+    double x = a.x[m], theta = a.theta[m], hnext = a.hnext[m], hdid;
+    int k_targ = a.k_targ[m], flags = a.flags[m], k, nrej;
+    sx::seulex_step_one<Ham>(P.ham_par, P.sign, a.atol, a.rtol, a.KMAXX, a.quirks, a.htry[m], y, x, theta, k_targ, hnext, hdid,
+                             flags, yj, k, nrej);
+    store_row<NY>(a.y, m, y);
+    store_row<NY>(a.yjac, m, yj);
+    a.x[m] = x;
+    a.theta[m] = theta;
+    a.k_targ[m] = k_targ;
+    a.hnext[m] = hnext;
+    a.hdid[m] = hdid;
+    a.flags[m] = flags;
+    if (a.k_out) a.k_out[m] = k;
+    if (a.nrej) a.nrej[m] = nrej;
+  }
+}
+template <class Ham>
+int launch_seulex(Handle* H, const sx::StepArgs& a, cudaStream_t st) {
+#ifdef JB_SLIM
+  return fail(JB200_ENOTSUP, "this plugin was built without the SEULEX kernel");
+#else
+  const long long blocks = std::max<long long>(1, std::min<long long>((a.M + 127) / 128, (long long)H->sm_count * 8));
+  seulex_kernel<Ham><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  JB_CUDA(cudaGetLastError());
+  H->launches = 1;
+  return 0;
+#endif
+}
+
 // forward sensitivities (radau_core.cuh: Sens / sens_step): one thread = one trajectory with its Ny x Ny
 // sensitivity matrix, all stage counts inside one kernel (order selection at run time)
 template <class Ham, int SM, bool VAR>
@@ -865,12 +903,14 @@ struct HamOps {
   int (*sens)(Handle*, const double*, const double*, const double*, long long, double*, double*, double*, double*, int*,
               long long*, int*, long long*, int*, cudaStream_t) = nullptr;   // solve with forward sensitivities
   void (*st_free)(EpochWS&) = nullptr;   // optional: the state of the incremental protocol is not a plain EpochWS
+  int (*seulex)(Handle*, const sx::StepArgs&, cudaStream_t) = nullptr;   // SEULEX step (thread-resident Hamiltonians)
 };
 template <class Ham>
 HamOps make_ops() {
   return HamOps{Ham::NV,           Ham::NPAR,         &dispatch_order<Ham>, &launch_dyns<Ham>,
                 &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>,
-                nullptr,          nullptr,           &launch_dopri<Ham>,   &launch_sens<Ham>};
+                nullptr,          nullptr,           &launch_dopri<Ham>,   &launch_sens<Ham>,
+                nullptr,          &launch_seulex<Ham>};
 }
 
 }  // namespace jb

@@ -365,6 +365,96 @@ def fp64_peak_tflops(iters=20000):
     return v.value
 
 
+class SeulexState:
+    """State object of the reference's stiff extrapolation stepper, same constructor and fields as
+    SeulexState(y, x, atoll, rtoll, KMAXX, alpha, ft) (/root/reference/src/python/seulext.py:8-70): y [M,D],
+    x [M], hnext / hdid [M], k_targ [M], theta [M], first_step / last_step / reject / prev_reject [M] (bool views
+    of one flag word).  `alpha` and `ft` are carried like the reference does (its step() does not read them).
+    Everything lives on the CUDA device of `y`; `dfdy` (the kept Jacobian) is evaluated on demand from the state it
+    was taken at."""
+
+    def __init__(self, y, x, atoll, rtoll, KMAXX=13, alpha=0.0, ft=None):
+        if not (isinstance(y, torch.Tensor) and y.is_cuda and y.dtype == torch.float64 and y.dim() == 2):
+            raise _lib.JanusB200Error("SeulexState lives on CUDA float64 tensors [M,D] only (no CPU fallback)")
+        dev = y.device
+        self.M, self.D = y.shape
+        self.y = y.contiguous().clone()
+        self.x = torch.as_tensor(x, dtype=torch.float64, device=dev).reshape(-1).expand(self.M).contiguous().clone()
+        self.atol, self.rtol = float(atoll), float(rtoll)
+        self.alpha, self.ft = alpha, ft
+        self.KMAXX, self.IMAXX = int(KMAXX), int(KMAXX) + 1
+        th, kt = C.c_double(), C.c_int32()
+        _lib.check(_lib.lib().jb200_seulex_init(self.atol, self.rtol, self.KMAXX, C.byref(th), C.byref(kt)))
+        self.theta = torch.full((self.M,), th.value, dtype=torch.float64, device=dev)
+        self.k_targ = torch.full((self.M,), kt.value, dtype=torch.int32, device=dev)
+        self.hnext = torch.full((self.M,), -1.0e99, dtype=torch.float64, device=dev)
+        self.hdid = torch.zeros(self.M, dtype=torch.float64, device=dev)
+        self.flags = torch.ones(self.M, dtype=torch.int32, device=dev)       # first_step
+        self.k = torch.zeros(self.M, dtype=torch.int32, device=dev)          # table rows of the last step
+        self.nrej = torch.zeros(self.M, dtype=torch.int32, device=dev)       # rejected attempts of the last step
+        self._yjac = self.y.clone()
+        self.xold = self.x.clone()
+        self.EPS = torch.finfo(torch.float64).eps
+        self._dyns = None
+
+    first_step = property(lambda self: (self.flags & 1) != 0)
+    last_step = property(lambda self: (self.flags & 2) != 0)
+    reject = property(lambda self: (self.flags & 4) != 0)
+    prev_reject = property(lambda self: (self.flags & 8) != 0)
+
+    @property
+    def dfdy(self):
+        """the Jacobian the stepper currently holds, [M,D,D] (state.dfdy of the reference)"""
+        if self._dyns is None:
+            raise _lib.JanusB200Error("no step has been taken yet")
+        return self._dyns.jacobian(self.x, self._yjac)
+
+    _FIELDS = ("y", "x", "theta", "k_targ", "hnext", "hdid", "flags", "k", "nrej", "_yjac", "xold")
+
+    def __getitem__(self, mask):
+        """sub-state of the selected trajectories (seulext.py:118-148), used as `state[mask] = step(..., state[mask])`"""
+        import copy
+        sub = copy.copy(self)
+        for f in self._FIELDS:
+            setattr(sub, f, getattr(self, f)[mask].contiguous())
+        sub.M = sub.y.shape[0]
+        return sub
+
+    def __setitem__(self, mask, new):
+        for f in self._FIELDS:
+            getattr(self, f)[mask] = getattr(new, f)
+        self._dyns = new._dyns or self._dyns
+
+
+class SeulexT:
+    """`state = SeulexT().step(htry, dyns, state)`: one step of the semi-implicit extrapolation method for every
+    trajectory of `state`, like /root/reference/src/python/seulext.py:158-581 (driver loop:
+    src/python/seulex_batch_example.py:44-77: htry = state.hnext, clipped to the final time).  `dyns` must be a
+    HamiltonianSystem; the whole step runs in one kernel (`jb200_seulex_step`, csrc/seulex.cuh).
+    reference_clock=True reproduces the reference's time bookkeeping after an in-step reduction (x advances by htry,
+    seulext.py:483-485); the default advances x by the step actually taken."""
+
+    def __init__(self, reference_clock: bool = False):
+        self.quirks = 1 if reference_clock else 0
+
+    def step(self, htry, dyns, state: SeulexState) -> SeulexState:
+        if not isinstance(dyns, HamiltonianSystem):
+            raise TypeError("dyns must be a janus_ode_b200.HamiltonianSystem")
+        if state.D != dyns.hamiltonian.Ny:
+            raise ValueError(f"state.y must be [M,{dyns.hamiltonian.Ny}]")
+        dev = state.y.device
+        ht = torch.as_tensor(htry, dtype=torch.float64, device=dev).reshape(-1).expand(state.M).contiguous()
+        H = dyns._h()
+        state._dyns = dyns
+        state.xold = state.x.clone()
+        with torch.cuda.device(dev):
+            _lib.check_h(H, H.L.jb200_seulex_step(H.h, state.M, state.atol, state.rtol, state.KMAXX, self.quirks, _ptr(ht),
+                                                  _ptr(state.y), _ptr(state.x), _ptr(state.theta), _ptr(state.k_targ),
+                                                  _ptr(state.hnext), _ptr(state.hdid), _ptr(state.flags), _ptr(state._yjac),
+                                                  _ptr(state.k), _ptr(state.nrej), _stream_ptr(dev)))
+        return state
+
+
 class Dopri853Te:
     """Explicit Dormand-Prince 8(5,3) stepper for non-stiff batches with the reference's object shape
     (/root/reference/src/python/dopri853te.py:4-5, 290-315):

@@ -1172,6 +1172,215 @@ int oracle_radau_trace(int problem, const double *par, int sign, int Ny, const d
   return radau_one(&pb, op, tspan[0], tspan[1], y0, y_out, t_out, &h_out, stats, &nstg, rec_h, rec_cap, rec_n, NULL);
 }
 
+/* ------------------------------------------------------------------ SEULEX (semi-implicit extrapolation)
+ * One call = one step() of the reference's Python stepper, per trajectory:
+ *   /root/reference/src/python/seulext.py:8-64 (SeulexState: nseq, cost, coeff, k_targ, theta, jac_redo),
+ *   :158-581 (SeulexT.step: order / step-size control), :593-667 (dy_batch: the linearly implicit Euler sequence
+ *   with the stability check), polyextr (src/python/seulex.py:439-462).  The reference's masked code is restated
+ *   for a batch of ONE trajectory (M = 1), which is how it is run live for the golden vectors
+ *   (tests/golden/make_seulex_golden.py).  Its algorithm is Numerical Recipes' StepperSie; the reference's
+ *   deviations from it are kept (they are what the live stepper does):
+ *     S2  after a rejected attempt without a fresh Jacobian: theta *= jac_redo (seulext.py:476-478; NR: theta =
+ *         2 jac_redo and the Jacobian is re-evaluated)
+ *     S3  kopt is capped at KMAXX, not KMAXX - 1 (:511, :527)
+ *     S4  in the k == k_targ - 1 branch the new step size / break only happen when k_targ is also lowered (:378-389)
+ *     S5  the sequence is integrated with |h| (forward in time only, :249)
+ *   and one is switchable, default OFF because it corrupts the time axis:
+ *     S1  quirks & 1: the clock advances by htry even when the step was shortened after a rejected attempt
+ *         (x += h with h = htry, :483-485: `h` is never updated inside compute_jac)
+ * flags: 1 first_step, 2 last_step, 4 reject, 8 prev_reject.                                                   */
+#define SX_IMAXX 16
+static void seulex_one(const problem_t *pb, double atol, double rtol, int KMAXX, int quirks, double htry, double *y,
+                       double *x_io, double *theta_io, int *ktarg_io, double *hnext_io, double *hdid_out, int *flags_io,
+                       double *dfdy, int *k_out, int *nrej_out) {
+  const int n = pb->Ny, IMAXX = KMAXX + 1;
+  int nseq[SX_IMAXX + 1];
+  double cost[SX_IMAXX + 1], coeff[SX_IMAXX + 1][SX_IMAXX + 1], hopt[SX_IMAXX + 1], work[SX_IMAXX + 1];
+  double table[SX_IMAXX][NYMAX], ysav[NYMAX], yseq[NYMAX], scale[NYMAX];
+  nseq[0] = 2; nseq[1] = 3;
+  for (int i = 2; i < IMAXX; i++) nseq[i] = 2 * nseq[i - 2];
+  cost[0] = 5.0 + 1.0 + nseq[0] * (1.0 + 1.0);
+  for (int k = 0; k < KMAXX; k++) cost[k + 1] = cost[k] + (nseq[k + 1] - 1) * (1.0 + 1.0) + 1.0;
+  for (int k = 0; k < IMAXX; k++)
+    for (int l = 0; l < k; l++) coeff[k][l] = 1.0 / ((double)nseq[k] / (double)nseq[l] - 1.0);
+  const double jac_redo = fmin(1.0e-4, rtol);
+  double x = *x_io, theta = *theta_io, hnext = *hnext_io;
+  int k_targ = *ktarg_io, fl = *flags_io;
+  int first_step = fl & 1, last_step = (fl >> 1) & 1, reject = (fl >> 2) & 1, prev_reject = (fl >> 3) & 1, calcjac = 0;
+  double errold = 0.0, fac = 0.0;
+  for (int i = 0; i < IMAXX; i++) { hopt[i] = 0.0; work[i] = 0.0; }
+  work[0] = 1.0e30;
+  const double h = htry;
+  for (int i = 0; i < n; i++) ysav[i] = y[i];
+  const int forward = h > 0;
+  if (h != hnext && !first_step) last_step = 1;
+  if (reject) { last_step = 0; prev_reject = 1; theta = 2.0 * jac_redo; }
+  for (int i = 0; i < n; i++) scale[i] = FMA(rtol, fabs(y[i]), atol);
+  reject = 0;
+  double hnew = fabs(h), h_att = fabs(h);
+  int k = 0, firstk = 1, nrej = 0;
+  while (firstk || reject) {
+    if (theta > jac_redo && !calcjac && fabs(h) > EPS) {
+      jacobian(pb, x, y, dfdy);
+      calcjac = 1;
+    }
+    firstk = 0; reject = 0;
+    h_att = hnew;
+    int brk = 0;
+    k = 0;
+    while (k <= k_targ + 1 && !brk) {
+      /* ---- dy: nseq[k] linearly implicit Euler steps over h_att (seulext.py:593-667) */
+      int success = 1;
+      {
+        const int nsteps = nseq[k];
+        const double hh = hnew / nsteps, rhh = 1.0 / hh;
+        rlu_t lu;
+        for (int i = 0; i < n; i++)
+          for (int j = 0; j < n; j++) lu.a[i * n + j] = (i == j) ? (-dfdy[i * n + j] + rhh) : -dfdy[i * n + j];
+        rlu_factor(n, &lu);
+        double xnew = x + hh, ytemp[NYMAX], delta[NYMAX], yend[NYMAX];
+        for (int i = 0; i < n; i++) ytemp[i] = ysav[i];
+        rhs(pb, xnew, ytemp, delta);
+        rlu_solve(n, &lu, delta);
+        for (int nn = 1; nn < nsteps; nn++) {
+          for (int i = 0; i < n; i++) ytemp[i] = ytemp[i] + delta[i];
+          xnew += hh;
+          rhs(pb, xnew, ytemp, yend);
+          if (nn == 1 && k <= 1) {
+            double del1 = 0.0, del2 = 0.0, dyt[NYMAX];
+            for (int i = 0; i < n; i++) { const double v = delta[i] / scale[i]; del1 = FMA(v, v, del1); }
+            del1 = sqrt(del1);
+            rhs(pb, x + hh, ytemp, dyt);
+            for (int i = 0; i < n; i++) delta[i] = dyt[i] - delta[i] * rhh;
+            rlu_solve(n, &lu, delta);
+            for (int i = 0; i < n; i++) { const double v = delta[i] / scale[i]; del2 = FMA(v, v, del2); }
+            del2 = sqrt(del2);
+            theta = del2 / fmax(1.0, del1);
+            if (theta > 1.0) { success = 0; break; }
+          }
+          rlu_solve(n, &lu, yend);
+          for (int i = 0; i < n; i++) delta[i] = yend[i];
+        }
+        for (int i = 0; i < n; i++) yseq[i] = ytemp[i] + delta[i];
+      }
+      if (!success) { hnew = fabs(hnew) * 0.5; reject = 1; brk = 1; break; }
+      if (k == 0) {
+        for (int i = 0; i < n; i++) y[i] = yseq[i];
+      } else {
+        for (int i = 0; i < n; i++) table[k - 1][i] = yseq[i];
+        for (int j = k - 1; j > 0; j--)   /* polyextr */
+          for (int i = 0; i < n; i++) table[j - 1][i] = FMA(coeff[k][j], table[j][i] - table[j - 1][i], table[j][i]);
+        for (int i = 0; i < n; i++) y[i] = FMA(coeff[k][0], table[0][i] - y[i], table[0][i]);
+        double err = 0.0;
+        for (int i = 0; i < n; i++) {
+          scale[i] = FMA(rtol, fabs(ysav[i]), atol);
+          const double v = (y[i] - table[0][i]) / scale[i];
+          err = FMA(v, v, err);
+        }
+        err = sqrt(err / n);
+        if (err > 1.0 / EPS || (k > 1 && err >= errold)) { reject = 1; hnew = fabs(hnew) * 0.5; brk = 1; break; }
+        errold = fmax(4.0 * err, 1.0);
+        const double expo = 1.0 / (k + 1);
+        const double facmin = POW(0.1, expo);
+        if (err == 0.0) fac = 1.0 / facmin;
+        else {
+          fac = 0.93 / POW(err / 0.6, expo);
+          fac = fmax(facmin / 4.0, fmin(1.0 / facmin, fac));
+        }
+        hopt[k] = fabs(hnew * fac);
+        work[k] = cost[k] / hopt[k];
+        if ((first_step || last_step) && err <= 1.0) { brk = 1; break; }
+        if (k == k_targ - 1 && !prev_reject && !first_step && !last_step) {
+          if (err <= 1.0) { brk = 1; break; }
+          if (err > (double)nseq[k_targ] * (double)nseq[k_targ + 1] * 4.0) {
+            reject = 1; k_targ = k;
+            if (k_targ > 1 && work[k - 1] < 0.7 * work[k]) {   /* S4: step size and break only in here */
+              k_targ -= 1;
+              hnew = hopt[k_targ];
+              brk = 1; break;
+            }
+          }
+        }
+        if (k == k_targ) {
+          if (err <= 1.0) { brk = 1; break; }
+          if (err > nseq[k + 1] * 2.0) {
+            reject = 1;
+            if (k_targ > 1 && work[k - 1] < 0.7 * work[k]) k_targ -= 1;
+            hnew = hopt[k_targ];
+            brk = 1; break;
+          }
+        }
+        if (k == k_targ + 1) {
+          if (err > 1.0) {
+            reject = 1;
+            if (k_targ > 1 && work[k_targ - 1] < 0.7 * work[k_targ]) k_targ -= 1;
+            hnew = hopt[k_targ];
+          }
+          brk = 1; break;
+        }
+      }
+      k += 1;
+    }
+    if (reject) {
+      nrej += 1;
+      prev_reject = 1;
+      if (!calcjac) theta = theta * jac_redo;   /* S2 */
+      if (nrej > 200) break;                    /* guard of this restatement only: a step that can never succeed */
+    }
+  }
+  const double hs = (quirks & 1) ? h : (forward ? h_att : -h_att);   /* S1 */
+  x = x + hs;
+  *hdid_out = hs;
+  first_step = 0;
+  int kopt = k;
+  if (k == 1) kopt = 2;
+  if (k <= k_targ) {
+    kopt = k;
+    if (work[k - 1] < work[k] * 0.7) kopt = k - 1;
+    if (work[k] < 0.9 * work[k - 1]) kopt = imin(k + 1, KMAXX);
+  }
+  if (k != 1 && k > k_targ) {
+    kopt = k - 1;
+    if (k > 2 && work[k - 2] < 0.7 * work[k - 1]) kopt = k - 2;
+    if (work[k] < 0.9 * work[kopt]) kopt = imin(k, KMAXX);
+  }
+  if (prev_reject) {
+    k_targ = imin(kopt, k);
+    hnew = fmin(fabs(hs), hopt[k_targ]);
+    prev_reject = 0;
+  } else {
+    if (kopt <= k) hnew = hopt[kopt];
+    else if (k < k_targ && work[k] < 0.9 * work[k - 1]) hnew = hopt[k] * cost[imin(kopt + 1, KMAXX)] / cost[k];
+    else hnew = hopt[k] * cost[kopt] / cost[k];
+    k_targ = kopt;
+  }
+  *hnext_io = forward ? hnew : -hnew;
+  *x_io = x; *theta_io = theta; *ktarg_io = k_targ;
+  *flags_io = (first_step ? 1 : 0) | (last_step ? 2 : 0) | (reject ? 4 : 0) | (prev_reject ? 8 : 0);
+  *k_out = k; *nrej_out = nrej;
+}
+
+/* initial controller state of SeulexState (seulext.py:44-46, 66-70) */
+void oracle_seulex_init(double atol, double rtol, int KMAXX, double *theta, int *k_targ) {
+  const double jac_redo = fmin(1.0e-4, rtol);
+  *theta = 2.0 * jac_redo;
+  const double logfact = -log10(rtol + atol) * 0.6 + 0.5;
+  double kt = fmax(1.0, fmin((double)(KMAXX - 1), nearbyint(logfact)));
+  *k_targ = (int)floor(kt);
+}
+
+int oracle_seulex_step(int problem, const double *par, int sign, int Ny, long long M, double atol, double rtol, int KMAXX,
+                       int quirks, const double *htry, double *y, double *x, double *theta, int *k_targ, double *hnext,
+                       double *hdid, int *flags, double *dfdy, int *k_out, int *nrej) {
+  if (KMAXX + 1 > SX_IMAXX) return -1;
+  problem_t pb;
+  pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+  for (long long m = 0; m < M; m++)
+    seulex_one(&pb, atol, rtol, KMAXX, quirks, htry[m], y + m * Ny, x + m, theta + m, k_targ + m, hnext + m, hdid + m,
+               flags + m, dfdy + m * Ny * Ny, k_out + m, nrej + m);
+  return 0;
+}
+
 /* batched dynamics / Jacobian (checks the stage-eval kernel) */
 int oracle_radau_trace2(int problem, const double *par, int sign, int Ny, const double *y0, const double *tspan,
                         const oracle_opts *op, double *y_out, long long *stats, double *plog, int cap, int *n) {

@@ -236,5 +236,41 @@ def lu_solve(A, b, arith="reference"):
     return xr
 
 
+class SeulexOracleState:
+    """controller state of one batch for seulex_step (mirrors the fields of the reference's SeulexState,
+    /root/reference/src/python/seulext.py:8-70 that survive between step() calls)."""
+
+    def __init__(self, y, x, atol, rtol, KMAXX=13):
+        self.y = np.ascontiguousarray(y, dtype=np.float64).copy()
+        self.M, self.D = self.y.shape
+        self.x = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.M,))).copy()
+        self.atol, self.rtol, self.KMAXX = float(atol), float(rtol), int(KMAXX)
+        th, kt = C.c_double(), C.c_int()
+        lib().oracle_seulex_init(C.c_double(self.atol), C.c_double(self.rtol), C.c_int(self.KMAXX), C.byref(th), C.byref(kt))
+        self.theta = np.full(self.M, th.value)
+        self.k_targ = np.full(self.M, kt.value, dtype=np.int32)
+        self.hnext = np.full(self.M, -1.0e99)
+        self.hdid = np.zeros(self.M)
+        self.flags = np.ones(self.M, dtype=np.int32)          # first_step
+        self.dfdy = np.zeros((self.M, self.D, self.D))
+        self.k = np.zeros(self.M, dtype=np.int32)
+        self.nrej = np.zeros(self.M, dtype=np.int32)
+
+
+def seulex_step(problem, par, sign, htry, st, quirks=0, arith="reference"):
+    """one SeulexT.step() per trajectory of `st` (in place)."""
+    set_arith(arith)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    htry = np.ascontiguousarray(np.broadcast_to(np.asarray(htry, dtype=np.float64), (st.M,))).copy()
+    ip = C.POINTER(C.c_int)
+    rc = lib().oracle_seulex_step(
+        C.c_int(PB[problem]), _dp(par), C.c_int(sign), C.c_int(st.D), C.c_longlong(st.M), C.c_double(st.atol),
+        C.c_double(st.rtol), C.c_int(st.KMAXX), C.c_int(quirks), _dp(htry), _dp(st.y), _dp(st.x), _dp(st.theta),
+        st.k_targ.ctypes.data_as(ip), _dp(st.hnext), _dp(st.hdid), st.flags.ctypes.data_as(ip), _dp(st.dfdy),
+        st.k.ctypes.data_as(ip), st.nrej.ctypes.data_as(ip))
+    assert rc == 0
+    return st
+
+
 def max_threads():
     return lib().oracle_max_threads()

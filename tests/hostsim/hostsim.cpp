@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../janus_ode_b200/csrc/radau_core.cuh"
+#include "../../janus_ode_b200/csrc/seulex.cuh"
 
 using namespace jb;
 
@@ -46,7 +47,30 @@ static void dispatch(const RadauParams& P, const double* y0, const double* tspan
   else run<Ham, 7, true>(P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg);
 }
 
+template <class Ham>
+static void seulex_run(const double* par, int sign, long long M, double atol, double rtol, int KMAXX, int quirks,
+                       const double* htry, double* y, double* x, double* theta, int* k_targ, double* hnext, double* hdid,
+                       int* flags, double* yjac, int* k_out, int* nrej) {
+  constexpr int NY = Ham::NV;
+  for (long long m = 0; m < M; m++)
+    sx::seulex_step_one<Ham>(par, (double)sign, atol, rtol, KMAXX, quirks, htry[m], y + m * NY, x[m], theta[m], k_targ[m],
+                             hnext[m], hdid[m], flags[m], yjac + m * NY, k_out[m], nrej[m]);
+}
+
 extern "C" {
+// the SEULEX step of csrc/seulex.cuh on the CPU (same source as the kernel)
+int hostsim_seulex_step(int ham_id, const double* par, int sign, long long M, double atol, double rtol, int KMAXX, int quirks,
+                        const double* htry, double* y, double* x, double* theta, int* k_targ, double* hnext, double* hdid,
+                        int* flags, double* yjac, int* k_out, int* nrej) {
+  switch (ham_id) {
+    case HAM_HARMONIC: seulex_run<HamHarmonic>(par, sign, M, atol, rtol, KMAXX, quirks, htry, y, x, theta, k_targ, hnext, hdid, flags, yjac, k_out, nrej); return 0;
+    case HAM_VDP: seulex_run<HamVdp>(par, sign, M, atol, rtol, KMAXX, quirks, htry, y, x, theta, k_targ, hnext, hdid, flags, yjac, k_out, nrej); return 0;
+    case HAM_VDP_PMP_SMOOTH: seulex_run<HamVdpPmp<false>>(par, sign, M, atol, rtol, KMAXX, quirks, htry, y, x, theta, k_targ, hnext, hdid, flags, yjac, k_out, nrej); return 0;
+    case HAM_VDP_PMP_BANG: seulex_run<HamVdpPmp<true>>(par, sign, M, atol, rtol, KMAXX, quirks, htry, y, x, theta, k_targ, hnext, hdid, flags, yjac, k_out, nrej); return 0;
+  }
+  return -1;
+}
+
 void hostsim_set_dense(int nts, double* tout, double* yout, int* nout) {
   g_nts = nts; g_tout = tout; g_yout = yout; g_nout = nout;
 }

@@ -128,3 +128,21 @@ def solve(ham, par, sign, y0, tspan, opts, epochs_K=0):
     rc = lib.hostsim_solve_epochs(*args, C.c_int(epochs_K)) if epochs_K != 0 else lib.hostsim_solve(*args)
     assert rc == 0
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, **out)
+
+
+def seulex_step(ham_id, par, sign, htry, st, quirks=0):
+    """csrc/seulex.cuh compiled for the host: one step of every trajectory of an oracle.c_oracle.SeulexOracleState
+    (in place; st.dfdy is not used -- the kept Jacobian is st.yjac here)."""
+    lib = build()
+    L = C.CDLL(lib) if isinstance(lib, str) else lib
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    htry = np.ascontiguousarray(np.broadcast_to(np.asarray(htry, dtype=np.float64), (st.M,))).copy()
+    if not hasattr(st, "yjac"):
+        st.yjac = st.y.copy()
+    ip = C.POINTER(C.c_int)
+    rc = L.hostsim_seulex_step(C.c_int(ham_id), _dp(par), C.c_int(sign), C.c_longlong(st.M), C.c_double(st.atol),
+                               C.c_double(st.rtol), C.c_int(st.KMAXX), C.c_int(quirks), _dp(htry), _dp(st.y), _dp(st.x),
+                               _dp(st.theta), st.k_targ.ctypes.data_as(ip), _dp(st.hnext), _dp(st.hdid),
+                               st.flags.ctypes.data_as(ip), _dp(st.yjac), st.k.ctypes.data_as(ip), st.nrej.ctypes.data_as(ip))
+    assert rc == 0
+    return st
