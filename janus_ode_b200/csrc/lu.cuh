@@ -285,6 +285,100 @@ JB_HD void zlu_solve(const ZLUS<N>& S, double* br, double* bi) {
 #endif
 }
 
+// ------------------------------------------------------------------ compact complex factors, runtime block index
+// Storage of the rolled high-order steppers (radau_core.cuh: attempt_step_hi): ALL (s-1)/2 complex blocks of a
+// trajectory live in shared memory and are addressed by a RUN-TIME block number, so the factor / solve code exists
+// once in the instruction stream instead of once per block (the unrolled 5- and 7-stage steppers were 186 / 255 kB
+// of SASS and instruction-fetch bound: ncu `no_instruction` 4.3 / 5.4 of ~8 stall cycles per issue, round-2 profile).
+// Only what the solves read is kept: the strictly lower / upper parts (N^2 - N complex numbers), the reciprocals of
+// U's diagonal (N) and the pivots packed into one word: 2 N^2 + 1 words per block (33 for N = 4; three blocks of a
+// 7-stage stepper at 2 x 128 threads per SM = 198 kB of the 227 kB).  Same arithmetic as zlu_solve, bit for bit.
+template <int N>
+struct ZLUC {
+  static constexpr int OFF = N * N - N;
+  static constexpr int WORDS = 2 * N * N + 1;
+  JB_HD static constexpr int idx(int i, int j) { return i * (N - 1) + (j < i ? j : j - 1); }
+};
+
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+template <int N>
+__device__ __forceinline__ void zluc_store(int block, const ZLU<N>& L) {
+  const int b0 = block * ZLUC<N>::WORDS;
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++)
+      if (i != j) {
+        lc_smem(b0 + ZLUC<N>::idx(i, j)) = L.re[i * N + j];
+        lc_smem(b0 + ZLUC<N>::OFF + ZLUC<N>::idx(i, j)) = L.im[i * N + j];
+      }
+  int pk = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    lc_smem(b0 + 2 * ZLUC<N>::OFF + k) = L.rdre[k];
+    lc_smem(b0 + 2 * ZLUC<N>::OFF + N + k) = L.rdim[k];
+    pk |= L.piv[k] << (4 * k);
+  }
+  lc_smem(b0 + 2 * N * N) = __longlong_as_double((long long)pk);
+}
+
+template <int N>
+__device__ __forceinline__ void zluc_solve(int block, double* br, double* bi) {
+  const int b0 = block * ZLUC<N>::WORDS;
+  const int pk = (int)__double_as_longlong(lc_smem(b0 + 2 * N * N));
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int pv = (pk >> (4 * k)) & 15;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = (pv == i);
+      double x = br[k], y = br[i];
+      br[k] = sw ? y : x;
+      br[i] = sw ? x : y;
+      x = bi[k];
+      y = bi[i];
+      bi[k] = sw ? y : x;
+      bi[i] = sw ? x : y;
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) {
+      const double lr = lc_smem(b0 + ZLUC<N>::idx(i, j)), li = lc_smem(b0 + ZLUC<N>::OFF + ZLUC<N>::idx(i, j));
+      sr = fma(li, bi[j], fma(-lr, br[j], sr));
+      si = fma(-li, br[j], fma(-lr, bi[j], si));
+    }
+    br[i] = sr;
+    bi[i] = si;
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    double sr = br[i], si = bi[i];
+#pragma unroll
+    for (int j = i + 1; j < N; j++) {
+      const double ur = lc_smem(b0 + ZLUC<N>::idx(i, j)), ui = lc_smem(b0 + ZLUC<N>::OFF + ZLUC<N>::idx(i, j));
+      sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+      si = fma(-ui, br[j], fma(-ur, bi[j], si));
+    }
+    const double rr = lc_smem(b0 + 2 * ZLUC<N>::OFF + i), ri = lc_smem(b0 + 2 * ZLUC<N>::OFF + N + i);
+    br[i] = fma(-si, ri, sr * rr);
+    bi[i] = fma(si, rr, sr * ri);
+  }
+}
+#endif
+
+// which steppers run rolled (all complex blocks in shared memory, z / w in local memory): 5 and 7 stages on the device
+template <int N, int S>
+struct HiRoll {
+#if defined(JB_LC_SMEM) && !defined(JB_NO_ROLL_HI)
+  static constexpr bool on = (S >= 5) && (N <= 4);
+#else
+  static constexpr bool on = false;
+#endif
+};
+
 // how many of the (s-1)/2 complex blocks of an s-stage stepper are parked in shared memory
 template <int N, int S>
 struct LcPlace {

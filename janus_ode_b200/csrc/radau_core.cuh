@@ -91,7 +91,28 @@ struct Traj {
   using Place = LcPlace<NY, SM>;
   ZLUS<NY> LcS[Place::NS > 0 ? Place::NS : 1];
   ZLU<NY> Lc[Place::NR > 0 ? Place::NR : 1];
+#if !defined(__CUDA_ARCH__)
+  ZLU<NY> hiblk[3];   // host pass of the rolled high-order stepper (device: shared memory, lu.cuh ZLUC)
+#endif
 };
+
+// complex block `block` (run-time index) of the rolled high-order stepper
+template <int NY, int SM>
+JB_HD void hi_store(Traj<NY, SM>& T, int block, const ZLU<NY>& Z) {
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+  zluc_store<NY>(block, Z);
+#else
+  T.hiblk[block] = Z;
+#endif
+}
+template <int NY, int SM>
+JB_HD void hi_solve(const Traj<NY, SM>& T, int block, double* br, double* bi) {
+#if defined(__CUDA_ARCH__) && defined(JB_LC_SMEM)
+  zluc_solve<NY>(block, br, bi);
+#else
+  zlu_solve<NY>(T.hiblk[block], br, bi);
+#endif
+}
 
 JB_HD int imin(int a, int b) { return a < b ? a : b; }
 JB_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -306,7 +327,8 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
             zz[q3 * NY + i] = b;
           }
           constexpr int NS = LcPlace<NY, SM>::NS;
-          if ((q - 1) < NS) zlu_solve(T.LcS[(q - 1) < NS ? (q - 1) : 0], &zz[q2 * NY], &zz[q3 * NY]);
+          if constexpr (HiRoll<NY, S>::on) hi_solve<NY, SM>(T, q - 1, &zz[q2 * NY], &zz[q3 * NY]);
+          else if ((q - 1) < NS) zlu_solve(T.LcS[(q - 1) < NS ? (q - 1) : 0], &zz[q2 * NY], &zz[q3 * NY]);
           else zlu_solve<NY>(T.Lc[(q - 1 - NS) > 0 ? (q - 1 - NS) : 0], &zz[q2 * NY], &zz[q3 * NY]);
         }
       }
@@ -338,9 +360,402 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
   }
 }
 
+// factorisation of the rolled high-order steppers: real block in registers, complex blocks in a rolled loop into the
+// compact run-time-indexed store (lu.cuh ZLUC); same arithmetic as decomrc
+template <int NY, int S, int SM>
+JB_HD void decomrc_hi(Traj<NY, SM>& T, const double* Jac) {
+  using Tab = RadauTab<S>;
+  const double rh0 = 1.0 / T.h;
+  const double valp0 = Tab::ValP(0) * rh0;
+#pragma unroll
+  for (int i = 0; i < NY; i++)
+#pragma unroll
+    for (int j = 0; j < NY; j++) T.L0.a[i * NY + j] = (i == j) ? (valp0 - Jac[i * NY + j]) : -Jac[i * NY + j];
+  rlu_factor<NY>(T.L0);
+#pragma unroll 1
+  for (int q = 1; q <= (S - 1) / 2; q++) {
+    const double al = Tab::ValP(2 * q - 1) * rh0, be = Tab::ValP(2 * q) * rh0;
+    ZLU<NY> Z;
+#pragma unroll
+    for (int i = 0; i < NY; i++)
+#pragma unroll
+      for (int j = 0; j < NY; j++) {
+        Z.re[i * NY + j] = (i == j) ? (al - Jac[i * NY + j]) : -Jac[i * NY + j];
+        Z.im[i * NY + j] = (i == j) ? be : 0.0;
+      }
+    zlu_factor<NY>(Z);
+    hi_store<NY, SM>(T, q - 1, Z);
+  }
+}
+
+// ------------------------------------------------------------------ rolled high-order attempt (5 and 7 stages)
+// Same operations in the same order as attempt_step below -- bit-identical results -- but organised for the
+// instruction cache: the loops over the complex blocks (factorisation, Solvrad) and over the output stage of the
+// T / TI transforms are ROLLED, the transformed stage vectors z and w live in local memory (dynamically indexed;
+// the unrolled version spilled them anyway: 2.1 kB of spill stores per step at 7 stages) and all complex factors in
+// shared memory (lu.cuh: ZLUC).  The 7-stage stepper shrinks from ~16,000 to ~5,000 SASS instructions.
+template <class Ham, int NY, int S, int SM>
+JB_HD bool attempt_step_hi(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool jac_fresh, const DenseOut* out,
+                           Sens<NY>* sens) {
+  using Tab = RadauTab<S>;
+  constexpr int si = (S - 1) / 2, NQ = (S - 1) / 2;
+  const int Nit = nit_of(S, P.MaxNbrNewton);
+  double zl[S * NY], wl[S * NY];  // [stage][component], local memory
+
+  if (T.NeedNewLU) {  // radau.m:827-844
+    if (!jac_fresh) ham_jac<Ham>(T.yJ, P.ham_par, P.sign, Jac);
+    decomrc_hi<NY, S, SM>(T, Jac);
+    T.st[ST_DEC] += 1;
+    T.work += W_lu(S, NY);
+    T.NeedNewLU = false;
+  }
+  const bool Variab = (P.MaxNbrStg - P.MinNbrStg) != 0;
+  if (Variab && T.Keep) {  // radau.m:846-853
+    T.Keep = false;
+    T.ChangeNbr += 1;
+    if (T.ChangeNbr >= 10 && S < P.MaxNbrStg) T.NeedNewJac = false;
+  }
+  if (0.1 * fabs(T.h) <= fabs(T.t) * EPS) {  // radau.m:855
+    T.res = 1;
+    return true;
+  }
+  double rscal[NY];
+#pragma unroll
+  for (int i = 0; i < NY; i++) {
+    const double sc = fma(P.RelTol1[si][i], fabs(T.y[i]), P.AbsTol1[si][i]);  // radau.m:858-862
+    rscal[i] = 1.0 / sc;
+  }
+  if (T.First || P.Start_Newt || T.ChangeFlag) {  // radau.m:872-891
+#pragma unroll 1
+    for (int k = 0; k < S * NY; k++) {
+      zl[k] = 0.0;
+      wl[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) T.cont[k] = 0.0;
+  } else {
+    const double hquot = T.h / T.h_old;
+#pragma unroll 1
+    for (int q = 0; q < S; q++) {
+      const double cq = Tab::C(q) * hquot;
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        double zq = (cq - Tab::C(0) + 1.0) * T.cont[(S - 1) * NY + i];
+#pragma unroll
+        for (int q1 = 2; q1 <= S; q1++) zq = (zq + T.cont[(S - q1) * NY + i]) * (cq - Tab::C(q1 - 1) + 1.0);
+        zl[q * NY + i] = zq;
+      }
+    }
+    double zr[S * NY];
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) zr[k] = zl[k];
+#pragma unroll 1
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        double acc = Tab::TI(j, 0) * zr[i];
+#pragma unroll
+        for (int q = 1; q < S; q++) acc = fma(Tab::TI(j, q), zr[q * NY + i], acc);
+        wl[j * NY + i] = acc;
+      }
+  }
+  // ------- simplified Newton (radau.m:897-1018)
+  const double FNewt = P.FNewt[si];
+  T.FacConv = det_pow(fmax(T.FacConv, EPS), 0.8);
+  T.Theta = fabs(P.Thet);
+  T.Newt = 0;
+  const double rh = 1.0 / T.h;
+  double NewNrm = 0.0, OldNrm = 0.0, thqold = 0.0;
+  bool newton_failed = false;
+  for (;;) {
+    T.Reject = false;  // radau.m:913 (quirk Q9)
+    T.Newt += 1;
+    if (T.Newt > Nit) {  // radau.m:915-925
+      T.UnExpStepRej = true;
+      T.st[ST_REJ] += 1;
+      T.st[ST_NREJ] += 1;
+      T.h = T.h * 0.5;
+      T.Reject = true;
+      T.Last = false;
+      T.NeedNewLU = true;
+      newton_failed = true;
+      break;
+    }
+    {  // stage right-hand sides f(y + z_q), then z = TI f  (radau.m:932-948)
+      double fq[S * NY];
+      bool nanf = false;
+#pragma unroll
+      for (int q = 0; q < S; q++) {
+        double yq[NY];
+#pragma unroll
+        for (int i = 0; i < NY; i++) yq[i] = T.y[i] + zl[q * NY + i];
+        ham_dyns<Ham>(yq, P.ham_par, P.sign, &fq[q * NY]);
+#pragma unroll
+        for (int i = 0; i < NY; i++) nanf = nanf || (fq[q * NY + i] != fq[q * NY + i]);
+      }
+      if (nanf) {
+        T.res = 2;
+        return true;
+      }
+      T.st[ST_FCN] += S;
+#pragma unroll 1
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          double acc = Tab::TI(j, 0) * fq[i];
+#pragma unroll
+          for (int q = 1; q < S; q++) acc = fma(Tab::TI(j, q), fq[q * NY + i], acc);
+          zl[j * NY + i] = acc;
+        }
+    }
+    {  // Solvrad (radaute_impl.hpp:1721-1868)
+      const double valp0 = Tab::ValP(0) * rh;
+      double z0[NY];
+#pragma unroll
+      for (int i = 0; i < NY; i++) z0[i] = fma(-valp0, wl[i], zl[i]);
+      rlu_solve<NY>(T.L0, z0);
+#pragma unroll
+      for (int i = 0; i < NY; i++) zl[i] = z0[i];
+#pragma unroll 1
+      for (int q = 1; q <= NQ; q++) {
+        const int q2 = 2 * q - 1, q3 = 2 * q;
+        const double v2 = Tab::ValP(q2) * rh, v3 = Tab::ValP(q3) * rh;
+        double a[NY], b[NY];
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          const double w2 = wl[q2 * NY + i], w3 = wl[q3 * NY + i];
+          a[i] = fma(v3, w3, fma(-v2, w2, zl[q2 * NY + i]));
+          b[i] = fma(-v2, w3, fma(-v3, w2, zl[q3 * NY + i]));
+        }
+        hi_solve<NY, SM>(T, q - 1, a, b);
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          zl[q2 * NY + i] = a[i];
+          zl[q3 * NY + i] = b[i];
+        }
+      }
+    }
+    T.st[ST_SOL] += 1;
+    T.work += W_newt(S, NY, Ham::FLOPS_F);
+    NewNrm = 0.0;  // radau.m:955-959
+#pragma unroll 1
+    for (int q = 0; q < S; q++) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NY; i++) {
+        const double v = zl[q * NY + i] * rscal[i];
+        s = fma(v, v, s);
+      }
+      NewNrm += ::sqrt(s);
+    }
+    NewNrm = NewNrm * P.inv_sqrt_sn[si];
+    if (bad(NewNrm)) {
+      T.res = 2;
+      return true;
+    }
+    if (T.Newt > 1 && T.Newt < Nit) {  // radau.m:962-996
+      const double thq = NewNrm / OldNrm;
+      if (T.Newt == 2) T.Theta = thq;
+      else T.Theta = ::sqrt(thq * thqold);
+      thqold = thq;
+      if (T.Theta < 0.99) {
+        T.FacConv = T.Theta / (1.0 - T.Theta);
+        const double dyth = T.FacConv * NewNrm * ipow(T.Theta, Nit - 1 - T.Newt) / FNewt;
+        if (dyth >= 1.0) {
+          const double qNewt = fmax(1.0e-4, fmin(20.0, dyth));
+          const double hhfac = 0.8 * det_pow(qNewt, -1.0 / (4.0 + Nit - 1 - T.Newt));
+          T.h = hhfac * T.h;
+          T.Reject = true;
+          T.Last = false;
+          T.UnExpNewtRej = hhfac <= 0.5;
+          T.st[ST_NREJ] += 1;
+          T.st[ST_REJ] += 1;
+          T.NeedNewLU = true;
+          newton_failed = true;
+          break;
+        }
+      } else {
+        T.h = T.h * 0.5;
+        T.Reject = true;
+        T.Last = false;
+        T.UnExpStepRej = true;
+        T.st[ST_REJ] += 1;
+        T.NeedNewLU = true;
+        newton_failed = true;
+        break;
+      }
+    }
+    OldNrm = fmax(NewNrm, EPS);  // radau.m:1001-1012
+    {
+      double wr[S * NY];
+#pragma unroll
+      for (int k = 0; k < S * NY; k++) {
+        wr[k] = wl[k] + zl[k];
+        wl[k] = wr[k];
+      }
+#pragma unroll 1
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+          double acc = Tab::T(j, 0) * wr[i];
+#pragma unroll
+          for (int q = 1; q < S; q++) acc = fma(Tab::T(j, q), wr[q * NY + i], acc);
+          zl[j * NY + i] = acc;
+        }
+    }
+    if (T.FacConv * NewNrm > FNewt) continue;  // radau.m:1014
+    break;
+  }
+  if (newton_failed) return false;  // radau.m:1020-1022
+
+  // ------- Estrad (radaute_impl.hpp:1902-1986)
+  T.work += W_tail(S, NY, Ham::FLOPS_F);
+  double temp[NY], ev[NY];
+#pragma unroll
+  for (int i = 0; i < NY; i++) temp[i] = zl[i] * (Tab::Dd(0) * rh);
+#pragma unroll 1
+  for (int q = 1; q < S; q++) {
+    const double d = Tab::Dd(q) * rh;
+#pragma unroll
+    for (int i = 0; i < NY; i++) temp[i] = fma(zl[q * NY + i], d, temp[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NY; i++) ev[i] = T.f0[i] + temp[i];
+  rlu_solve<NY>(T.L0, ev);
+  double err;
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      const double v = ev[i] * rscal[i];
+      s = fma(v, v, s);
+    }
+    err = fmax(::sqrt(s) * P.inv_sqrt_n, 1e-10);
+  }
+  if (err >= 1.0 && (T.First || T.Reject)) {
+    double ya[NY];
+#pragma unroll
+    for (int i = 0; i < NY; i++) ya[i] = T.y[i] + err;  // sic: scalar err (radaute_impl.hpp:1951)
+    ham_dyns<Ham>(ya, P.ham_par, P.sign, ev);
+    T.st[ST_FCN] += 1;
+    T.work += Ham::FLOPS_F + 2LL * NY * NY + 3LL * NY;
+#pragma unroll
+    for (int i = 0; i < NY; i++) ev[i] = ev[i] + temp[i];
+    rlu_solve<NY>(T.L0, ev);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NY; i++) {
+      const double v = ev[i] * rscal[i];
+      s = fma(v, v, s);
+    }
+    err = fmax(::sqrt(s) * P.inv_sqrt_n, 1e-10);
+  }
+  if (bad(err)) {
+    T.res = 2;
+    return true;
+  }
+  // ------- new step size (radau.m:1038-1050)
+  const double fac = fmin(P.Safe, (2.0 * Nit + 1.0) / (2.0 * Nit + T.Newt));
+  double quot = fmax(P.FacR, fmin(P.FacL, det_pow(err, 1.0 / S + 1.0) / fac));
+  double hnew = T.h / quot;
+  if (err < 1.0) {  // ------- accepted (radau.m:1054-1232)
+    T.First = false;
+    T.st[ST_ACC] += 1;
+    const bool gus_upd = (P.Gustafsson & 1) && !T.ChangeFlag;   // quirk Q8: see attempt_step
+    const bool gus_lim = (P.Gustafsson & 2) ? true : gus_upd;
+    if (gus_lim) {
+      if (T.st[ST_ACC] > 1) {
+        const double ratio = err * err / T.erracc;
+        double root;
+        if (S == 7) root = ::sqrt(::sqrt(::sqrt(ratio)));
+        else root = det_pow(ratio, 1.0 / (S + 1.0));
+        double facgus = (T.hacc / T.h) * root / P.Safe;
+        facgus = fmax(P.FacR, fmin(P.FacL, facgus));
+        quot = fmax(quot, facgus);
+        hnew = T.h / quot;
+      }
+    }
+    if (gus_upd) {
+      T.hacc = T.h;
+      T.erracc = fmax(1.0e-2, err);
+    }
+    if (sens) sens_step<Ham, NY, S, SM>(T, P, zl, rscal, *sens);
+    T.h_old = T.h;
+    T.t = T.t + T.h;
+    double z[S * NY];
+#pragma unroll
+    for (int k = 0; k < S * NY; k++) z[k] = zl[k];
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.y[i] = T.y[i] + z[(S - 1) * NY + i];
+    // collocation polynomial (radau.m:1093-1107)
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.cont[(S - 1) * NY + i] = z[i] * (1.0 / Tab::C(0));
+#pragma unroll
+    for (int q = 1; q <= S - 1; q++) {
+      const double Fact = 1.0 / (Tab::C(S - q - 1) - Tab::C(S - q));
+#pragma unroll
+      for (int i = 0; i < NY; i++) T.cont[(q - 1) * NY + i] = (z[(S - q - 1) * NY + i] - z[(S - q) * NY + i]) * Fact;
+    }
+#pragma unroll
+    for (int jj = 2; jj <= S; jj++)
+#pragma unroll
+      for (int k = S; k >= jj; k--) {
+        const double Fact = (S - k == 0) ? 1.0 / (-Tab::C(jj - 1)) : 1.0 / (Tab::C(S - k - 1) - Tab::C(S - k + jj - 1));
+#pragma unroll
+        for (int i = 0; i < NY; i++) T.cont[(k - 1) * NY + i] = (T.cont[(k - 1) * NY + i] - T.cont[(k - 2) * NY + i]) * Fact;
+      }
+    if (out) dense_output<NY, S, SM>(T, *out);  // radau.m:1150-1168
+    T.NeedNewJac = true;
+    if (T.Last) {  // radau.m:1193-1197
+      T.h = T.hopt;
+      T.st[ST_REJ] += 1;
+      return true;
+    }
+    ham_dyns<Ham>(T.y, P.ham_par, P.sign, T.f0);
+    T.st[ST_FCN] += 1;
+    {
+      bool nanf = false;
+#pragma unroll
+      for (int i = 0; i < NY; i++) nanf = nanf || (T.f0[i] != T.f0[i]);
+      if (nanf) {
+        T.res = 2;
+        return true;
+      }
+    }
+    hnew = T.PosNeg * fmin(fabs(hnew), fabs(T.hmaxn));
+    T.hopt = T.PosNeg * fmin(fabs(T.h), fabs(hnew));
+    if (T.Reject) hnew = T.PosNeg * fmin(fabs(hnew), fabs(T.h));
+    T.Reject = false;
+    if ((T.t + hnew / P.Quot1 - T.tfinal) * T.PosNeg >= 0) {
+      T.h = T.tfinal - T.t;
+      T.Last = true;
+    } else {
+      const double qt = hnew / T.h;
+      if (T.Theta <= P.Thet && qt >= P.Quot1 && qt <= P.Quot2) {
+        T.Keep = true;
+        T.NeedNewJac = false;
+        T.NeedNewLU = false;
+        return false;
+      }
+      T.h = hnew;
+    }
+    T.NeedNewLU = true;
+    if (T.Theta <= P.Thet) T.NeedNewJac = false;
+  } else {  // ------- rejected (radau.m:1234-1253)
+    T.Reject = true;
+    T.Last = false;
+    if (T.First) T.h = T.h / 10.0;
+    else T.h = hnew;
+    if (T.st[ST_ACC] >= 1) T.st[ST_REJ] += 1;
+    T.NeedNewLU = true;
+  }
+  return false;
+}
+
 template <class Ham, int NY, int S, int SM>
 JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool jac_fresh, const DenseOut* out = nullptr,
                         Sens<NY>* sens = nullptr) {
+  if constexpr (HiRoll<NY, S>::on) return attempt_step_hi<Ham, NY, S, SM>(T, P, Jac, jac_fresh, out, sens);
   using Tab = RadauTab<S>;
   constexpr int si = (S - 1) / 2;
   const int Nit = nit_of(S, P.MaxNbrNewton);
@@ -825,34 +1240,57 @@ JB_HD void unpark(const Parked<NY>& p, Traj<NY, SM>& T, double& t0, bool& head_d
 // used up, or its order changed -> head_done tells the next owner to skip pass_head).
 // stop_on_accept (incremental step() API): also stop, with *stepped = true, right after the first
 // accepted step.
+// rebuild the factors a trajectory was parked with (first thing after unpark)
+template <class Ham, int NY, int S>
+JB_HD void epoch_begin(Traj<NY, S>& T, const RadauParams& P) {
+  if (!T.NeedNewLU) {
+    double Jac[NY * NY];
+    ham_jac<Ham>(T.yJ, P.ham_par, P.sign, Jac);
+    if constexpr (HiRoll<NY, S>::on) decomrc_hi<NY, S, S>(T, Jac);
+    else decomrc<NY, S, S>(T, Jac);
+  }
+}
+
+// one pass of run_epoch's loop: 0 = go on, 1 = trajectory finished, 2 = must be re-parked (its order changed ->
+// head_done, or stop_on_accept hit -> *stepped)
+template <class Ham, int NY, int S, bool VAR = true>
+JB_HD int epoch_pass(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int acc0, const DenseOut* out = nullptr,
+                     bool stop_on_accept = false, bool* stepped = nullptr) {
+  if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
+    if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
+    return 1;
+  }
+  double Jac[NY * NY];
+  bool jf = false;
+  if (!head_done) {
+    if (!pass_head<Ham, NY, S, VAR>(T, P, Jac, jf)) return 1;
+  }
+  if (T.NbrStg != S) {
+    head_done = true;
+    return 2;
+  }
+  head_done = false;
+  if (attempt_step<Ham, NY, S, S>(T, P, Jac, jf, out)) return 1;
+  if (stop_on_accept && T.st[ST_ACC] != acc0) {
+    *stepped = true;
+    return 2;
+  }
+  return 0;
+}
+
+// Run one parked trajectory at stage count S for at most max_passes attempted steps.
+// Returns true when the trajectory is finished; otherwise it must be re-parked (epoch budget
+// used up, or its order changed -> head_done tells the next owner to skip pass_head).
+// stop_on_accept (incremental step() API): also stop, with *stepped = true, right after the first
+// accepted step.
 template <class Ham, int NY, int S, bool VAR = true>
 JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes,
                      const DenseOut* out = nullptr, bool stop_on_accept = false, bool* stepped = nullptr) {
-  double Jac[NY * NY];
-  if (!T.NeedNewLU) {  // rebuild the factors this trajectory was parked with
-    ham_jac<Ham>(T.yJ, P.ham_par, P.sign, Jac);
-    decomrc<NY, S, S>(T, Jac);
-  }
+  epoch_begin<Ham, NY, S>(T, P);
   const int acc0 = T.st[ST_ACC];
   for (int passes = 0;;) {
-    bool jf = false;
-    if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
-      if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
-      return true;
-    }
-    if (!head_done) {
-      if (!pass_head<Ham, NY, S, VAR>(T, P, Jac, jf)) return true;
-    }
-    if (T.NbrStg != S) {
-      head_done = true;
-      return false;
-    }
-    head_done = false;
-    if (attempt_step<Ham, NY, S, S>(T, P, Jac, jf, out)) return true;
-    if (stop_on_accept && T.st[ST_ACC] != acc0) {
-      *stepped = true;
-      return false;
-    }
+    const int r = epoch_pass<Ham, NY, S, VAR>(T, P, head_done, acc0, out, stop_on_accept, stepped);
+    if (r) return r == 1;
     if (++passes >= max_passes) return false;
   }
 }

@@ -391,7 +391,11 @@ struct Handle {
 // dynamic shared memory of a kernel whose stepper parks complex LU blocks there (lu.cuh: ZLUS)
 template <int NY, int S>
 inline size_t lc_smem_bytes(int threads) {
-  return sizeof(double) * (size_t)LcPlace<NY, S>::NS * (size_t)ZLUS<NY>::WORDS * (size_t)threads;
+  // S = the largest stage count the kernel may run: the unrolled steppers park LcPlace::NS blocks (ZLUS layout), the rolled
+  // 5/7-stage steppers all (S-1)/2 blocks in the compact layout (ZLUC); an all-orders kernel needs the larger of the two
+  size_t words = (size_t)LcPlace<NY, S>::NS * (size_t)ZLUS<NY>::WORDS;
+  if (HiRoll<NY, S>::on) words = std::max(words, (size_t)((S - 1) / 2) * (size_t)ZLUC<NY>::WORDS);
+  return sizeof(double) * words * (size_t)threads;
 }
 
 // rows sorted by H(y0): radix sort (CUB) of the order-preserving bit pattern of H, payload = row index
