@@ -123,6 +123,24 @@ int jb200_solve_dense(void* handle, const double* y0, const double* tspan, int n
                       int32_t* nstg, int64_t* work, double* tout, double* yout, int32_t* nout,
                       void* stream);
 
+/* Output at every accepted step and event location.
+ * jb200_set_events: event functions of the handle, E_k(t, y) = A[k,:] . y - b[k], k < K <= 4, with the reference's
+ * `isterminal` (stop[k]) and `direction` (slope[k] = +1 rising, -1 falling, 0 both) -- EventFnType,
+ * src/cpp/radaute.hpp:44-47; zero location = EventZeroFcn, src/matlab/radau.m:1494-1618 (regula falsi / pegasus on the
+ * collocation polynomial; the C++ port src/cpp/radaute_impl.hpp:2030-2185 is incomplete).  K = 0 removes them.  A kernel
+ * cannot call a Python / std::function callback, hence the closed family of linear event functions.
+ * jb200_solve_out: tspan [M,2]; the computed points are recorded like the reference's OutFlag 1 (refine = 1,
+ * radaute_impl.hpp:1166-1183) / OutFlag 2 (refine > 1: refine - 1 interpolated points before each, radau.m:1130-1143) into
+ * tout [M,cap], yout [M,cap,Ny]; nout [M] counts ALL points (nout > cap: the caller's buffer was too small -- the
+ * reference regrows its buffer instead); the last stored point is overwritten with the final (t, y) like radau.m:1267-1269.
+ * Events (if set): te [M,ecap], ye [M,ecap,Ny], ie [M,ecap] (1-based index of the event function), nev [M]; a terminal
+ * event ends the trajectory at (te, ye) with res 0.  cap = 0 / ecap = 0: count only.  Device pointers.             */
+int jb200_set_events(void* handle, int K, const double* A, const double* b, const int32_t* stop, const int32_t* slope);
+int jb200_solve_out(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
+                    double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work, int refine, int cap,
+                    double* tout, double* yout, int32_t* nout, int ecap, double* te, double* ye, int32_t* ie,
+                    int32_t* nev, void* stream);
+
 /* Same with HOST pointers (what a reference caller holds: CPU tensors).  Copies in, solves,
  * copies out and synchronises; the device workspace lives in the handle.                   */
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,

@@ -367,6 +367,47 @@ int jb200_solve_dense(void* handle, const double* y0, const double* tspan, int n
                    (long long*)work, dense, (cudaStream_t)stream);
 }
 
+int jb200_set_events(void* handle, int K, const double* A, const double* b, const int32_t* stop, const int32_t* slope) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (K < 0 || K > 4) return fail(JB200_EINVAL, "0 <= K <= 4 event functions");
+  if (K > 0 && (!A || !b || !stop || !slope)) return fail(JB200_EINVAL, "null argument");
+  if (H->ham_id == JB200_HAM_MLP && K > 0) return fail(JB200_ENOTSUP, "events are available for the thread-resident Hamiltonians only");
+  H->P.ev_K = K;
+  for (int k = 0; k < K; k++) {
+    for (int i = 0; i < H->ny; i++) H->P.ev_A[k][i] = A[k * H->ny + i];
+    H->P.ev_b[k] = b[k];
+    H->P.ev_stop[k] = stop[k] != 0;
+    H->P.ev_slope[k] = slope[k] > 0 ? 1 : (slope[k] < 0 ? -1 : 0);
+  }
+  return 0;
+}
+
+int jb200_solve_out(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out, double* h_out,
+                    int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work, int refine, int cap, double* tout, double* yout,
+                    int32_t* nout, int ecap, double* te, double* ye, int32_t* ie, int32_t* nev, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M < 0) return fail(JB200_EINVAL, "M < 0");
+  if (refine < 1 || cap < 0 || ecap < 0) return fail(JB200_EINVAL, "refine >= 1, cap >= 0, ecap >= 0");
+  if (M > 0 && (!y0 || !tspan || !y_out || !t_out || !h_out || !res || !stats || !nout)) return fail(JB200_EINVAL, "null buffer");
+  if (cap > 0 && (!tout || !yout)) return fail(JB200_EINVAL, "null output buffer");
+  if (H->P.ev_K > 0 && (!nev || (ecap > 0 && (!te || !ye || !ie)))) return fail(JB200_EINVAL, "null event buffer");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  JB_CUDA(cudaMemsetAsync(nout, 0, sizeof(int) * M, st));
+  if (nev) JB_CUDA(cudaMemsetAsync(nev, 0, sizeof(int) * M, st));
+  DenseArgs d{2, cap > 0 ? tout : nullptr, cap > 0 ? yout : nullptr, (int*)nout};
+  d.mode = refine > 1 ? 2 : 1;
+  d.cap = cap;
+  d.refine = refine;
+  if (H->P.ev_K > 0) {
+    d.te = te; d.ye = ye; d.ie = (int*)ie; d.nev = (int*)nev; d.ecap = ecap;
+  }
+  return solve_dev(H, y0, tspan, (long long)M, y_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
+                   (long long*)work, d, st);
+}
+
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
                      double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work) {
   Handle* H = (Handle*)handle;

@@ -44,6 +44,10 @@ struct RadauParams {
   int Start_Newt, MaxNbrNewton, NbrStg, MinNbrStg, MaxNbrStg;
   int Gustafsson;            // bit 0: on; bit 1: limiter not gated by ChangeFlag (RadauTe, quirk Q8)
   double ham_par[8];
+  // event functions E_k(t, y) = ev_A[k] . y - ev_b[k]  (EventsFcn of the reference: value, isterminal, direction --
+  // src/cpp/radaute.hpp:44-47; zero location src/matlab/radau.m:1494-1618).  ev_K = 0: none.
+  int ev_K, ev_stop[4], ev_slope[4];
+  double ev_A[4][NYMAX], ev_b[4];
 };
 
 // Algorithmic FLOP model of SURVEY.md 8(d) (mul, add, div, sqrt, pow = 1; complex mul = 6, add = 2),
@@ -70,8 +74,19 @@ JB_HD constexpr int nit_of(int s, int MaxNbrNewton) {
 struct DenseOut {
   const double* tspan;  // [ntspan] requested output times (first = t0, last = tfinal)
   int ntspan;
-  double* tout;         // [ntspan]
+  double* tout;         // [ntspan]   (mode 1 / 2: [cap])
   double* yout;         // [ntspan][NY]
+  // mode 3 (default): output at the tspan points.  mode 1: every accepted step (OutFlag 1, radaute_impl.hpp:1166-1183);
+  // mode 2: plus refine - 1 interpolated points per step (OutFlag 2, radau.m:1130-1143).  cap = rows of tout / yout:
+  // the reference grows its buffers (torch::cat of the whole [M, .] tensor on every overflow); here the caller sizes
+  // them, points beyond cap are counted in nout but not stored.
+  int mode = 3, cap = 0, refine = 1;
+  // located events of this trajectory (radau.m:1110-1121): te [ecap], ye [ecap][NY], ie [ecap]; *nev counts them
+  double* te = nullptr;
+  double* ye = nullptr;
+  int* ie = nullptr;
+  int* nev = nullptr;
+  int ecap = 0;
 };
 
 template <int NY, int SM>
@@ -205,9 +220,115 @@ JB_HD void decomrc(Traj<NY, SM>& T, const double* Jac) {
 // returns true when the trajectory is finished (done or failed; T.res holds the code)
 // dense output after an accepted step: every requested time in (t - h, t] is evaluated on the
 // collocation polynomial (ntrprad, src/cpp/radaute_impl.hpp:1413-1440 == radau.m:1291-1308)
+// collocation polynomial of the step that just ended at (T.t, T.y) with size T.h_old, evaluated at time tn
+template <int NY, int S, int SM>
+JB_HD void ntrprad(const Traj<NY, SM>& T, double tn, double* yi_out) {
+  using Tab = RadauTab<S>;
+  const double s = (tn - T.t) / T.h_old;
+#pragma unroll
+  for (int i = 0; i < NY; i++) {
+    double yi = (s - (Tab::C(0) - 1.0)) * T.cont[(S - 1) * NY + i];
+#pragma unroll
+    for (int q = 1; q < S; q++) yi = (s - (Tab::C(q) - 1.0)) * (yi + T.cont[(S - 1 - q) * NY + i]);
+    yi_out[i] = yi + T.y[i];
+  }
+}
+
+JB_HD double eps_of(double t) {   // MATLAB eps(t): spacing of the doubles at |t|
+  const double a = fabs(t);
+  if (a < 2.2250738585072014e-308) return 4.9406564584124654e-324;
+  const int e = (int)((dbl_bits(a) >> 52) & 0x7ff) - 1023;
+  return bits_dbl((int64_t)(e - 52 + 1023) << 52);
+}
+
+// Event location after an accepted step (EventZeroFcn, src/matlab/radau.m:1494-1618; the C++ port
+// src/cpp/radaute_impl.hpp:2030-2185 is incomplete): E1 = event values at the start of the step, (T.t, T.y) its end.
+// For every event whose value changed sign in the requested direction the zero is located on the collocation polynomial
+// by the regula falsi / pegasus iteration of the reference; the earliest one is recorded.  Returns true when that
+// event is terminal: the trajectory then ends at (te, ye).
+template <int NY, int S, int SM>
+JB_HD bool locate_events(Traj<NY, SM>& T, const RadauParams& P, const DenseOut& out, const double* E1v, double t1) {
+  const double t2 = T.t;
+  double tol = 65536.0 * fmax(EPS, fmax(eps_of(t2), eps_of(t1)));
+  tol = fmin(tol, fabs(t2 - t1));
+  bool found = false, stop = false;
+  double tbest = 0.0, ybest[NY];
+  int ibest = 0;
+  for (int k = 0; k < P.ev_K; k++) {
+    double E2 = -P.ev_b[k];
+#pragma unroll
+    for (int i = 0; i < NY; i++) E2 = fma(P.ev_A[k][i], T.y[i], E2);
+    double t1N = t1, t2N = t2, E1 = E1v[k];
+    const double p12 = (E2 - E1) / (t2N - t1N);
+    if (!(E1 * E2 < 0 && p12 * P.ev_slope[k] >= 0)) continue;
+    double tNew = t2N, ENew = E2, yNew[NY];
+#pragma unroll
+    for (int i = 0; i < NY; i++) yNew[i] = T.y[i];
+    for (int iter = 1; iter < 50; iter++) {
+      const bool tRel = fabs(t1N - t2N) * tol < fmax(fabs(t1N), fabs(t2N));
+      const bool tAbs = fabs(t1N - t2N) < tol;
+      if ((fabs(ENew) < tol && tRel && tAbs) || fabs(ENew) == 0.0) break;
+      if (fabs(E1) < 200.0 * tol || fabs(E2) < 200.0 * tol) tNew = 0.5 * (t1N + t2N);
+      else tNew = tNew + (-ENew / (E2 - E1) * (t2N - t1N));
+      ntrprad<NY, S, SM>(T, tNew, yNew);
+      ENew = -P.ev_b[k];
+#pragma unroll
+      for (int i = 0; i < NY; i++) ENew = fma(P.ev_A[k][i], yNew[i], ENew);
+      if (ENew * E2 < 0) {
+        t1N = t2N;
+        E1 = E2;
+      } else {
+        E1 = E1 * E2 / (E2 + ENew);
+      }
+      t2N = tNew;
+      E2 = ENew;
+    }
+    if (!found || (t1 < t2 ? tNew < tbest : tNew > tbest)) {
+      found = true;
+      tbest = tNew;
+      ibest = k + 1;
+      stop = P.ev_stop[k] != 0;
+#pragma unroll
+      for (int i = 0; i < NY; i++) ybest[i] = yNew[i];
+    }
+  }
+  if (!found) return false;
+  const int n = *out.nev;
+  if (n < out.ecap) {
+    out.te[n] = tbest;
+    out.ie[n] = ibest;
+#pragma unroll
+    for (int i = 0; i < NY; i++) out.ye[n * NY + i] = ybest[i];
+  }
+  *out.nev = n + 1;
+  if (stop) {
+    T.t = tbest;
+#pragma unroll
+    for (int i = 0; i < NY; i++) T.y[i] = ybest[i];
+  }
+  return stop;
+}
+
 template <int NY, int S, int SM>
 JB_HD void dense_output(Traj<NY, SM>& T, const DenseOut& out) {
   using Tab = RadauTab<S>;
+  if (out.mode != 3) {   // OutFlag 1 / 2: the computed points (+ refine - 1 interpolated ones before each)
+    for (int r = 1; r < out.refine; r++) {
+      const double tint = T.t + T.h_old * ((double)r / (double)out.refine) - T.h_old;
+      if (T.nout < out.cap) {
+        out.tout[T.nout] = tint;
+        ntrprad<NY, S, SM>(T, tint, out.yout + (long long)T.nout * NY);
+      }
+      T.nout += 1;
+    }
+    if (T.nout < out.cap) {
+      out.tout[T.nout] = T.t;
+#pragma unroll
+      for (int i = 0; i < NY; i++) out.yout[(long long)T.nout * NY + i] = T.y[i];
+    }
+    T.nout += 1;
+    return;
+  }
   while (T.nout < out.ntspan) {
     const double tn = out.tspan[T.nout];
     if (T.PosNeg * (T.t - tn) < 0) break;
@@ -234,6 +355,7 @@ JB_HD void dense_output(Traj<NY, SM>& T, const DenseOut& out) {
 // radau.m:1267-1269: the last recorded point is overwritten with the final (t, y)
 template <int NY, int SM>
 JB_HD void dense_finish(const Traj<NY, SM>& T, const DenseOut& out) {
+  if (out.mode != 3 && T.nout > out.cap) return;   // the last computed point was not stored
   if (T.nout >= 1) {
     out.tout[T.nout - 1] = T.t;
 #pragma unroll
@@ -680,6 +802,16 @@ JB_HD bool attempt_step_hi(Traj<NY, SM>& T, const RadauParams& P, double* Jac, b
       T.erracc = fmax(1.0e-2, err);
     }
     if (sens) sens_step<Ham, NY, S, SM>(T, P, zl, rscal, *sens);
+    double E1v[4];
+    const double t_ev1 = T.t;
+    if (out && P.ev_K > 0) {   // event values at the start of the step (the reference keeps them from its previous call)
+      for (int k = 0; k < P.ev_K; k++) {
+        double e = -P.ev_b[k];
+#pragma unroll
+        for (int i = 0; i < NY; i++) e = fma(P.ev_A[k][i], T.y[i], e);
+        E1v[k] = e;
+      }
+    }
     T.h_old = T.h;
     T.t = T.t + T.h;
     double z[S * NY];
@@ -704,6 +836,7 @@ JB_HD bool attempt_step_hi(Traj<NY, SM>& T, const RadauParams& P, double* Jac, b
 #pragma unroll
         for (int i = 0; i < NY; i++) T.cont[(k - 1) * NY + i] = (T.cont[(k - 1) * NY + i] - T.cont[(k - 2) * NY + i]) * Fact;
       }
+    if (out && P.ev_K > 0 && locate_events<NY, S, SM>(T, P, *out, E1v, t_ev1)) return true;   // terminal event (radau.m:1110-1121)
     if (out) dense_output<NY, S, SM>(T, *out);  // radau.m:1150-1168
     T.NeedNewJac = true;
     if (T.Last) {  // radau.m:1193-1197
@@ -1029,6 +1162,16 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool
       T.erracc = fmax(1.0e-2, err);
     }
     if (sens) sens_step<Ham, NY, S, SM>(T, P, z, rscal, *sens);   // before y moves: needs y_n, z, the LU of this step
+    double E1v[4];
+    const double t_ev1 = T.t;
+    if (out && P.ev_K > 0) {   // event values at the start of the step (the reference keeps them from its previous call)
+      for (int k = 0; k < P.ev_K; k++) {
+        double e = -P.ev_b[k];
+#pragma unroll
+        for (int i = 0; i < NY; i++) e = fma(P.ev_A[k][i], T.y[i], e);
+        E1v[k] = e;
+      }
+    }
     T.h_old = T.h;
     T.t = T.t + T.h;
 #pragma unroll
@@ -1050,6 +1193,7 @@ JB_HD bool attempt_step(Traj<NY, SM>& T, const RadauParams& P, double* Jac, bool
 #pragma unroll
         for (int i = 0; i < NY; i++) T.cont[(k - 1) * NY + i] = (T.cont[(k - 1) * NY + i] - T.cont[(k - 2) * NY + i]) * Fact;
       }
+    if (out && P.ev_K > 0 && locate_events<NY, S, SM>(T, P, *out, E1v, t_ev1)) return true;   // terminal event (radau.m:1110-1121)
     if (out) dense_output<NY, S, SM>(T, *out);  // radau.m:1150-1168
     T.NeedNewJac = true;
     if (T.Last) {  // radau.m:1193-1197

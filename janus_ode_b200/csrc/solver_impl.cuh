@@ -83,10 +83,29 @@ __device__ __forceinline__ void store_row(double* __restrict__ dst, long long m,
 // optional dense output (tspan with interior points): device arrays, nullptr when unused
 struct DenseArgs {
   int ntspan;      // columns of tspan (>= 2)
-  double* tout;    // [M, ntspan] or nullptr
-  double* yout;    // [M, ntspan, NY]
+  double* tout;    // [M, ntspan] (mode 3) / [M, cap] (mode 1, 2) or nullptr
+  double* yout;    // [M, ntspan or cap, NY]
   int* nout;       // [M]
+  int mode = 3, cap = 0, refine = 1;   // radau_core.cuh: DenseOut
+  double* te = nullptr;   // [M, ecap] located events (ev_K > 0)
+  double* ye = nullptr;   // [M, ecap, NY]
+  int* ie = nullptr;      // [M, ecap]
+  int* nev = nullptr;     // [M], zeroed by the host
+  int ecap = 0;
 };
+template <int NY>
+__device__ __forceinline__ DenseOut make_dout(const DenseArgs& d, const double* tspan, long long m) {
+  const long long rows = d.mode == 3 ? d.ntspan : d.cap;
+  DenseOut o{tspan ? tspan + m * d.ntspan : nullptr, d.ntspan, d.tout ? d.tout + m * rows : nullptr,
+             d.yout ? d.yout + m * rows * NY : nullptr};
+  o.mode = d.mode; o.cap = d.cap; o.refine = d.refine;
+  o.te = d.te ? d.te + m * d.ecap : nullptr;
+  o.ye = d.ye ? d.ye + m * (long long)d.ecap * NY : nullptr;
+  o.ie = d.ie ? d.ie + m * d.ecap : nullptr;
+  o.nev = d.nev ? d.nev + m : nullptr;
+  o.ecap = d.ecap;
+  return o;
+}
 
 template <class Ham, int SM, bool VAR, bool DENSE>
 __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : (SM <= 3 ? JB_MINB_FIXED : 2)) radau_kernel(const __grid_constant__ RadauParams P,
@@ -113,8 +132,7 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : (SM <= 3 ? JB_
       traj_init<Ham, NY, SM>(T, P, y, __ldg(tspan + m * nts), __ldg(tspan + m * nts + nts - 1));
       have = true;
     }
-    const DenseOut dout{tspan + m * nts, nts, DENSE ? dense.tout + m * nts : nullptr,
-                        DENSE ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut dout = DENSE ? make_dout<NY>(dense, tspan, m) : DenseOut{nullptr, 2, nullptr, nullptr};
     const DenseOut* dp = DENSE ? &dout : nullptr;   // compile-time: no cost when no dense output is requested
     bool done;
     if (T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep)) {
@@ -264,8 +282,7 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     double t0;
     bool head_done;
     unpark<NY, S>(st[m], T, t0, head_done);
-    const DenseOut dout{tspan + m * nts, nts, DENSE ? dense.tout + m * nts : nullptr,
-                        DENSE ? dense.yout + m * nts * NY : nullptr};
+    const DenseOut dout = DENSE ? make_dout<NY>(dense, tspan, m) : DenseOut{nullptr, 2, nullptr, nullptr};
     const DenseOut* dp = DENSE ? &dout : nullptr;
     bool stepped = false;
     const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp, stop_on_accept != 0, &stepped);
@@ -438,10 +455,10 @@ template <class Ham, int SM, bool VAR>
 int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out,
                         double* h_out, int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
 #ifdef JB_SLIM   // slim plugin builds (large user Hamiltonians): no dense-output kernel variants
-  if (dense.tout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
+  if (dense.nout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
   auto kern = radau_kernel<Ham, SM, VAR, false>;
 #else
-  auto kern = dense.tout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
+  auto kern = dense.nout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
 #endif
   int bps = 0;
   const size_t smem = lc_smem_bytes<Ham::NV, SM>(JB_THREADS);
@@ -488,10 +505,10 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
     JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
   }
 #ifdef JB_SLIM
-  if (dense.tout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
+  if (dense.nout) return fail(JB200_ENOTSUP, "this plugin was built without dense-output kernels");
   auto kern = epoch_kernel<Ham, S, VAR, false>;
 #else
-  auto kern = dense.tout ? epoch_kernel<Ham, S, VAR, true> : epoch_kernel<Ham, S, VAR, false>;
+  auto kern = dense.nout ? epoch_kernel<Ham, S, VAR, true> : epoch_kernel<Ham, S, VAR, false>;
 #endif
   constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;

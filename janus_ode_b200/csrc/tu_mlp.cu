@@ -463,6 +463,8 @@ static State bind(Work* C, long long M, const double* tspan, const DenseArgs& de
 
 static int solve(Handle* H, const double* y0, const double* tspan, long long M, double* y_out, double* t_out, double* h_out,
                  int* res, long long* stats, int* nstg, long long* work, const DenseArgs& dense, cudaStream_t st) {
+  if (dense.nout && (dense.mode != 3 || dense.nev))
+    return fail(JB200_ENOTSUP, "the MLP-Hamiltonian path records output at tspan points only (no per-step output, no events)");
   Work* C = &ctx_of(H)->w;
   int rc = ensure(H, *C, M, true);
   if (rc) return rc;

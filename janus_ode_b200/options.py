@@ -11,13 +11,42 @@ STAT_NAMES = ("FcnNbr", "JacNbr", "DecompNbr", "SolveNbr", "StepNbr", "AccptNbr"
               "NewtRejNbr")
 
 
+class LinearEvents:
+    """EventsFcn of the accelerated path (reference: EventFnType, src/cpp/radaute.hpp:44-47 -- value, isterminal,
+    direction; zero location src/matlab/radau.m:1494-1618): K <= 4 event functions E_k(t, y) = A[k] . y - b[k].
+    stop[k]: terminal event; slope[k]: +1 only rising zeros, -1 only falling, 0 both.  A kernel cannot call back into
+    Python, so the family is closed; a component crossing a level (the reference's examples) is A = unit vector."""
+
+    def __init__(self, A, b, stop=None, slope=None):
+        A = np.atleast_2d(np.asarray(_to_np(A), dtype=np.float64))
+        K = A.shape[0]
+        if not 1 <= K <= 4:
+            raise ValueError("1 to 4 event functions")
+        self.A = tuple(map(tuple, A.tolist()))
+        self.b = tuple(np.broadcast_to(np.asarray(_to_np(b), dtype=np.float64), (K,)).tolist())
+        self.stop = tuple(int(bool(v)) for v in np.broadcast_to(np.asarray(0 if stop is None else stop), (K,)))
+        self.slope = tuple(int(np.sign(v)) for v in np.broadcast_to(np.asarray(0 if slope is None else slope), (K,)))
+
+    def _key(self):
+        return (self.A, self.b, self.stop, self.slope)
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __eq__(self, other):
+        return isinstance(other, LinearEvents) and self._key() == other._key()
+
+
 @dataclass
 class OptionsTe:
     """Same field names and defaults as the reference's OptionsTe (solver knobs).
 
     MaxStep is accepted and ignored exactly like the reference (hmax = tfinal - t0,
-    src/cpp/radaute_impl.hpp:227).  MassFcn / EventsFcn / OutputFcn / Complex / Refine > 1 are
+    src/cpp/radaute_impl.hpp:227).  EventsFcn takes a LinearEvents object.  MassFcn / OutputFcn / Complex are
     outside the accelerated path and raise if set.
+    OutputCapacity > 0 (two-column tspan): the computed points are recorded like the reference's OutFlag 1 (Refine = 1)
+    / OutFlag 2 (Refine > 1) into tout [M,cap], yout [M,cap,Ny], nout [M] -- the reference grows these buffers step by
+    step for the whole batch; here the caller sizes them (nout > cap: too small).  EventsCapacity: events kept per row.
     """
     RelTol: object = 1.0e-3
     AbsTol: object = 1.0e-6
@@ -48,13 +77,19 @@ class OptionsTe:
     MassFcn: object = None
     EventsFcn: object = None
     OutputFcn: object = None
+    OutputCapacity: int = 0
+    EventsCapacity: int = 8
 
     def to_c(self, ny: int, costate_sign: int) -> jb200_opts:
-        for nm in ("MassFcn", "EventsFcn", "OutputFcn"):
+        for nm in ("MassFcn", "OutputFcn"):
             if getattr(self, nm) is not None:
                 raise NotImplementedError(f"{nm} is outside the accelerated Radau path")
-        if self.Complex or self.Refine > 1:
-            raise NotImplementedError("Complex=true tables / Refine>1 are outside the accelerated path")
+        if self.EventsFcn is not None and not isinstance(self.EventsFcn, LinearEvents):
+            raise NotImplementedError("EventsFcn must be a janus_ode_b200.LinearEvents (a kernel cannot call a Python function)")
+        if self.Complex:
+            raise NotImplementedError("Complex=true tables are outside the accelerated path")
+        if self.Refine < 1:
+            raise ValueError("Refine must be >= 1")
         o = jb200_opts()
         rt = np.atleast_1d(np.asarray(_to_np(self.RelTol), dtype=np.float64)).ravel()
         at = np.atleast_1d(np.asarray(_to_np(self.AbsTol), dtype=np.float64)).ravel()

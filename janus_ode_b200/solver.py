@@ -67,6 +67,16 @@ class _Handle:
         _lib.check(L.jb200_create(C.byref(o), ham.ham_id, par, len(ham.params), C.byref(h)), L)
         self.h = h
         self.L = L
+        ev = options.EventsFcn
+        if ev is not None:
+            K = len(ev.b)
+            A = (C.c_double * (K * ham.Ny))(*[v for row in ev.A for v in row])
+            if len(ev.A[0]) != ham.Ny:
+                raise ValueError(f"LinearEvents.A must be [K,{ham.Ny}]")
+            b = (C.c_double * K)(*ev.b)
+            stop = (C.c_int32 * K)(*ev.stop)
+            slope = (C.c_int32 * K)(*ev.slope)
+            _lib.check(L.jb200_set_events(h, K, A, b, stop, slope), L)
 
     def close(self):
         if self.h:
@@ -176,6 +186,7 @@ class RadauTe:
         self.tspan = tspan.contiguous()
         self.ntspan = tspan.shape[1]
         self.tout = self.yout = self.nout = None
+        self.te = self.ye = self.ie = self.nev = None     # located events (teout, yeout, ieout of radau.m:1110-1121)
         self.y = y0.contiguous()          # never written: solve() replaces it with the result tensor
         self.t = t0.clone()
         self.h = torch.zeros(self.M, dtype=torch.float64, device=self.device)
@@ -198,6 +209,10 @@ class RadauTe:
         stats = torch.empty(M, 8, dtype=torch.int32 if host else torch.int64, **kw)
         nstg = torch.empty(M, dtype=torch.int32, **kw)
         work = None if (host and not self.want_work) else torch.empty(M, dtype=torch.int64, **kw)
+        if self.ntspan > 2 and (self.options.EventsFcn is not None or self.options.OutputCapacity > 0 or self.options.Refine > 1):
+            raise NotImplementedError("events / per-step output need a two-column tspan (OutFlag 3 records the tspan points only)")
+        if not self.y.is_cuda and (self.options.EventsFcn is not None or self.options.OutputCapacity > 0 or self.options.Refine > 1):
+            raise NotImplementedError("events / per-step output run on CUDA tensors")
         if self.y.is_cuda and self.ntspan > 2:
             # output at the requested tspan points (radau.m OutFlag 3): tout, yout, nout like the reference
             self.tout = torch.zeros(M, self.ntspan, dtype=torch.float64, **kw)
@@ -208,6 +223,21 @@ class RadauTe:
                                                      _ptr(t_out), _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg),
                                                      _ptr(work), _ptr(self.tout), _ptr(self.yout), _ptr(self.nout),
                                                      _stream_ptr(dev)))
+        elif self.y.is_cuda and (self.options.OutputCapacity > 0 or self.options.EventsFcn is not None or self.options.Refine > 1):
+            # every computed point (OutFlag 1 / 2) and / or located events
+            cap, ecap = int(self.options.OutputCapacity), int(self.options.EventsCapacity)
+            self.tout = torch.zeros(M, max(cap, 1), dtype=torch.float64, **kw)
+            self.yout = torch.zeros(M, max(cap, 1), ny, dtype=torch.float64, **kw)
+            self.nout = torch.zeros(M, dtype=torch.int32, **kw)
+            self.te = torch.zeros(M, max(ecap, 1), dtype=torch.float64, **kw)
+            self.ye = torch.zeros(M, max(ecap, 1), ny, dtype=torch.float64, **kw)
+            self.ie = torch.zeros(M, max(ecap, 1), dtype=torch.int32, **kw)
+            self.nev = torch.zeros(M, dtype=torch.int32, **kw)
+            with torch.cuda.device(dev):
+                _lib.check_h(H, H.L.jb200_solve_out(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out), _ptr(h_out),
+                                                   _ptr(res), _ptr(stats), _ptr(nstg), _ptr(work), int(self.options.Refine), cap,
+                                                   _ptr(self.tout), _ptr(self.yout), _ptr(self.nout), ecap, _ptr(self.te),
+                                                   _ptr(self.ye), _ptr(self.ie), _ptr(self.nev), _stream_ptr(dev)))
         elif self.y.is_cuda:
             with torch.cuda.device(dev):
                 _lib.check_h(H, H.L.jb200_solve(H.h, _ptr(self.y), _ptr(self.tspan), M, _ptr(y_out), _ptr(t_out),

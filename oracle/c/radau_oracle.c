@@ -793,7 +793,80 @@ static int g_quirks = 1;
 static double *g_plog = 0; static int g_plog_cap = 0, g_plog_n = 0;
 /* one trajectory; returns res code */
 /* dense output rows of one trajectory (radau.m:1150-1168 OutFlag 3); tsp == NULL: final state only */
-typedef struct { const double *tsp; int ntspan; double *tout, *yout; int nout; } dense_t;
+typedef struct {
+  const double *tsp; int ntspan; double *tout, *yout; int nout;
+  /* mode 3: tspan points (default, mode == 0 means 3); 1 / 2: every accepted step (+ refine - 1 interpolated points),
+   * radaute_impl.hpp:1166-1183 / radau.m:1122-1143, stored while nout < cap */
+  int mode, cap, refine;
+  /* events E_k = A[k].y - b[k] (radau.m:1110-1121, EventZeroFcn :1494-1618) */
+  int ev_K; const double *ev_A, *ev_b; const int *ev_stop, *ev_slope;
+  double *te, *ye; int *ie; int nev, ecap;
+} dense_t;
+
+static double eps_of(double t) {
+  double a = fabs(t);
+  if (a < 2.2250738585072014e-308) return 4.9406564584124654e-324;
+  int e; frexp(a, &e);            /* a = f 2^e, f in [0.5,1)  ->  spacing 2^(e-53) */
+  return ldexp(1.0, e - 53);
+}
+
+static void ntrp(int n, int s, const tab_t *tb, double cont[SMAX][NYMAX], double t, const double *y, double h_old,
+                 double tn, double *out) {
+  const double sfr = (tn - t) / h_old;
+  for (int i = 0; i < n; i++) {
+    double yi = (sfr - (tb->C[0] - 1.0)) * cont[s - 1][i];
+    for (int q = 1; q < s; q++) yi = (sfr - (tb->C[q] - 1.0)) * (yi + cont[s - 1 - q][i]);
+    out[i] = yi + y[i];
+  }
+}
+
+/* EventZeroFcn (radau.m:1494-1618) after an accepted step from (t1, E1v) to (t, y); returns 1 on a terminal event */
+static int locate_events(int n, int s, const tab_t *tb, double cont[SMAX][NYMAX], dense_t *dn, const double *E1v, double t1,
+                         double *t_io, double *y, double h_old) {
+  const double t2 = *t_io;
+  double tol = 65536.0 * fmax(EPS, fmax(eps_of(t2), eps_of(t1)));
+  tol = fmin(tol, fabs(t2 - t1));
+  int found = 0, stop = 0, ibest = 0;
+  double tbest = 0.0, ybest[NYMAX];
+  for (int k = 0; k < dn->ev_K; k++) {
+    double E2 = -dn->ev_b[k];
+    for (int i = 0; i < n; i++) E2 = FMA(dn->ev_A[k * n + i], y[i], E2);
+    double t1N = t1, t2N = t2, E1 = E1v[k];
+    const double p12 = (E2 - E1) / (t2N - t1N);
+    if (!(E1 * E2 < 0 && p12 * dn->ev_slope[k] >= 0)) continue;
+    double tNew = t2N, ENew = E2, yNew[NYMAX];
+    for (int i = 0; i < n; i++) yNew[i] = y[i];
+    for (int iter = 1; iter < 50; iter++) {
+      const int tRel = fabs(t1N - t2N) * tol < fmax(fabs(t1N), fabs(t2N));
+      const int tAbs = fabs(t1N - t2N) < tol;
+      if ((fabs(ENew) < tol && tRel && tAbs) || fabs(ENew) == 0.0) break;
+      if (fabs(E1) < 200.0 * tol || fabs(E2) < 200.0 * tol) tNew = 0.5 * (t1N + t2N);
+      else tNew = tNew + (-ENew / (E2 - E1) * (t2N - t1N));
+      ntrp(n, s, tb, cont, t2, y, h_old, tNew, yNew);
+      ENew = -dn->ev_b[k];
+      for (int i = 0; i < n; i++) ENew = FMA(dn->ev_A[k * n + i], yNew[i], ENew);
+      if (ENew * E2 < 0) { t1N = t2N; E1 = E2; }
+      else E1 = E1 * E2 / (E2 + ENew);
+      t2N = tNew;
+      E2 = ENew;
+    }
+    if (!found || (t1 < t2 ? tNew < tbest : tNew > tbest)) {
+      found = 1; tbest = tNew; ibest = k + 1; stop = dn->ev_stop[k] != 0;
+      for (int i = 0; i < n; i++) ybest[i] = yNew[i];
+    }
+  }
+  if (!found) return 0;
+  if (dn->nev < dn->ecap) {
+    dn->te[dn->nev] = tbest; dn->ie[dn->nev] = ibest;
+    for (int i = 0; i < n; i++) dn->ye[dn->nev * n + i] = ybest[i];
+  }
+  dn->nev += 1;
+  if (stop) {
+    *t_io = tbest;
+    for (int i = 0; i < n; i++) y[i] = ybest[i];
+  }
+  return stop;
+}
 
 static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, double tfinal, const double *y0,
                      double *y_out, double *t_out, double *h_out, long long *st, int *nstg_out,
@@ -1032,6 +1105,14 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
         hacc = h;
         erracc = fmax(1.0e-2, err);
       }
+      double E1v[4] = {0, 0, 0, 0};
+      const double t_ev1 = t;
+      if (dn && dn->ev_K > 0)
+        for (int k = 0; k < dn->ev_K; k++) {
+          double e = -dn->ev_b[k];
+          for (int i = 0; i < n; i++) e = FMA(dn->ev_A[k * n + i], y[i], e);
+          E1v[k] = e;
+        }
       h_old = h;
       t = t + h;
       for (int i = 0; i < n; i++) y[i] = y[i] + z[s - 1][i];
@@ -1046,7 +1127,22 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
           for (int i = 0; i < n; i++) cont[k - 1][i] = (cont[k - 1][i] - cont[k - 2][i]) * Fact;
         }
       if (rec_h && rec_n && *rec_n < rec_cap) rec_h[(*rec_n)++] = h;
-      if (dn && dn->tsp) { /* radau.m:1150-1168 + ntrprad :1291-1308 (h_old = the step just taken) */
+      if (dn && dn->ev_K > 0 && locate_events(n, s, &tb, cont, dn, E1v, t_ev1, &t, y, h_old)) { finished = 1; break; }
+      if (dn && (dn->mode == 1 || dn->mode == 2)) {
+        for (int r = 1; r < dn->refine; r++) {
+          const double tint = t + h_old * ((double)r / (double)dn->refine) - h_old;
+          if (dn->nout < dn->cap) {
+            dn->tout[dn->nout] = tint;
+            ntrp(n, s, &tb, cont, t, y, h_old, tint, dn->yout + dn->nout * n);
+          }
+          dn->nout += 1;
+        }
+        if (dn->nout < dn->cap) {
+          dn->tout[dn->nout] = t;
+          for (int i = 0; i < n; i++) dn->yout[dn->nout * n + i] = y[i];
+        }
+        dn->nout += 1;
+      } else if (dn && dn->tsp) { /* radau.m:1150-1168 + ntrprad :1291-1308 (h_old = the step just taken) */
         while (dn->nout < dn->ntspan) {
           const double tn = dn->tsp[dn->nout];
           if (PosNeg * (t - tn) < 0) break;
@@ -1103,7 +1199,12 @@ static int radau_one(const problem_t *pb, const oracle_opts *op, double t0, doub
   /* radau.m:1287: only the step cap ends the loop early (t + (tfinal - t) may round below tfinal) */
   if (res == 0 && !finished && PosNeg * t < PosNeg * tfinal) res = 3;
 done:
-  if (dn && dn->tsp && dn->nout >= 1) { /* radau.m:1267-1269 */
+  if (dn && (dn->mode == 1 || dn->mode == 2)) {
+    if (dn->nout >= 1 && dn->nout <= dn->cap) {
+      dn->tout[dn->nout - 1] = t;
+      for (int i = 0; i < n; i++) dn->yout[(dn->nout - 1) * n + i] = y[i];
+    }
+  } else if (dn && dn->tsp && dn->nout >= 1) { /* radau.m:1267-1269 */
     dn->tout[dn->nout - 1] = t;
     for (int i = 0; i < n; i++) dn->yout[(dn->nout - 1) * n + i] = y[i];
   }
@@ -1153,11 +1254,40 @@ int oracle_radau_solve_dense(int problem, const double *par, int sign, int Ny, l
 #pragma omp parallel for schedule(dynamic, 16)
   for (long long m = 0; m < M; m++) {
     dense_t dn;
+    memset(&dn, 0, sizeof dn);
     dn.tsp = tspan + m * ntspan; dn.ntspan = ntspan; dn.tout = tout + m * ntspan;
     dn.yout = yout + m * ntspan * Ny; dn.nout = 0;
     res[m] = radau_one(&pb, op, tspan[m * ntspan], tspan[m * ntspan + ntspan - 1], y0 + m * Ny, y_out + m * Ny,
                        t_out + m, h_out + m, stats + 8 * m, nstg + m, NULL, 0, NULL, &dn);
     nout[m] = dn.nout;
+  }
+  return 0;
+}
+
+/* output at every accepted step (OutFlag 1 / 2) and located events; tspan [M][2] */
+int oracle_radau_solve_out(int problem, const double *par, int sign, int Ny, long long M, const double *y0,
+                           const double *tspan, const oracle_opts *op, double *y_out, double *t_out, double *h_out, int *res,
+                           long long *stats, int *nstg, int refine, int cap, double *tout, double *yout, int *nout,
+                           int ev_K, const double *ev_A, const double *ev_b, const int *ev_stop, const int *ev_slope,
+                           int ecap, double *te, double *ye, int *ie, int *nev, int nthreads) {
+  problem_t pb;
+  pb.id = problem; pb.Ny = Ny; pb.sign = (double)sign; pb.par = par;
+  if (Ny > NYMAX) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+  for (long long m = 0; m < M; m++) {
+    dense_t dn;
+    memset(&dn, 0, sizeof dn);
+    dn.mode = refine > 1 ? 2 : 1; dn.cap = cap; dn.refine = refine;
+    dn.tout = tout + m * cap; dn.yout = yout + m * cap * Ny;
+    dn.ev_K = ev_K; dn.ev_A = ev_A; dn.ev_b = ev_b; dn.ev_stop = ev_stop; dn.ev_slope = ev_slope;
+    dn.te = te + m * ecap; dn.ye = ye + m * ecap * Ny; dn.ie = ie + m * ecap; dn.ecap = ecap;
+    res[m] = radau_one(&pb, op, tspan[2 * m], tspan[2 * m + 1], y0 + m * Ny, y_out + m * Ny, t_out + m, h_out + m,
+                       stats + 8 * m, nstg + m, NULL, 0, NULL, &dn);
+    nout[m] = dn.nout;
+    nev[m] = dn.nev;
   }
   return 0;
 }

@@ -150,6 +150,48 @@ def solve_dense(problem, par, sign, y0, tspan, opts, nthreads=0, arith="referenc
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, tout=tout, yout=yout, nout=nout)
 
 
+def solve_out(problem, par, sign, y0, tspan, opts, cap, refine=1, events=None, ecap=8, nthreads=0, arith="reference"):
+    """every accepted step recorded (OutFlag 1 / 2) + located events.  events = (A [K,Ny], b [K], stop [K], slope [K])."""
+    set_arith(arith)
+    set_quirks(getattr(opts, "RadauTeQuirks", 1))
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, Ny = y0.shape
+    y = np.empty_like(y0)
+    t = np.empty(M)
+    h = np.empty(M)
+    res = np.empty(M, dtype=np.int32)
+    stats = np.empty((M, 8), dtype=np.int64)
+    nstg = np.empty(M, dtype=np.int32)
+    tout = np.zeros((M, max(cap, 1)))
+    yout = np.zeros((M, max(cap, 1), Ny))
+    nout = np.zeros(M, dtype=np.int32)
+    K = 0
+    A = b = np.zeros(1)
+    stop = slope = np.zeros(1, dtype=np.int32)
+    if events is not None:
+        A = np.ascontiguousarray(events[0], dtype=np.float64).reshape(-1, Ny)
+        K = A.shape[0]
+        b = np.ascontiguousarray(events[1], dtype=np.float64).reshape(K)
+        stop = np.ascontiguousarray(events[2], dtype=np.int32).reshape(K)
+        slope = np.ascontiguousarray(events[3], dtype=np.int32).reshape(K)
+    te = np.zeros((M, max(ecap, 1)))
+    ye = np.zeros((M, max(ecap, 1), Ny))
+    ie = np.zeros((M, max(ecap, 1)), dtype=np.int32)
+    nev = np.zeros(M, dtype=np.int32)
+    o = _opts(opts, Ny)
+    ip = C.POINTER(C.c_int)
+    rc = lib().oracle_radau_solve_out(
+        C.c_int(PB[problem]), _dp(par), C.c_int(sign), C.c_int(Ny), C.c_longlong(M), _dp(y0), _dp(tspan), C.byref(o), _dp(y),
+        _dp(t), _dp(h), res.ctypes.data_as(ip), stats.ctypes.data_as(C.POINTER(C.c_longlong)), nstg.ctypes.data_as(ip),
+        C.c_int(refine), C.c_int(cap), _dp(tout), _dp(yout), nout.ctypes.data_as(ip), C.c_int(K), _dp(A), _dp(b),
+        stop.ctypes.data_as(ip), slope.ctypes.data_as(ip), C.c_int(ecap), _dp(te), _dp(ye), ie.ctypes.data_as(ip),
+        nev.ctypes.data_as(ip), C.c_int(nthreads))
+    assert rc == 0
+    return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, tout=tout, yout=yout, nout=nout, te=te, ye=ye, ie=ie, nev=nev)
+
+
 def trace(problem, par, sign, y0, tspan, opts, cap=100000, arith="reference"):
     """one trajectory, with the accepted step sizes."""
     set_arith(arith)

@@ -301,4 +301,55 @@ int ref_radau_trace(int ham, double par, int sign, int adaptor, int Ny, const do
   return 0;
 }
 
+// One trajectory with the reference's own record of the computed points: RadauTe's OutFlag 1 buffers tout [1,nout],
+// yout [1,nout,Ny], nout (radaute_impl.hpp:288-296, 1166-1183), copied out up to `cap` points.
+int ref_radau_steps(int ham, double par, int sign, int adaptor, int Ny, const double* y0, const double* tspan,
+                    double rtol, double atol, double h0, int nbrstg, int minstg, int maxstg, int max_steps,
+                    int cap, double* tout, double* yout, int* nout, double* y, int64_t* stats) {
+  Problem P{ham, par, sign, adaptor};
+  torch::set_num_threads(1);
+  std::cerr.setstate(std::ios_base::failbit);
+  std::cout.flush(); fflush(stdout); fflush(stderr);
+  const int fd_out = dup(1), fd_err = dup(2), fd_null = open("/dev/null", O_WRONLY);
+  dup2(fd_null, 1); dup2(fd_null, 2);
+  int rc = 0;
+  try {
+    janus::OdeFnType f = [P](const Tensor&, const Tensor& yy, const Tensor&) {
+      return P.adaptor ? adaptor_dyns(P, yy) : closed_dyns(P, yy);
+    };
+    janus::JacFnType jf = [P](const Tensor&, const Tensor& yy, const Tensor&) {
+      return P.adaptor ? adaptor_jac(P, yy) : closed_jac(P, yy);
+    };
+    auto yt = torch::from_blob((void*)y0, {1, Ny}, torch::kFloat64).clone();
+    auto ts = torch::from_blob((void*)tspan, {1, 2}, torch::kFloat64).clone();
+    janus::OptionsTe op;
+    op.RelTol = torch::tensor({rtol}, torch::kFloat64);
+    op.AbsTol = torch::tensor({atol}, torch::kFloat64);
+    op.InitialStep = torch::tensor({h0}, torch::kFloat64);
+    op.NbrStg = torch::tensor(nbrstg, torch::kInt64);
+    op.MinNbrStg = torch::tensor(minstg, torch::kInt64);
+    op.MaxNbrStg = torch::tensor(maxstg, torch::kInt64);
+    op.MaxNbrStep = max_steps;
+    auto params = torch::empty({0}, torch::kFloat64);
+    janus::RadauTe r(f, jf, ts, yt, op, params);
+    r.solve();
+    const int n = (int)r.nout.reshape({-1})[0].item<int64_t>();
+    *nout = n;
+    auto to = r.tout.to(torch::kFloat64).contiguous();
+    auto yo = r.yout.to(torch::kFloat64).contiguous();
+    for (int k = 0; k < n && k < cap; ++k) {
+      tout[k] = to[0][k].item<double>();
+      for (int i = 0; i < Ny; ++i) yout[k * Ny + i] = yo[0][k][i].item<double>();
+    }
+    std::memcpy(y, r.y.contiguous().data_ptr<double>(), sizeof(double) * Ny);
+    const Tensor* st[8] = {&r.stats.FcnNbr, &r.stats.JacNbr, &r.stats.DecompNbr, &r.stats.SolveNbr,
+                           &r.stats.StepNbr, &r.stats.AccptNbr, &r.stats.StepRejNbr, &r.stats.NewtRejNbr};
+    for (int c = 0; c < 8; ++c) stats[c] = st[c]->defined() ? st[c]->to(torch::kInt64).reshape({-1})[0].item<int64_t>() : -1;
+  } catch (const std::exception& e) { g_err = e.what(); rc = -3; }
+  std::cout.flush(); fflush(stdout); fflush(stderr);
+  dup2(fd_out, 1); dup2(fd_err, 2); close(fd_out); close(fd_err); close(fd_null);
+  std::cerr.clear();
+  return rc;
+}
+
 }  // extern "C"

@@ -113,6 +113,25 @@ def trace(problem, par, sign, y0, tspan, rtol, atol, h0=1e-2, stages=(3, 3, 7), 
     return dict(log=log[:n.value].copy(), y=y, stats=stats)
 
 
+def steps(problem, par, sign, y0, tspan, rtol, atol, h0=1e-2, stages=(3, 3, 7), max_steps=100000, adaptor=False, cap=4096):
+    """one trajectory: the reference's own OutFlag-1 record (tout [n], yout [n,Ny]) of every accepted step."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64).reshape(-1)
+    tspan = np.ascontiguousarray(tspan, dtype=np.float64).reshape(2)
+    Ny = y0.shape[0]
+    tout = np.zeros(cap)
+    yout = np.zeros((cap, Ny))
+    n = C.c_int()
+    y = np.empty(Ny)
+    stats = np.empty(8, dtype=np.int64)
+    rc = lib().ref_radau_steps(
+        C.c_int(PB[problem]), C.c_double(par), C.c_int(sign), C.c_int(int(adaptor)), C.c_int(Ny), _dp(y0), _dp(tspan),
+        C.c_double(rtol), C.c_double(atol), C.c_double(h0), C.c_int(stages[0]), C.c_int(stages[1]), C.c_int(stages[2]),
+        C.c_int(max_steps), C.c_int(cap), _dp(tout), _dp(yout), C.byref(n), _dp(y), _ip(stats))
+    assert rc == 0, rc
+    k = min(n.value, cap)
+    return dict(tout=tout[:k].copy(), yout=yout[:k].copy(), nout=n.value, y=y, stats=stats)
+
+
 def solve(problem, par, sign, y0, tspan, rtol, atol, h0=1e-2, stages=(3, 3, 7), max_steps=100000,
           adaptor=False, batch=False, procs=1):
     """Run janus::RadauTe on every row (one solver object per row unless batch=True).

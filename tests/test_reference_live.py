@@ -86,7 +86,9 @@ def test_variable_order_gap_was_the_gustafsson_gate():
 @pytest.mark.parametrize("base,other,lo,hi", [("c2_vdp_s3", "c2_vdp_s3_ulp", 0.95, 0.998),
                                                ("c2_vdp_s3", "c2_vdp_s3_adaptor", 0.95, 1.0),
                                                ("c2_vdp_var", "c2_vdp_var_ulp", 0.88, 0.99),
-                                               ("c2_vdp_var", "c2_vdp_var_adaptor", 0.88, 1.0)])
+                                               ("c2_vdp_var", "c2_vdp_var_adaptor", 0.88, 1.0),
+                                               ("c1_harmonic_s3", "c1_harmonic_s3_ulp", 0.3, 0.9),
+                                               ("c3_pmp_bang_var", "c3_pmp_bang_var_ulp", 0.0, 0.5)])
 def test_reference_roundoff_floor(base, other, lo, hi):
     """the live reference against itself after a 1-ulp change of x1(0) / with its own autograd adaptor: equal
     accepted-step counts on well under 99.9 % of the rows -- the bar no reimplementation can clear."""
