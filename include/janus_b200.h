@@ -62,6 +62,7 @@ extern "C" {
 #define JB200_RES_STEP_TOO_SMALL 1
 #define JB200_RES_NAN 2
 #define JB200_RES_MAX_STEPS 3
+#define JB200_RES_SENS_UNCONVERGED 4   /* jb200_solve_sens only: the state converged, a sensitivity iteration did not */
 
 /* stats columns: StatsTe, src/cpp/radaute.hpp:98-108 (MATLAB counting rules, radau.m) */
 enum {
@@ -146,6 +147,15 @@ int jb200_solve_out(void* handle, const double* y0, const double* tspan, int64_t
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out,
                      double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                      int64_t* work);
+
+/* evalDynsDual / evalJacDual (+ U twins) and the eight third-order ladders ppppppH ... pxpxpxH of the reference
+ * (src/cpp/janus_ode_common.hpp:2075-2158, :2302-2416, :787-2072) from ONE third-order jet of H per trajectory.
+ * y [M,Ny] -> f [M,Ny], J [M,Ny,Ny] (as jb200_eval_dyns / _jac), T [M,Ny,Ny,Ny] with T[r][c][k] = d J[r][c] / d y_k
+ * (the third-order blocks in y-order, costate sign on the pdot rows; may be NULL); with ND dual directions
+ * yd [M,Ny,ND] (the `.d` of the reference's TensorDual y): fd [M,Ny,ND] = J yd, Jd [M,Ny,Ny,ND] = T yd (the `.d` parts
+ * of the returned TensorDual / TensorMatDual; may be NULL).  Device pointers.                                   */
+int jb200_eval_jac_dual(void* handle, const double* y, const double* yd, int ND, int64_t M, double* f, double* J,
+                        double* T, double* fd, double* Jd, void* stream);
 
 /* SEULEX (semi-implicit extrapolation) behind the same boundary: one call = one `SeulexT.step(htry, dyns, state)` of the
  * reference's Python stepper for every trajectory (src/python/seulext.py:158-581, dy_batch :593-667; state fields

@@ -283,6 +283,8 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
   const HamOps* ops = ham_ops(ham_id);
   if (!ops) return fail(JB200_ENOTSUP, "unknown Hamiltonian id (not compiled into this library)");
   const int ny = ops->ny;
+  if (!ops->create && ops->npar > JB200_MAX_HAM_PARAMS)   // parameters live in RadauParams::ham_par[8] (device-resident ones: create)
+    return fail(JB200_EINVAL, "this Hamiltonian declares more than JB200_MAX_HAM_PARAMS parameters");
   if (n_ham_params < ops->npar || (n_ham_params > 0 && !ham_params))
     return fail(JB200_EINVAL, "Hamiltonian needs " + std::to_string(ops->npar) + " parameters");
   int rc = validate(o, ny);
@@ -569,6 +571,19 @@ int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, do
   const dp::StepArgs a{(long long)M, (long long)(norm_M > 0 ? norm_M : M), atol, rtol, x, y, dydx, errold, hnext, aliased, htry, hdid,
                        (int*)nrej};
   return ops->dopri(H, a, (cudaStream_t)stream);
+}
+
+int jb200_eval_jac_dual(void* handle, const double* y, const double* yd, int ND, int64_t M, double* f, double* J, double* T,
+                        double* fd, double* Jd, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  if (!y || !f || !J) return fail(JB200_EINVAL, "null buffer");
+  if (ND < 0 || (ND > 0 && !yd)) return fail(JB200_EINVAL, "ND directions need yd");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->jac_dual) return fail(JB200_ENOTSUP, "third-order evaluation is available for the thread-resident Hamiltonians only");
+  const JacDualArgs a{(long long)M, ND, y, ND > 0 ? yd : nullptr, f, J, T, ND > 0 ? fd : nullptr, ND > 0 ? Jd : nullptr};
+  return ops->jac_dual(H, a, (cudaStream_t)stream);
 }
 
 int jb200_seulex_step(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry, double* y,

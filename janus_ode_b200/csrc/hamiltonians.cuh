@@ -19,6 +19,7 @@
 #include <utility>
 
 #include "dual.cuh"
+#include "dual3.cuh"
 
 namespace jb {
 
@@ -105,6 +106,55 @@ JB_HD auto ham_eval1(const double* y, const double* par, double u, std::index_se
 template <class Ham, size_t... I>
 JB_HD auto ham_eval2(const double* y, const double* par, double u, std::index_sequence<I...>) {
   return Ham::H(seed2<Ham::NV, (int)I>(y[I])..., par, u);
+}
+
+template <class Ham, size_t... I>
+JB_HD auto ham_eval3(const double* y, const double* par, double u, std::index_sequence<I...>) {
+  return Ham::H(seed3<Ham::NV, (int)I>(y[I])..., par, u);
+}
+
+// value + dual part of the dynamics and of the Jacobian (evalDynsDual / evalJacDual and their U twins,
+// /root/reference/src/cpp/janus_ode_common.hpp:2075-2158, :2302-2416), from ONE third-order jet of H:
+//   f [NV], J [NV*NV] as ham_dyns / ham_jac;  T [NV*NV*NV]: T[r][c][k] = d J[r][c] / d y_k  (the reference's eight
+//   third-order blocks pxpppxH ... assembled in y-order, sigma on the pdot rows);
+//   with ND directions yd [NV][ND]:  fd [NV][ND] = J yd,  Jd [NV][NV][ND] = T yd   (the .d parts of the reference's
+//   TensorDual / TensorMatDual results).  Any of T, fd, Jd may be nullptr.
+template <class Ham>
+JB_HD void ham_jac_dual(const double* y, const double* par, double sign, const double* yd, int ND, double* f, double* J,
+                        double* T, double* fd, double* Jd) {
+  constexpr int N = Ham::N, NV = Ham::NV;
+  const double u = Ham::HAS_CONTROL ? Ham::control(y, par) : 0.0;
+  const D3<NV> r = ham_eval3<Ham>(y, par, u, std::make_index_sequence<NV>{});
+  for (int rr = 0; rr < NV; rr++) {
+    const int vi = (rr < N) ? (N + rr) : (rr - N);
+    const double sg = (rr < N) ? sign : 1.0;
+    f[rr] = sg * r.g[vi];
+    for (int c = 0; c < NV; c++) {
+      J[rr * NV + c] = sg * r.h[hsorted(NV, vi, c)];
+      for (int k = 0; k < NV; k++) {
+        const double t = sg * r.t[tsorted(NV, vi, c, k)];
+        if (T) T[(rr * NV + c) * NV + k] = t;
+      }
+    }
+  }
+  if (!yd) return;
+  for (int rr = 0; rr < NV; rr++) {
+    const int vi = (rr < N) ? (N + rr) : (rr - N);
+    const double sg = (rr < N) ? sign : 1.0;
+    for (int l = 0; l < ND; l++) {
+      if (fd) {
+        double s = 0.0;
+        for (int k = 0; k < NV; k++) s = fma(J[rr * NV + k], yd[k * ND + l], s);
+        fd[rr * ND + l] = s;
+      }
+      if (Jd)
+        for (int c = 0; c < NV; c++) {
+          double s = 0.0;
+          for (int k = 0; k < NV; k++) s = fma(sg * r.t[tsorted(NV, vi, c, k)], yd[k * ND + l], s);
+          Jd[(rr * NV + c) * ND + l] = s;
+        }
+    }
+  }
 }
 
 // f = [sigma dH/dx ; dH/dp]

@@ -379,6 +379,8 @@ struct Sens {
   static constexpr int ND = NY;
   double S[NY * NY];   // S[i * ND + d] = d y_i / d (direction d)
   int iters;           // sensitivity Newton iterations spent (all directions, all steps)
+  int unconverged;     // (direction, step) pairs whose iteration hit its cap or produced a non-finite increment: S is then
+                       // not to be trusted -- reported to the caller instead of silently propagated
 };
 
 template <class Ham, int NY, int S, int SM>
@@ -475,7 +477,12 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
       nrm = ::sqrt(nrm) * P.inv_sqrt_sn[si];
       sn.iters += 1;
       T.work += W_newt(S, NY, 2 * NY * NY);
+      if (bad(nrm)) {
+        sn.unconverged += 1;
+        break;
+      }
       if (!(nrm > tol)) break;
+      if (it == Nit - 1) sn.unconverged += 1;
     }
 #pragma unroll
     for (int i = 0; i < NY; i++) sn.S[i * ND + d] = Sd[i] + Zs[(S - 1) * NY + i];

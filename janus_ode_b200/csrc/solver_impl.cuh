@@ -330,6 +330,29 @@ __global__ void jac_kernel(const __grid_constant__ RadauParams P, const double* 
   }
 }
 
+// evalDynsDual / evalJacDual: value + dual parts of the dynamics and the Jacobian from one third-order jet of H
+struct JacDualArgs {
+  long long M;
+  int ND;                // dual directions (0: none)
+  const double* y;       // [M,NY]
+  const double* yd;      // [M,NY,ND] or nullptr
+  double *f, *J;         // [M,NY], [M,NY,NY]
+  double *T, *fd, *Jd;   // [M,NY,NY,NY], [M,NY,ND], [M,NY,NY,ND]   (each may be nullptr)
+};
+template <class Ham>
+__global__ void __launch_bounds__(128) jac_dual_kernel(const __grid_constant__ RadauParams P, const JacDualArgs a) {
+  constexpr int NY = Ham::NV;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
+    double y[NY], f[NY], J[NY * NY];
+    load_row<NY>(a.y, m, y);
+    ham_jac_dual<Ham>(y, P.ham_par, P.sign, a.yd ? a.yd + m * NY * a.ND : nullptr, a.ND, f, J,
+                      a.T ? a.T + m * NY * NY * NY : nullptr, a.fd ? a.fd + m * NY * a.ND : nullptr,
+                      a.Jd ? a.Jd + m * NY * NY * a.ND : nullptr);
+    store_row<NY>(a.f, m, f);
+#pragma unroll
+    for (int r = 0; r < NY; r++) store_row<NY>(a.J, m * NY + r, &J[r * NY]);
+  }
+}
 // ------------------------------------------------------------------ host side
 // parked trajectories + the index lists of the epoch scheme; owned by a handle (solve) or by an
 // incremental-stepping state (jb200_state_*)
@@ -843,6 +866,18 @@ int launch_seulex(Handle* H, const sx::StepArgs& a, cudaStream_t st) {
 #endif
 }
 
+template <class Ham>
+int launch_jac_dual(Handle* H, const JacDualArgs& a, cudaStream_t st) {
+#ifdef JB_SLIM
+  return fail(JB200_ENOTSUP, "this plugin was built without the third-order kernel");
+#else
+  const long long blocks = std::max<long long>(1, std::min<long long>((a.M + 127) / 128, (long long)H->sm_count * 16));
+  jac_dual_kernel<Ham><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  JB_CUDA(cudaGetLastError());
+  return 0;
+#endif
+}
+
 // forward sensitivities (radau_core.cuh: Sens / sens_step): one thread = one trajectory with its Ny x Ny
 // sensitivity matrix, all stage counts inside one kernel (order selection at run time)
 template <class Ham, int SM, bool VAR>
@@ -862,6 +897,7 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
     traj_init<Ham, NY, SM>(T, P, y, tspan[2 * m], tspan[2 * m + 1]);
     Sens<NY> sn;
     sn.iters = 0;
+    sn.unconverged = 0;
 #pragma unroll
     for (int k = 0; k < NY * NY; k++) sn.S[k] = S0 ? S0[m * NY * NY + k] : ((k / NY == k % NY) ? 1.0 : 0.0);
     integrate<Ham, NY, SM, VAR>(T, P, nullptr, &sn);
@@ -876,6 +912,7 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
     if (nstg) nstg[m] = T.NbrStg;
     if (work) work[m] = T.work;
     if (sens_iters) sens_iters[m] = sn.iters;
+    if (T.res == 0 && sn.unconverged > 0) res[m] = JB200_RES_SENS_UNCONVERGED;   // the state is fine, S is not
   }
 }
 template <class Ham>
@@ -925,13 +962,14 @@ struct HamOps {
               long long*, int*, long long*, int*, cudaStream_t) = nullptr;   // solve with forward sensitivities
   void (*st_free)(EpochWS&) = nullptr;   // optional: the state of the incremental protocol is not a plain EpochWS
   int (*seulex)(Handle*, const sx::StepArgs&, cudaStream_t) = nullptr;   // SEULEX step (thread-resident Hamiltonians)
+  int (*jac_dual)(Handle*, const JacDualArgs&, cudaStream_t) = nullptr;  // evalDynsDual / evalJacDual / third-order ladders
 };
 template <class Ham>
 HamOps make_ops() {
   return HamOps{Ham::NV,           Ham::NPAR,         &dispatch_order<Ham>, &launch_dyns<Ham>,
                 &launch_jac<Ham>, &ws_init<Ham>,     &state_step<Ham>,     &state_read<Ham>,
                 nullptr,          nullptr,           &launch_dopri<Ham>,   &launch_sens<Ham>,
-                nullptr,          &launch_seulex<Ham>};
+                nullptr,          &launch_seulex<Ham>, &launch_jac_dual<Ham>};
 }
 
 }  // namespace jb

@@ -136,6 +136,41 @@ class HamiltonianSystem:
         return out
 
 
+def _hs_third(self, y):
+    """T [M,Ny,Ny,Ny], T[m,r,c,k] = d J[r][c] / d y_k: the reference's third-order ladders in y-order."""
+    return self.jacobian_dual(None, y)[2]
+
+
+def _hs_jacobian_dual(self, t, y, yd=None):
+    """evalJacDual (+ evalDynsDual) of the reference, src/cpp/janus_ode_common.hpp:2075-2158, 2302-2416:
+    y [M,Ny], yd [M,Ny,D] (dual part of the TensorDual state) -> (f, J, T, fd, Jd): dynamics [M,Ny], Jacobian
+    [M,Ny,Ny], third-order tensor [M,Ny,Ny,Ny], and their dual parts fd [M,Ny,D] = J yd, Jd [M,Ny,Ny,D] = T yd
+    (None without yd).  One third-order jet of H per trajectory instead of N + N^2 backward passes per block."""
+    y = self._check(y)
+    M, ny = y.shape
+    dev = y.device
+    f = torch.empty(M, ny, dtype=torch.float64, device=dev)
+    J = torch.empty(M, ny, ny, dtype=torch.float64, device=dev)
+    T = torch.empty(M, ny, ny, ny, dtype=torch.float64, device=dev)
+    fd = Jd = None
+    D = 0
+    if yd is not None:
+        if yd.dim() != 3 or yd.shape[:2] != (M, ny) or yd.dtype != torch.float64 or not yd.is_cuda:
+            raise ValueError(f"yd must be a CUDA float64 tensor [M,{ny},D]")
+        yd = yd.contiguous()
+        D = yd.shape[2]
+        fd = torch.empty(M, ny, D, dtype=torch.float64, device=dev)
+        Jd = torch.empty(M, ny, ny, D, dtype=torch.float64, device=dev)
+    H = self._h()
+    _lib.check_h(H, H.L.jb200_eval_jac_dual(H.h, _ptr(y), _ptr(yd), D, M, _ptr(f), _ptr(J), _ptr(T), _ptr(fd), _ptr(Jd),
+                                            _stream_ptr(dev)))
+    return f, J, T, fd, Jd
+
+
+HamiltonianSystem.jacobian_dual = _hs_jacobian_dual
+HamiltonianSystem.third_derivatives = _hs_third
+
+
 class RadauTe:
     """Batched variable-order Radau IIA for a Hamiltonian system, one adaptive step per trajectory.
 

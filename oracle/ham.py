@@ -114,6 +114,84 @@ def eval_jac(y, W, H, u=None, costate_sign=+1, gate_constant_rows=False):
     return torch.cat([jac1, jac2], dim=1)
 
 
+def _third_block(x, p, W, H, u, a, b, c, gate):
+    """[m,i,j,k] = d/dc_k d/db_j d/da_i H, a, b, c in {'x','p'}: the ladder `p{c}p{b}p{a}H` of janus_ode_common.hpp:787-2072.
+    Like there, the pure blocks track gradients of their own class only (ppppppH :795-796, pxpxpxH :959-960) and a row is
+    stored only if its autograd result requires grad (quirk Q1, e.g. :851-856) when gate=True."""
+    need_x = "x" in (a, b, c)
+    need_p = "p" in (a, b, c)
+    xt = x.clone().detach().requires_grad_(need_x)
+    pt = p.clone().detach().requires_grad_(need_p)
+    Hv = _call(H, xt, pt, u, W)
+    var = {"x": xt, "p": pt}
+    g1 = _safe_jac(Hv, var[a])
+    M, N = x.shape
+    out = torch.zeros(M, N, N, N, dtype=x.dtype)
+    for i in range(N):
+        gi = _safe_jac(g1[:, i], var[b])
+        for j in range(N):
+            gij = _safe_jac(gi[:, j], var[c])
+            if gate and not gij.requires_grad:
+                continue
+            out[:, i, j, :] = gij.detach()
+    return out
+
+
+def eval_jac_dual_ladders(y, yd, W, H, u=None, costate_sign=+1, gate=True):
+    """evalDynsDual + evalJacDual assembled block by block from the eight third-order ladders exactly like
+    janus_ode_common.hpp:2302-2416 (gate=True reproduces the reference, which DROPS third-order rows that are constant:
+    e.g. d^3H/dx^3 of the PMP Hamiltonian, constant in x, comes back zero).  Returns (f, fd, J, Jd)."""
+    N = y.shape[1] // 2
+    p, x = y[:, :N], y[:, N:]
+    pd, xd = yd[:, :N], yd[:, N:]
+    f = eval_dyns(y, W, H, u, costate_sign)
+    J = eval_jac(y, W, H, u, costate_sign)
+    fd = torch.einsum("mrk,mkl->mrl", J, yd)
+
+    def dual(a, b):   # J block rows d/da_i, cols d/db_j: its dual part
+        return (torch.einsum("mijk,mkl->mijl", _third_block(x, p, W, H, u, a, b, "x", gate), xd) +
+                torch.einsum("mijk,mkl->mijl", _third_block(x, p, W, H, u, a, b, "p", gate), pd))
+    jac1 = costate_sign * torch.cat([dual("x", "p"), dual("x", "x")], dim=2)
+    jac2 = torch.cat([dual("p", "p"), dual("p", "x")], dim=2)
+    return f, fd, J, torch.cat([jac1, jac2], dim=1)
+
+
+def eval_jac_dual(y, yd, W, H, u=None, costate_sign=+1):
+    """evalDynsDual + evalJacDual (+ U twins), janus_ode_common.hpp:2075-2158, :2302-2416, restated with the same autograd
+    engine: returns (f [M,Ny], fd [M,Ny,D], J [M,Ny,Ny], Jd [M,Ny,Ny,D], T [M,Ny,Ny,Ny]) with T[m,r,c,k] = d J[r][c] / d y_k
+    (the eight third-order ladders :787-2072 assembled in y-order), fd = J yd, Jd = T yd.  Mathematically correct
+    derivatives (structurally-zero blocks are zero; the reference's safe_jac throws there under libtorch 2.x)."""
+    M, Ny = y.shape
+    N = Ny // 2
+    yt = y.clone().detach().requires_grad_(True)
+
+    def dyn(yy):
+        p, x = yy[:, :N], yy[:, N:]
+        Hv = _call(H, x, p, u, W)
+        g = torch.autograd.grad(Hv.sum(), yy, create_graph=True)[0]
+        return torch.cat([costate_sign * g[:, N:], g[:, :N]], dim=1)
+
+    f = dyn(yt)
+    J = torch.zeros(M, Ny, Ny, dtype=y.dtype)
+    T = torch.zeros(M, Ny, Ny, Ny, dtype=y.dtype)
+    for r in range(Ny):
+        if not f[:, r].requires_grad:
+            continue
+        Jr = torch.autograd.grad(f[:, r].sum(), yt, create_graph=True, allow_unused=True)[0]
+        if Jr is None:
+            continue
+        J[:, r] = Jr.detach()
+        for c in range(Ny):
+            if not Jr[:, c].requires_grad:
+                continue
+            Trc = torch.autograd.grad(Jr[:, c].sum(), yt, retain_graph=True, allow_unused=True)[0]
+            if Trc is not None:
+                T[:, r, c] = Trc.detach()
+    fd = torch.einsum("mrk,mkl->mrl", J, yd)
+    Jd = torch.einsum("mrck,mkl->mrcl", T, yd)
+    return f.detach(), fd, J, Jd, T
+
+
 # ---------------------------------------------------------------------------------------
 # Hamiltonians of the benchmark configs (SURVEY.md 8d) in torch form (for autograd) --
 # written in forms for which quirk Q1 and the mathematically correct Hessian agree.

@@ -352,4 +352,41 @@ int ref_radau_steps(int ham, double par, int sign, int adaptor, int Ny, const do
   return rc;
 }
 
+// evalDynsDual / evalJacDual (+ U twins) of the reference (janus_ode_common.hpp:2075-2158, :2302-2416) on the fixture
+// Hamiltonians: y [M,Ny], yd [M,Ny,D] -> f [M,Ny], fd [M,Ny,D], J [M,Ny,Ny], Jd [M,Ny,Ny,D].  These run the eight
+// third-order autograd ladders (:787-2072).
+int ref_eval_dual(int ham, double par, int64_t M, int Ny, int D, const double* y, const double* yd, double* f, double* fd,
+                  double* J, double* Jd) {
+  using HFn = std::function<Tensor(const Tensor&, const Tensor&, double)>;
+  using HuFn = std::function<Tensor(const Tensor&, const Tensor&, const Tensor&, double)>;
+  int rc = 0;
+  try {
+    auto yt = torch::from_blob((void*)y, {M, Ny}, torch::kFloat64).clone();
+    auto ydt = torch::from_blob((void*)yd, {M, Ny, D}, torch::kFloat64).clone();
+    janus::TensorDual yy(yt, ydt);
+    janus::TensorDual fr;
+    janus::TensorMatDual Jr;
+    if (ham == HAM_HARMONIC) {
+      HFn H = [](const Tensor& x, const Tensor& p, double w) { return H_harmonic(x, p, w, +1); };
+      fr = janus::evalDynsDual<double>(yy, par, H);
+      Jr = janus::evalJacDual<double>(yy, par, H);
+    } else if (ham == HAM_VDP) {
+      HFn H = [](const Tensor& x, const Tensor& p, double mu) { return H_vdp(x, p, mu); };
+      fr = janus::evalDynsDual<double>(yy, par, H);
+      Jr = janus::evalJacDual<double>(yy, par, H);
+    } else {
+      HuFn Hu = [](const Tensor& x, const Tensor& p, const Tensor& u, double W) { return Hu_pmp(x, p, u, W); };
+      auto u = control(yt, ham, par);
+      fr = janus::evalDynsUDual<double>(yy, u, par, Hu);
+      Jr = janus::evalJacDualU<double>(yy, u, par, Hu);
+    }
+    auto cp = [](double* dst, const Tensor& src) {
+      auto c = src.detach().to(torch::kFloat64).contiguous();
+      std::memcpy(dst, c.data_ptr<double>(), sizeof(double) * c.numel());
+    };
+    cp(f, fr.r); cp(fd, fr.d); cp(J, Jr.r); cp(Jd, Jr.d);
+  } catch (const std::exception& e) { g_err = e.what(); rc = -3; }
+  return rc;
+}
+
 }  // extern "C"

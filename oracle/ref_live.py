@@ -70,6 +70,21 @@ def evaluate(problem, par, sign, y, adaptor=True):
     return f, J
 
 
+def evaluate_dual(problem, par, y, yd):
+    """evalDynsDual / evalJacDual (+U) of the live reference: (f [M,Ny], fd [M,Ny,D], J [M,Ny,Ny], Jd [M,Ny,Ny,D])."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    yd = np.ascontiguousarray(yd, dtype=np.float64)
+    M, Ny = y.shape
+    D = yd.shape[2]
+    f, fd, J, Jd = np.empty((M, Ny)), np.empty((M, Ny, D)), np.empty((M, Ny, Ny)), np.empty((M, Ny, Ny, D))
+    rc = lib().ref_eval_dual(C.c_int(PB[problem]), C.c_double(par), C.c_int64(M), C.c_int(Ny), C.c_int(D), _dp(y), _dp(yd),
+                             _dp(f), _dp(fd), _dp(J), _dp(Jd))
+    if rc != 0:
+        lib().ref_last_error.restype = C.c_char_p
+        raise RuntimeError(lib().ref_last_error().decode()[:400])
+    return f, fd, J, Jd
+
+
 def _solve_chunk(args):
     (problem, par, sign, adaptor, batch, y0, tspan, rtol, atol, h0, stg, max_steps) = args
     import time

@@ -182,6 +182,7 @@ static void run_sens(const RadauParams& P, const double* y0, const double* tspan
     traj_init<Ham, NY, 7>(T, P, y0 + m * NY, tspan[2 * m], tspan[2 * m + 1]);
     Sens<NY> sn;
     sn.iters = 0;
+    sn.unconverged = 0;
     for (int k = 0; k < NY * NY; k++) sn.S[k] = (k / NY == k % NY) ? 1.0 : 0.0;
     integrate<Ham, NY, 7, true>(T, P, nullptr, &sn);
     for (int i = 0; i < NY; i++) y_out[m * NY + i] = T.y[i];
