@@ -356,6 +356,7 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         r, _, _ = one_device_step()
     peak = jb.fp64_peak_tflops(20000) if rank == 0 else None       # FP64 DFMA probe (roofline denominator)
+    dmma = jb.fp64_dmma_tflops(20000) if rank == 0 else None       # FP64 tensor-core (mma.sync f64) probe, for the MLP GEMMs
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     evs, launches = [], 0
@@ -468,6 +469,7 @@ def run_ours(a):
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": _traffic(a),
                             "peak_source": "DFMA probe jb200_fp64_peak on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                            "fp64_dmma_probe_tflops": dmma,
                             "algorithmic_flops_per_launch": flops / world,
                             "flops_per_accepted_step": flops / max(acc, 1),
                             "hbm_bytes_per_launch": h2d + d2h,

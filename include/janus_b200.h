@@ -232,6 +232,9 @@ int jb200_det_pow(const double* x, const double* y, int64_t n, double* out, void
 
 /* FP64 roofline probe: runs a dependent-chain-free DFMA kernel and returns achieved TFLOP/s */
 int jb200_fp64_peak(int iters, double* tflops);
+/* FP64 tensor-core (DMMA, mma.sync m8n8k4 f64) throughput probe in TFLOP/s, next to the DFMA probe: tcgen05 has no
+ * f64 kind, so this is the only tensor-core rate an fp64 GEMM could reach on sm_100a.                         */
+int jb200_dmma_peak(int iters, double* tflops);
 
 const char* jb200_last_error(void);
 const char* jb200_version(void);

@@ -84,6 +84,31 @@ __global__ void dfma_kernel(int iters, double seed, double* sink) {
   if (s == 123.456) sink[0] = s;
 }
 
+// FP64 tensor-core probe: independent chains of mma.sync.aligned.m8n8k4.f64 (DMMA) per warp, 512 FLOP each.
+// tcgen05 has no f64 kind, so DMMA is the only tensor-core route for an fp64 GEMM on sm_100a; this measures whether it
+// beats the DFMA pipe (it would decide the inner loops of the MLP-Hamiltonian GEMMs, csrc/mlp_kernels.cuh).
+__global__ void dmma_kernel(int iters, double seed, double* sink) {
+  constexpr int NCH = 8;
+  double c0[NCH], c1[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; k++) {
+    c0[k] = seed + k * 1e-3;
+    c1[k] = seed - k * 1e-3;
+  }
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < NCH; k++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[k]), "+d"(c1[k])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < NCH; k++) s += c0[k] + c1[k];
+  if (s == 123.456) sink[0] = s;
+}
+
 // ------------------------------------------------------------------ Hamiltonian table
 #if defined(JB_USER_HAM_HEADER)
 static const HamOps jb_ops_user = make_ops<UserHam>();
@@ -320,6 +345,7 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
   if (const char* fe = std::getenv("JB200_FIXED_EPOCHS")) H->fixed_epochs = atoi(fe) != 0;
   if (const char* ps = std::getenv("JB200_PRESORT")) H->presort = atoi(ps) != 0;
   if (const char* eh = std::getenv("JB200_EPOCH_HORDER")) H->epoch_horder = atoi(eh);
+  H->P.key_fine = H->epoch_horder == 3;
   *handle = H;
   return 0;
 }
@@ -623,10 +649,13 @@ int jb200_lu_solve(int n, int64_t M, const double* Are, const double* Aim, const
     case 2: return launch_lu<2>(M, Are, Aim, bre, bim, xre, xim, st);
     case 3: return launch_lu<3>(M, Are, Aim, bre, bim, xre, xim, st);
     case 4: return launch_lu<4>(M, Are, Aim, bre, bim, xre, xim, st);
+    case 5: return launch_lu<5>(M, Are, Aim, bre, bim, xre, xim, st);
+    case 6: return launch_lu<6>(M, Are, Aim, bre, bim, xre, xim, st);
+    case 8: return launch_lu<8>(M, Are, Aim, bre, bim, xre, xim, st);   // Ny = 8: user Hamiltonians with N = 4
 #if !defined(JB_USER_HAM_HEADER) && !defined(JB_FAST_BUILD)
     case 16: return lu16_solve_launch(M, Are, Aim, bre, bim, xre, xim, st);   // 16 lanes per system (csrc/lu16.cuh)
 #endif
-    default: return fail(JB200_ENOTSUP, "jb200_lu_solve: n must be 2, 3, 4 or 16");
+    default: return fail(JB200_ENOTSUP, "jb200_lu_solve: n must be 2, 3, 4, 5, 6, 8 or 16");
   }
 }
 
@@ -658,6 +687,36 @@ int jb200_fp64_peak(int iters, double* tflops) {
     float ms = 0;
     JB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  *tflops = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+int jb200_dmma_peak(int iters, double* tflops) {
+  if (!tflops || iters < 1) return fail(JB200_EINVAL, "bad argument");
+  int dev = 0, sms = 148;
+  JB_CUDA(cudaGetDevice(&dev));
+  JB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  JB_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  JB_CUDA(cudaEventCreate(&e0));
+  JB_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256;
+  dmma_kernel<<<blocks, threads>>>(iters, 1.0, sink);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    JB_CUDA(cudaEventRecord(e0));
+    dmma_kernel<<<blocks, threads>>>(iters, 1.0, sink);
+    JB_CUDA(cudaEventRecord(e1));
+    JB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    JB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 512.0 * 8.0 * (double)iters * (double)blocks * (double)(threads / 32);   // 2*8*8*4 per warp-level mma
     best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
   *tflops = best;

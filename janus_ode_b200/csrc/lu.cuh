@@ -369,10 +369,15 @@ __device__ __forceinline__ void zluc_solve(int block, double* br, double* bi) {
 }
 #endif
 
-// which steppers run rolled (all complex blocks in shared memory, z / w in local memory): 5 and 7 stages on the device
+// which steppers run rolled (all complex blocks in shared memory, z / w in local memory): 5 and 7 stages on the device.
+// OPT-IN (-DJB_ROLL_HI).  Measured (round 2, config 2, 2^20 rows): the rolled 5/7-stage kernels are 39 % smaller and 7 %
+// faster on the epochs they dominate when every epoch is synchronised (89.6 vs 91.0 ms per solve), but in the real
+// pipeline -- the three per-order kernels of an epoch overlapping on three streams -- the solve is 5 % SLOWER (95.5 vs
+// 90.2 ms, bench.py, twice): their larger shared-memory footprint (99 instead of 80 words per thread) no longer lets a
+// 3-stage CTA share an SM with two 7-stage CTAs, which costs more overlap than the smaller code gains.
 template <int N, int S>
 struct HiRoll {
-#if defined(JB_LC_SMEM) && !defined(JB_NO_ROLL_HI)
+#if defined(JB_LC_SMEM) && defined(JB_ROLL_HI)
   static constexpr bool on = (S >= 5) && (N <= 4);
 #else
   static constexpr bool on = false;

@@ -46,6 +46,7 @@ struct RadauParams {
   double ham_par[8];
   // event functions E_k(t, y) = ev_A[k] . y - ev_b[k]  (EventsFcn of the reference: value, isterminal, direction --
   // src/cpp/radaute.hpp:44-47; zero location src/matlab/radau.m:1494-1618).  ev_K = 0: none.
+  int key_fine;              // scheduling only: epoch lists also ordered by the current step size (solver_impl.cuh regime_key)
   int ev_K, ev_stop[4], ev_slope[4];
   double ev_A[4][NYMAX], ev_b[4];
 };

@@ -165,13 +165,21 @@ __global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : (SM <= 3 ? JB_
 // of Newton iterations, same accept/reject pattern), so warps built from key-sorted lists diverge
 // less.  0 = finished.  Purely a scheduling hint: results do not depend on it.
 constexpr int NKEYS = 4 * 256;
-__device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int Newt) {
+// `fine` (RadauParams::key_fine, epoch_horder 3): 5 more bits = the leading mantissa bits of |h| appended below the
+// 10-bit key, so that within a regime the rows are ordered by their CURRENT step size -- an ordering that follows the
+// state of the integration instead of H(y0), for batches whose initial states are not a one-parameter family.
+constexpr int KEY_FINE_BITS = 5;
+__device__ __forceinline__ unsigned short regime_key(int NbrStg, double h, int Newt, int fine = 0) {
   const int k = (NbrStg - 1) >> 1;
-  int e = (int)((__double_as_longlong(h) >> 52) & 0x7ff) - 1023 + 44;   // |h| in [2^-44, 2^20) -> 0..63
+  const long long hb = __double_as_longlong(h);
+  int e = (int)((hb >> 52) & 0x7ff) - 1023 + 44;   // |h| in [2^-44, 2^20) -> 0..63
   e = e < 0 ? 0 : (e > 63 ? 63 : e);
   int nw = Newt - 1;
   nw = nw < 0 ? 0 : (nw > 3 ? 3 : nw);
-  return (unsigned short)(1 + k * 256 + e * 4 + nw);
+  const int coarse = k * 256 + e * 4 + nw;
+  if (!fine) return (unsigned short)(1 + coarse);
+  const int mant = (int)((hb >> (52 - KEY_FINE_BITS)) & ((1 << KEY_FINE_BITS) - 1));
+  return (unsigned short)(1 + ((coarse << KEY_FINE_BITS) | mant));
 }
 
 template <class Ham>
@@ -186,17 +194,17 @@ __global__ void init_kernel(const __grid_constant__ RadauParams P, const double*
     Traj<NY, 7> T;
     traj_init<Ham, NY, 7>(T, P, y, t0, __ldg(tspan + m * nts + nts - 1));
     park<NY, 7>(T, t0, false, false, st[m]);
-    tag[m] = regime_key(T.NbrStg, T.h, T.Newt);
+    tag[m] = regime_key(T.NbrStg, T.h, T.Newt, P.key_fine);
   }
 }
 
-static __global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ counts) {
+static __global__ void hist_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ counts, int shift) {
   __shared__ int sh[NKEYS];
   for (int i = threadIdx.x; i < NKEYS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     const int t = tag[m];
-    if (t) atomicAdd(&sh[t - 1], 1);
+    if (t) atomicAdd(&sh[(t - 1) >> shift], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NKEYS; i += blockDim.x)
@@ -207,11 +215,11 @@ static __global__ void hist_kernel(const unsigned short* __restrict__ tag, long 
 // Warp-aggregated: lanes holding the same key are matched and claim their slots with ONE atomic
 // (the live keys are few, so per-lane atomics serialise on a handful of addresses).
 static __global__ void scatter_kernel(const unsigned short* __restrict__ tag, long long M, int* __restrict__ cursor,
-                               int* __restrict__ list) {
+                               int* __restrict__ list, int shift) {
   const int lane = threadIdx.x & 31;
   for (long long base = blockIdx.x * (long long)blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
     const long long m = base + threadIdx.x;
-    const int t = (m < M) ? (int)tag[m] : 0;
+    const int t = (m < M && tag[m]) ? (((int)tag[m] - 1) >> shift) + 1 : 0;
     const unsigned peers = __match_any_sync(0xffffffffu, t);
     if (t) {
       const int leader = __ffs(peers) - 1;
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
     bool stepped = false;
     const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, dp, stop_on_accept != 0, &stepped);
     park<NY, S>(T, t0, head_done, fin, st[m]);
-    tag[m] = (fin || stepped) ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt);
+    tag[m] = (fin || stepped) ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt, P.key_fine);
     if (fin && y_out) {
       store_row<NY>(y_out, m, T.y);
       t_out[m] = T.t;
@@ -458,6 +466,10 @@ int build_order(Handle* H, EpochWS& ws, const double* y0, long long M, cudaStrea
   return 0;
 }
 
+static __global__ void iota_kernel(int* __restrict__ idx, long long M) {
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) idx[m] = (int)m;
+}
+
 static __global__ void gather_tag_kernel(const unsigned short* __restrict__ tag, const int* __restrict__ order, long long M,
                                          unsigned short* __restrict__ keys) {
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x)
@@ -467,10 +479,10 @@ static __global__ void gather_tag_kernel(const unsigned short* __restrict__ tag,
 // live rows of one stage-count bucket, taken in H-order (stable selection)
 struct StagePred {
   const unsigned short* tag;
-  int k;
+  int k, shift;
   __device__ __forceinline__ bool operator()(const int& idx) const {
     const int t = tag[idx];
-    return t != 0 && ((t - 1) >> 8) == k;
+    return t != 0 && ((t - 1) >> (8 + shift)) == k;
   }
 };
 
@@ -571,7 +583,7 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     for (int k = 0; k < 4; k++) {
       size_t bytes = ws.sort_tmp_bytes;
       JB_CUDA(cub::DeviceSelect::If(ws.sort_tmp, bytes, ws.order, ws.lists + (size_t)k * M, ws.nsel + k, (int)M,
-                                    StagePred{ws.tag, k}, st));
+                                    StagePred{ws.tag, k, H->P.key_fine ? KEY_FINE_BITS : 0}, st));
     }
     int cnt[4];
     JB_CUDA(cudaMemcpyAsync(cnt, ws.nsel, sizeof cnt, cudaMemcpyDeviceToHost, st));
@@ -586,7 +598,9 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     if (!rc && cnt[0]) rc = launch_epoch<Ham, 1, VAR>(H, ws, 0, 0, cnt[0], max_passes, stop_on_accept, o, tspan, dense, st, used);
     if (rc) return rc;
   }
-  const bool key_then_h = H->epoch_horder == 2 && ws.have_order;   // regime key major, H(y0) minor (stable radix sort)
+  // regime key major; minor: H(y0) (stable radix sort of the H-ordered rows, horder 2) or the current step size (the fine
+  // key bits, rows taken in index order, horder 3)
+  const bool key_then_h = (H->epoch_horder == 2 || H->epoch_horder == 3) && ws.have_order;
   static const bool trace = std::getenv("JB200_EPOCH_TRACE") != nullptr;   // developer aid: per-epoch timeline on stderr
   cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
   if (trace) for (auto& e : tev) cudaEventCreate(&e);
@@ -594,7 +608,8 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     if (trace) cudaEventRecord(tev[0], st);
     JB_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
-    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts);
+    const int shift = H->P.key_fine ? KEY_FINE_BITS : 0;
+    hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, shift);
     JB_CUDA(cudaGetLastError());
     JB_CUDA(cudaMemcpyAsync(hist.data(), ws.counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
@@ -614,12 +629,12 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
       void* tmp = (void*)(kout + M + (M & 1) + 8);
       size_t bytes = ws.sort_tmp_bytes - (size_t)((char*)tmp - (char*)ws.sort_tmp);
       gather_tag_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, ws.order, M, kin);
-      JB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, ws.order, ws.lists, (int)M, 0, 11, st));
+      JB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, ws.order, ws.lists, (int)M, 0, 11 + shift, st));
       const int n0 = (int)(M - run);   // finished rows (key 0) sort to the front
       for (int k = 0; k < 4; k++) base[k] += n0;
     } else {
       JB_CUDA(cudaMemcpyAsync(ws.counts, hist.data(), sizeof(int) * NKEYS, cudaMemcpyHostToDevice, st));
-      scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, ws.lists);
+      scatter_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, ws.lists, shift);
     }
     JB_CUDA(cudaGetLastError());
     H->launches += 1;
@@ -659,7 +674,11 @@ int ws_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int n
   init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, ntspan, M, (Parked<NY>*)ws.parked, ws.tag);
   JB_CUDA(cudaGetLastError());
   ws.use_order = ws.have_order = false;
-  if (H->epoch_horder && M >= (1 << 16)) {
+  if (H->epoch_horder == 3 && M >= (1 << 16)) {
+    iota_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.order, M);
+    JB_CUDA(cudaGetLastError());
+    ws.use_order = ws.have_order = true;
+  } else if (H->epoch_horder && M >= (1 << 16)) {
     bool ok = false;
     if ((rc = build_order<Ham>(H, ws, y0, M, st, ok))) return rc;
     ws.use_order = ws.have_order = ok;
@@ -703,7 +722,7 @@ __global__ void rearm_kernel(const __grid_constant__ RadauParams P, Parked<NY>* 
       p.h = h;
       p.flags = f;
     }
-    tag[m] = regime_key(p.NbrStg, p.h, p.Newt);
+    tag[m] = regime_key(p.NbrStg, p.h, p.Newt, P.key_fine);
   }
 }
 

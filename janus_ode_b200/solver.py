@@ -200,16 +200,18 @@ class RadauTe:
             raise ValueError("tspan must be [M,>=2]")
         if tspan.shape[1] > 2 and not y0.is_cuda:
             raise NotImplementedError("dense output (tspan with interior points) takes CUDA tensors")
-        d = tspan[:, 1:] - tspan[:, :-1]
-        if tspan.shape[1] > 2 and not (bool((d > 0).all()) or bool((d < 0).all())):
-            raise ValueError("Time vector must be strictly monotonic")
+        if tspan.shape[1] > 2:
+            d = tspan[:, 1:] - tspan[:, :-1]
+            if not (bool((d > 0).all()) or bool((d < 0).all())):
+                raise ValueError("Time vector must be strictly monotonic")
         if y0.dtype != torch.float64 or tspan.dtype != torch.float64:
             raise TypeError("y0 and tspan must be float64")
         if y0.device != tspan.device:
             raise ValueError("y0 and tspan must live on the same device")
         t0, tf = tspan[:, 0], tspan[:, -1]
-        if bool(((tf - t0) == 0).any()):
-            raise ValueError("Time vector must be strictly monotonic")   # radaute_impl.hpp:54-59
+        # radaute_impl.hpp:54-59; large host batches: jb200_solve_host_compact makes the same check on its way through the rows
+        if (y0.is_cuda or y0.shape[0] <= 65536) and bool((tf == t0).any()):
+            raise ValueError("Time vector must be strictly monotonic")
         dev_key = y0.device if y0.is_cuda else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "none"
         if y0.is_cuda:
             with torch.cuda.device(y0.device):
@@ -223,8 +225,8 @@ class RadauTe:
         self.tout = self.yout = self.nout = None
         self.te = self.ye = self.ie = self.nev = None     # located events (teout, yeout, ieout of radau.m:1110-1121)
         self.y = y0.contiguous()          # never written: solve() replaces it with the result tensor
-        self.t = t0.clone()
-        self.h = torch.zeros(self.M, dtype=torch.float64, device=self.device)
+        self.t = t0                        # a view until solve() replaces it with the final times
+        self.h = None                      # set by solve()
         self.stats = None
         self.nstg = None
         self._res = self._res32 = None
@@ -427,6 +429,13 @@ def det_pow(x, y):
 def fp64_peak_tflops(iters=20000):
     v = C.c_double()
     _lib.check(_lib.lib().jb200_fp64_peak(int(iters), C.byref(v)))
+    return v.value
+
+
+def fp64_dmma_tflops(iters=20000):
+    """FP64 tensor-core (mma.sync m8n8k4 f64) throughput probe, TFLOP/s"""
+    v = C.c_double()
+    _lib.check(_lib.lib().jb200_dmma_peak(int(iters), C.byref(v)))
     return v.value
 
 

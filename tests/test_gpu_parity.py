@@ -82,7 +82,7 @@ def test_stage_eval_vs_reference_autograd_golden():
     assert np.allclose(dyn.jacobian(None, y2).cpu().numpy(), g["harm_jac"], rtol=1e-14)
 
 
-@pytest.mark.parametrize("n", [2, 3, 4])
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("cplx", [False, True])
 def test_batched_lu(n, cplx):
     rng = np.random.default_rng(n)
