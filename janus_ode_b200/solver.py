@@ -238,6 +238,7 @@ class RadauTe:
         # host path: page-locked result buffers so the D2H copies of jb200_solve_host are direct DMA
         kw = dict(device=dev) if self.y.is_cuda else dict(device=dev, pin_memory=True)
         host = not self.y.is_cuda
+        launches = None
         y_out = torch.empty(M, ny, dtype=torch.float64, **kw)
         t_out = torch.empty(M, dtype=torch.float64, **kw)
         h_out = torch.empty(M, dtype=torch.float64, **kw)
@@ -288,7 +289,7 @@ class RadauTe:
         self.work = work           # algorithmic FLOPs per trajectory (roofline accounting)
         self._res32 = res
         self._res = None
-        self.gpu_launches = int(H.L.jb200_last_launches(H.h))
+        self.gpu_launches = launches if launches is not None else int(H.L.jb200_last_launches(H.h))
         return self.res
 
     @property

@@ -269,3 +269,4 @@ def test_full_size_1m_properties():
     assert np.array_equal(a["y"][idx], m["y"]) and np.array_equal(st[idx], m["stats"])
     # vdP limit cycle: |x1| <= ~2.1 for every trajectory that has completed a jump
     assert np.abs(a["y"][:, 2]).max() < 3.01
+

@@ -149,3 +149,45 @@ def test_gpu_sensitivities_unsupported():
     ts = torch.tensor([0.0, 1.0], dtype=torch.float64, device=DEV).repeat(2, 1)
     with pytest.raises(jb.JanusB200Error, match="thread-resident"):
         jb.RadauTeD(dyn, None, ts, y0, jb.OptionsTe()).solve()
+
+
+# ------------------------------------------------------------------ against the LIVE reference solver
+def _live_fd():
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_live_sens_fd.npz")
+    return np.load(p)
+
+
+@pytest.mark.parametrize("mu", [1, 30])
+def test_oracle_sensitivities_vs_live_reference_finite_differences(mu):
+    """d y(tf)/d y0 by central differences of the UNMODIFIED reference RadauTe (oracle/_ref, tests/golden/
+    make_reference_sens_fd.py) -- the reference's own way of checking RadauTeD (ode_solver_test.cpp:620-770)."""
+    g = _live_fd()
+    mu_f, tf = g[f"par_mu{mu}"]
+    f, j = problems.vdp(float(mu_f), +1)
+    op = RadauOptions(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=1000000)
+    for m, y0 in enumerate(g["y0"]):
+        r = radau_solve(f, j, 0.0, float(tf), y0.copy(), op, sens0=np.eye(4))
+        S = g[f"S_mu{mu}"][m]
+        assert np.allclose(r.y, g[f"y_mu{mu}"][m], rtol=1e-7, atol=1e-9)
+        assert np.allclose(r.sens, S, rtol=1e-4, atol=1e-4 * np.abs(S).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mu", [1, 30])
+@pytest.mark.parametrize("fixed", [True, False])
+def test_gpu_sensitivities_vs_live_reference_finite_differences(mu, fixed):
+    g = _live_fd()
+    mu_f, tf = g[f"par_mu{mu}"]
+    op = jb.OptionsTe(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=1000000)
+    if fixed:
+        op.MinNbrStg = op.MaxNbrStg = 3
+    dyn = jb.HamiltonianSystem(jb.VanDerPol(float(mu_f)), +1)
+    y0 = torch.from_numpy(g["y0"]).cuda()
+    ts = torch.tensor([0.0, float(tf)], dtype=torch.float64).repeat(3, 1).cuda()
+    r = jb.RadauTeD(dyn, dyn.jacobian, ts, y0, op)
+    res = r.solve()
+    assert bool((res == 0).all())
+    S = g[f"S_mu{mu}"]
+    assert np.allclose(r.yd.cpu().numpy(), S, rtol=1e-4, atol=1e-4 * np.abs(S).max())
+    assert np.allclose(r.y.cpu().numpy(), g[f"y_mu{mu}"], rtol=1e-7, atol=1e-9)
