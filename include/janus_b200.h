@@ -209,6 +209,16 @@ int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const 
                      double* S_out, double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
                      int64_t* work, int32_t* sens_iters, void* stream);
 
+/* The same with parameter directions: Sp_out [M, n_par, Ny] = d y(tfinal) / d par[par_index[k]], k < n_par <= 4, for the
+ * parameters of the handle's Hamiltonian (zero at t0).  The reference gets these by appending the parameter to the state
+ * with zero dynamics and seeding its dual part (/root/reference/tests/cpp/ode_solver_test.cpp:630-640: y = [y1, y2, mu]);
+ * here the source term d f / d par of the sensitivity equation comes from one more hyper-dual variable of H.  A control
+ * law is held constant under differentiation (evalDynsU semantics).  n_par = 0: jb200_solve_sens.                     */
+int jb200_solve_sens_par(void* handle, const double* y0, const double* tspan, const double* S0, int32_t n_par,
+                         const int32_t* par_index, int64_t M, double* y_out, double* S_out, double* Sp_out, double* t_out,
+                         double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work, int32_t* sens_iters,
+                         void* stream);
+
 /* Explicit Dormand-Prince 8(5,3) step for non-stiff batches: replaces
  * Dopri853Te.step(htry) of /root/reference/src/python/dopri853te.py:290-315 (+ dy :207-287, error :191-205,
  * control :318-355) with derivs = the handle's Hamiltonian dynamics.  One call = one ACCEPTED step of every

@@ -570,9 +570,10 @@ int jb200_eval_jac(void* handle, const double* y, int64_t M, double* jac, void* 
   return ham_ops(H->ham_id)->jac(H, y, M, jac, (cudaStream_t)stream);
 }
 
-int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const double* S0, int64_t M, double* y_out,
-                     double* S_out, double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
-                     int64_t* work, int32_t* sens_iters, void* stream) {
+int jb200_solve_sens_par(void* handle, const double* y0, const double* tspan, const double* S0, int32_t n_par,
+                         const int32_t* par_index, int64_t M, double* y_out, double* S_out, double* Sp_out, double* t_out,
+                         double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work, int32_t* sens_iters,
+                         void* stream) {
   Handle* H = (Handle*)handle;
   if (!H) return fail(JB200_EINVAL, "null handle");
   if (M < 0) return fail(JB200_EINVAL, "M < 0");
@@ -580,8 +581,23 @@ int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const 
   if (!y0 || !tspan || !y_out || !S_out || !t_out || !h_out || !res || !stats) return fail(JB200_EINVAL, "null buffer");
   const HamOps* ops = ham_ops(H->ham_id);
   if (!ops || !ops->sens) return fail(JB200_ENOTSUP, "forward sensitivities are available for the thread-resident Hamiltonians only");
-  return ops->sens(H, y0, tspan, S0, (long long)M, y_out, S_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
-                   (long long*)work, (int*)sens_iters, (cudaStream_t)stream);
+  if (n_par < 0 || n_par > JB_SENS_MAXPAR) return fail(JB200_EINVAL, "at most 4 parameter directions per solve");
+  if (n_par > 0 && (!par_index || !Sp_out)) return fail(JB200_EINVAL, "parameter directions need par_index and Sp_out");
+  for (int k = 0; k < n_par; k++)
+    if (par_index[k] < 0 || par_index[k] >= ops->npar) return fail(JB200_EINVAL, "parameter index out of range for this Hamiltonian");
+  H->P.sens_npar = n_par;
+  for (int k = 0; k < JB_SENS_MAXPAR; k++) H->P.sens_par[k] = k < n_par ? par_index[k] : 0;
+  const int rc = ops->sens(H, y0, tspan, S0, (long long)M, y_out, S_out, t_out, h_out, (int*)res, (long long*)stats, (int*)nstg,
+                           (long long*)work, (int*)sens_iters, Sp_out, (cudaStream_t)stream);
+  H->P.sens_npar = 0;
+  return rc;
+}
+
+int jb200_solve_sens(void* handle, const double* y0, const double* tspan, const double* S0, int64_t M, double* y_out,
+                     double* S_out, double* t_out, double* h_out, int32_t* res, int64_t* stats, int32_t* nstg,
+                     int64_t* work, int32_t* sens_iters, void* stream) {
+  return jb200_solve_sens_par(handle, y0, tspan, S0, 0, nullptr, M, y_out, S_out, nullptr, t_out, h_out, res, stats, nstg, work,
+                              sens_iters, stream);
 }
 
 int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,

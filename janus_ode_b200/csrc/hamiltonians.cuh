@@ -9,8 +9,9 @@
 //
 // A Hamiltonian is a struct with
 //   N, NV = 2N, NPAR, HAS_CONTROL
-//   template <class... V> static auto H(v0, ..., v_{NV-1}, const double* par, double u)
-//        arguments in y-order (p_1..p_N, x_1..x_N), each a D1/D2 number with its own mask
+//   template <class... V, class PAR> static auto H(v0, ..., v_{NV-1}, const PAR& par, double u)
+//        arguments in y-order (p_1..p_N, x_1..x_N), each a D1/D2 number with its own mask; par[k] is a plain double
+//        (ParPlain) or, for parameter sensitivities, a hyper-dual number (ParDual): take it with `const auto`
 //   static double control(const double* y, const double* par)          (if HAS_CONTROL)
 //   FLOPS_F, FLOPS_J   FP64 instructions of one dynamics / Jacobian evaluation, counted from the
 //                      SASS of dyns_kernel / jac_kernel (roofline accounting only)
@@ -38,9 +39,9 @@ struct HamHarmonic {
   static constexpr int N = 1, NV = 2, NPAR = 1;
   static constexpr int FLOPS_F = 4, FLOPS_J = 2;
   static constexpr bool HAS_CONTROL = false;
-  template <class P, class X>
-  JB_HD static auto H(const P& p, const X& x, const double* par, double) {
-    const double w = par[0];
+  template <class P, class X, class PAR>
+  JB_HD static auto H(const P& p, const X& x, const PAR& par, double) {
+    const auto w = par[0];
     return (square(p) + (w * w) * square(x)) * 0.5;
   }
   JB_HD static double control(const double*, const double*) { return 0.0; }
@@ -51,10 +52,10 @@ struct HamVdp {
   static constexpr int N = 2, NV = 4, NPAR = 1;
   static constexpr int FLOPS_F = 14, FLOPS_J = 16;
   static constexpr bool HAS_CONTROL = false;
-  template <class P1, class P2, class X1, class X2>
-  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+  template <class P1, class P2, class X1, class X2, class PAR>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const PAR& par,
                       double) {
-    const double mu = par[0];
+    const auto mu = par[0];
     return p1 * x2 + p2 * (mu * (1.0 - x1 * x1) * x2 - x1);
   }
   JB_HD static double control(const double*, const double*) { return 0.0; }
@@ -67,11 +68,11 @@ struct HamVdpPmp {
   static constexpr int N = 2, NV = 4, NPAR = 3;  // W, umin, umax
   static constexpr int FLOPS_F = BANG ? 16 : 34, FLOPS_J = BANG ? 18 : 38;
   static constexpr bool HAS_CONTROL = true;
-  template <class P1, class P2, class X1, class X2>
-  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+  template <class P1, class P2, class X1, class X2, class PAR>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const PAR& par,
                       double u) {
-    const double W = par[0];
-    return p1 * x2 + p2 * u * ((1.0 - x1 * x1) * x2 - x1) + ((W / 2) * u * u + 1.0);
+    const auto W = par[0];
+    return p1 * x2 + p2 * u * ((1.0 - x1 * x1) * x2 - x1) + ((W * 0.5) * u * u + 1.0);   // W * 0.5 == W / 2 exactly
   }
   JB_HD static double control(const double* y, const double* par) {
     const double p2 = y[1], x1 = y[2], x2 = y[3];
@@ -87,8 +88,8 @@ struct HamVdpAugBang {
   static constexpr int N = 2, NV = 4, NPAR = 2;  // umin, umax
   static constexpr int FLOPS_F = 16, FLOPS_J = 18;
   static constexpr bool HAS_CONTROL = true;
-  template <class P1, class P2, class X1, class X2>
-  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const double* par,
+  template <class P1, class P2, class X1, class X2, class PAR>
+  JB_HD static auto H(const P1& p1, const P2& p2, const X1& x1, const X2& x2, const PAR&,
                       double u) {
     return p1 * x2 + p2 * (u * (1.0 - x1 * x1) * x2 - x1);
   }
@@ -99,18 +100,59 @@ struct HamVdpAugBang {
 };
 
 // ------------------------------------------------------------------ adaptor
+// parameters as the Hamiltonian sees them: plain doubles ...
+struct ParPlain {
+  const double* p;
+  JB_HD double operator[](int k) const { return p[k]; }
+};
+// ... or, for the sensitivity with respect to parameter K (run-time index), hyper-dual numbers over NV + 1 variables whose
+// extra variable NV is that parameter: par[K] is seeded with 1, every other parameter with an explicit 0
+template <int NVX>
+struct ParDual {
+  const double* p;
+  int K;
+  JB_HD D2<NVX, (1u << (NVX - 1)), 0ull> operator[](int k) const {
+    D2<NVX, (1u << (NVX - 1)), 0ull> r;
+    r.v = p[k];
+    r.g[NVX - 1] = (k == K) ? 1.0 : 0.0;
+    return r;
+  }
+};
+
 template <class Ham, size_t... I>
 JB_HD auto ham_eval1(const double* y, const double* par, double u, std::index_sequence<I...>) {
-  return Ham::H(seed1<Ham::NV, (int)I>(y[I])..., par, u);
+  return Ham::H(seed1<Ham::NV, (int)I>(y[I])..., ParPlain{par}, u);
 }
 template <class Ham, size_t... I>
 JB_HD auto ham_eval2(const double* y, const double* par, double u, std::index_sequence<I...>) {
-  return Ham::H(seed2<Ham::NV, (int)I>(y[I])..., par, u);
+  return Ham::H(seed2<Ham::NV, (int)I>(y[I])..., ParPlain{par}, u);
 }
 
 template <class Ham, size_t... I>
 JB_HD auto ham_eval3(const double* y, const double* par, double u, std::index_sequence<I...>) {
-  return Ham::H(seed3<Ham::NV, (int)I>(y[I])..., par, u);
+  return Ham::H(seed3<Ham::NV, (int)I>(y[I])..., ParPlain{par}, u);
+}
+template <class Ham, size_t... I>
+JB_HD auto ham_eval2p(const double* y, const double* par, int K, double u, std::index_sequence<I...>) {
+  return Ham::H(seed2<Ham::NV + 1, (int)I>(y[I])..., ParDual<Ham::NV + 1>{par, K}, u);
+}
+
+// g = d f / d par[K] = [sigma d2H/dx dpar ; d2H/dp dpar]: the source term of a parameter direction of the forward
+// sensitivities (the reference appends the parameter to the state instead, tests/cpp/ode_solver_test.cpp:630-640).
+// A control law is evaluated on values and held constant (evalDynsU semantics), like in ham_jac.
+template <class Ham>
+JB_HD void ham_dpar(const double* y, const double* par, double sign, int K, double* g) {
+  constexpr int N = Ham::N, NV = Ham::NV;
+  const double u = Ham::HAS_CONTROL ? Ham::control(y, par) : 0.0;
+  const auto r = ham_eval2p<Ham>(y, par, K, u, std::make_index_sequence<NV>{});
+  using R = decltype(r);
+#pragma unroll
+  for (int rr = 0; rr < NV; rr++) {
+    const int vi = (rr < N) ? (N + rr) : (rr - N);
+    const int k = hidx(NV + 1, vi, NV);
+    const double val = JB_BIT(R::hm, k) ? r.h[k] : 0.0;
+    g[rr] = (rr < N) ? sign * val : val;
+  }
 }
 
 // value + dual part of the dynamics and of the Jacobian (evalDynsDual / evalJacDual and their U twins,

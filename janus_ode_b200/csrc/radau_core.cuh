@@ -49,7 +49,10 @@ struct RadauParams {
   int key_fine;              // scheduling only: epoch lists also ordered by the current step size (solver_impl.cuh regime_key)
   int ev_K, ev_stop[4], ev_slope[4];
   double ev_A[4][NYMAX], ev_b[4];
+  // forward sensitivities: parameter directions d y / d ham_par[sens_par[k]], k < sens_npar (sens_step)
+  int sens_npar, sens_par[4];
 };
+#define JB_SENS_MAXPAR 4
 
 // Algorithmic FLOP model of SURVEY.md 8(d) (mul, add, div, sqrt, pow = 1; complex mul = 6, add = 2),
 // n = Ny, s stages, F / Jf = FP64 instructions of one dynamics / Jacobian evaluation counted from
@@ -375,10 +378,14 @@ JB_HD void dense_finish(const Traj<NY, SM>& T, const DenseOut& out) {
 // the fixed point, so no third derivatives of H are needed), with the Jacobians J(y + z_j) evaluated by
 // hyper-dual numbers at the CONVERGED stage points.  The real part of the integration is untouched: states,
 // step sizes and counters are bit-identical to a solve without sensitivities.
+// Parameter directions (RadauParams::sens_par): the column s_k = d y / d par_k obeys the same linear stage system with
+// the source term g_k(Y_j) = d f / d par_k added (ham_dpar: one more hyper-dual variable), s_k(t0) = 0 -- what the
+// reference obtains by appending the parameter to the state (tests/cpp/ode_solver_test.cpp:630-640).
 template <int NY>
 struct Sens {
   static constexpr int ND = NY;
   double S[NY * NY];   // S[i * ND + d] = d y_i / d (direction d)
+  double Sp[JB_SENS_MAXPAR * NY];   // Sp[k * NY + i] = d y_i / d ham_par[sens_par[k]]
   int iters;           // sensitivity Newton iterations spent (all directions, all steps)
   int unconverged;     // (direction, step) pairs whose iteration hit its cap or produced a non-finite increment: S is then
                        // not to be trusted -- reported to the caller instead of silently propagated
@@ -401,17 +408,31 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
     ham_jac<Ham>(yq, P.ham_par, P.sign, &Jq[q * NY * NY]);
   }
   T.work += (long long)S * Ham::FLOPS_J;
-  for (int d = 0; d < ND; d++) {
+  for (int d = 0; d < ND + P.sens_npar; d++) {
     double Sd[NY], smax = 1.0;
+    double gq[S * NY];   // source term of a parameter direction at the stage points (unused for a state direction)
+    if (d < ND) {
 #pragma unroll
-    for (int i = 0; i < NY; i++) {
-      Sd[i] = sn.S[i * ND + d];
-      smax = fmax(smax, fabs(Sd[i]));
+      for (int i = 0; i < NY; i++) Sd[i] = sn.S[i * ND + d];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NY; i++) Sd[i] = sn.Sp[(d - ND) * NY + i];
+#pragma unroll
+      for (int q = 0; q < S; q++) {
+        double yq[NY];
+#pragma unroll
+        for (int i = 0; i < NY; i++) yq[i] = T.y[i] + z[q * NY + i];
+        ham_dpar<Ham>(yq, P.ham_par, P.sign, P.sens_par[d - ND], &gq[q * NY]);
+      }
+      T.work += (long long)S * Ham::FLOPS_J;
     }
+#pragma unroll
+    for (int i = 0; i < NY; i++) smax = fmax(smax, fabs(Sd[i]));
     const double rs = 1.0 / smax;
     double Zs[S * NY], Ws[S * NY];
 #pragma unroll
     for (int k = 0; k < S * NY; k++) Zs[k] = Ws[k] = 0.0;
+    double nrm_old = 0.0;
     for (int it = 0; it < Nit; it++) {
       double zz[S * NY];
       {  // F_q = J_q (S_d + Zs_q);  zz = TI F
@@ -423,7 +444,7 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < NY; j++) acc = fma(Jq[q * NY * NY + i * NY + j], Sd[j] + Zs[q * NY + j], acc);
-            Fq[q * NY + i] = acc;
+            Fq[q * NY + i] = (d < ND) ? acc : acc + gq[q * NY + i];
           }
 #pragma unroll
         for (int j = 0; j < S; j++)
@@ -483,10 +504,22 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
         break;
       }
       if (!(nrm > tol)) break;
+      // the iteration is linear: increments contract by a fixed operator, so theta / (1 - theta) * |increment| bounds what
+      // is left -- the state iteration's own stopping rule (radau.m:974-976, 1014), ten times tighter
+      if (it >= 1) {
+        const double theta = nrm / nrm_old;
+        if (theta < 0.99 && theta / (1.0 - theta) * nrm <= tol) break;
+      }
+      nrm_old = nrm;
       if (it == Nit - 1) sn.unconverged += 1;
     }
+    if (d < ND) {
 #pragma unroll
-    for (int i = 0; i < NY; i++) sn.S[i * ND + d] = Sd[i] + Zs[(S - 1) * NY + i];
+      for (int i = 0; i < NY; i++) sn.S[i * ND + d] = Sd[i] + Zs[(S - 1) * NY + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NY; i++) sn.Sp[(d - ND) * NY + i] = Sd[i] + Zs[(S - 1) * NY + i];
+    }
   }
 }
 
@@ -1407,7 +1440,7 @@ JB_HD void epoch_begin(Traj<NY, S>& T, const RadauParams& P) {
 // head_done, or stop_on_accept hit -> *stepped)
 template <class Ham, int NY, int S, bool VAR = true>
 JB_HD int epoch_pass(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int acc0, const DenseOut* out = nullptr,
-                     bool stop_on_accept = false, bool* stepped = nullptr) {
+                     bool stop_on_accept = false, bool* stepped = nullptr, Sens<NY>* sens = nullptr) {
   if (!(T.res == 0 && traj_active(T.PosNeg, T.t, T.tfinal, T.st[ST_STEP], P.MaxNbrStep))) {
     if (T.res == 0 && T.PosNeg * T.t < T.PosNeg * T.tfinal) T.res = 3;
     return 1;
@@ -1422,7 +1455,7 @@ JB_HD int epoch_pass(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int 
     return 2;
   }
   head_done = false;
-  if (attempt_step<Ham, NY, S, S>(T, P, Jac, jf, out)) return 1;
+  if (attempt_step<Ham, NY, S, S>(T, P, Jac, jf, out, sens)) return 1;
   if (stop_on_accept && T.st[ST_ACC] != acc0) {
     *stepped = true;
     return 2;
@@ -1437,11 +1470,12 @@ JB_HD int epoch_pass(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int 
 // accepted step.
 template <class Ham, int NY, int S, bool VAR = true>
 JB_HD bool run_epoch(Traj<NY, S>& T, const RadauParams& P, bool& head_done, int max_passes,
-                     const DenseOut* out = nullptr, bool stop_on_accept = false, bool* stepped = nullptr) {
+                     const DenseOut* out = nullptr, bool stop_on_accept = false, bool* stepped = nullptr,
+                     Sens<NY>* sens = nullptr) {
   epoch_begin<Ham, NY, S>(T, P);
   const int acc0 = T.st[ST_ACC];
   for (int passes = 0;;) {
-    const int r = epoch_pass<Ham, NY, S, VAR>(T, P, head_done, acc0, out, stop_on_accept, stepped);
+    const int r = epoch_pass<Ham, NY, S, VAR>(T, P, head_done, acc0, out, stop_on_accept, stepped, sens);
     if (r) return r == 1;
     if (++passes >= max_passes) return false;
   }

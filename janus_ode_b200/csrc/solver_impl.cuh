@@ -92,6 +92,11 @@ struct DenseArgs {
   int* ie = nullptr;      // [M, ecap]
   int* nev = nullptr;     // [M], zeroed by the host
   int ecap = 0;
+  // forward sensitivities through the epochs (epoch_sens_kernel): S [M, NY*NY] is the caller's result matrix, used as the
+  // working copy between epochs; sens_cnt [M, 2] = { sensitivity Newton iterations, unconverged (direction, step) pairs }
+  double* sens_S = nullptr;
+  int* sens_cnt = nullptr;
+  double* sens_Sp = nullptr;   // [M, sens_npar, NY] parameter directions (RadauParams::sens_par), or nullptr
 };
 template <int NY>
 __device__ __forceinline__ DenseOut make_dout(const DenseArgs& d, const double* tspan, long long m) {
@@ -313,6 +318,55 @@ __global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
   }
 }
 
+#ifndef JB_SLIM
+// The same epoch with the Ny x Ny sensitivity matrix riding along (radau_core.cuh: sens_step is a hook of attempt_step): S lives
+// in the caller's result array between epochs, the real part of the integration is the plain epoch kernel's, bit for bit.
+template <class Ham, int S, bool VAR>
+__global__ void __launch_bounds__(EpochCfg<S>::threads, EpochCfg<S>::minb)
+    epoch_sens_kernel(const __grid_constant__ RadauParams P, Parked<Ham::NV>* __restrict__ st, const int* __restrict__ list,
+                      int count, int max_passes, unsigned long long* __restrict__ counter, unsigned short* __restrict__ tag,
+                      double* __restrict__ y_out, double* __restrict__ t_out, double* __restrict__ h_out,
+                      int* __restrict__ res, long long* __restrict__ stats, int* __restrict__ nstg,
+                      long long* __restrict__ work, double* __restrict__ sens_S, int* __restrict__ sens_cnt,
+                      double* __restrict__ sens_Sp) {
+  constexpr int NY = Ham::NV;
+  const int npy = P.sens_npar * NY;
+  for (;;) {
+    const long long i = (long long)atomicAdd(counter, 1ull);
+    if (i >= count) break;
+    const long long m = list[i];
+    Traj<NY, S> T;
+    double t0;
+    bool head_done;
+    unpark<NY, S>(st[m], T, t0, head_done);
+    Sens<NY> sn;
+#pragma unroll
+    for (int k = 0; k < NY * NY; k++) sn.S[k] = sens_S[m * NY * NY + k];
+    for (int k = 0; k < npy; k++) sn.Sp[k] = sens_Sp[m * npy + k];
+    sn.iters = sens_cnt[2 * m];
+    sn.unconverged = sens_cnt[2 * m + 1];
+    const bool fin = run_epoch<Ham, NY, S, VAR>(T, P, head_done, max_passes, nullptr, false, nullptr, &sn);
+    park<NY, S>(T, t0, head_done, fin, st[m]);
+#pragma unroll
+    for (int k = 0; k < NY * NY; k++) sens_S[m * NY * NY + k] = sn.S[k];
+    for (int k = 0; k < npy; k++) sens_Sp[m * npy + k] = sn.Sp[k];
+    sens_cnt[2 * m] = sn.iters;
+    sens_cnt[2 * m + 1] = sn.unconverged;
+    tag[m] = fin ? (unsigned short)0 : regime_key(T.NbrStg, T.h, T.Newt, P.key_fine);
+    if (fin && y_out) {
+      store_row<NY>(y_out, m, T.y);
+      t_out[m] = T.t;
+      h_out[m] = T.h;
+      res[m] = (T.res == 0 && sn.unconverged > 0) ? JB200_RES_SENS_UNCONVERGED : T.res;   // the state is fine, S is not
+#pragma unroll
+      for (int k = 0; k < 8; k++) stats[m * 8 + k] = (long long)T.st[k];
+      if (nstg) nstg[m] = T.NbrStg;
+      if (work) work[m] = T.work;
+    }
+  }
+}
+#endif
+
 template <class Ham>
 __global__ void dyns_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y, long long M,
                             double* __restrict__ f) {
@@ -377,19 +431,22 @@ struct EpochWS {
   int* nsel = nullptr;     // [4] device counts of the per-stage selections
   void* sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
+  int* sens_cnt = nullptr;   // [cap, 2] counters of the sensitivity iteration (epoch_sens_kernel), allocated on first use
 };
+inline void ws_free(EpochWS& ws) {
+  cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
+  cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp); cudaFree(ws.sens_cnt);
+  ws = EpochWS();   // every pointer nulled, cap = 0
+}
 inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
   if (M <= ws.cap && parked_bytes <= ws.rec_bytes) {
     ws.M = M;
     return 0;
   }
-  cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
-  cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp);
-  ws = EpochWS();   // every pointer nulled, cap = 0: a failed allocation below leaves nothing dangling
+  ws_free(ws);      // a failed allocation below leaves nothing dangling
   struct Guard {
     EpochWS& ws; bool ok = false;
-    ~Guard() { if (!ok) { cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts); cudaFree(ws.order);
-                          cudaFree(ws.nsel); cudaFree(ws.sort_tmp); ws = EpochWS(); cudaGetLastError(); } }
+    ~Guard() { if (!ok) { ws_free(ws); cudaGetLastError(); } }
   } guard{ws};
   ws.rec_bytes = parked_bytes;
   JB_CUDA(cudaMalloc(&ws.parked, parked_bytes * M));
@@ -404,11 +461,6 @@ inline int ws_reserve(EpochWS& ws, long long M, size_t parked_bytes) {
   ws.M = M;
   guard.ok = true;
   return 0;
-}
-inline void ws_free(EpochWS& ws) {
-  cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
-  cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp);
-  ws = EpochWS();
 }
 
 struct Handle {
@@ -548,6 +600,28 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
   constexpr int TH = EpochCfg<S>::threads;
   int bps = 0;
   const size_t smem = lc_smem_bytes<Ham::NV, S>(TH);
+#ifndef JB_SLIM
+  if constexpr (VAR) if (dense.sens_S) {
+    auto ks = epoch_sens_kernel<Ham, S, VAR>;
+    if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ks, TH, smem));
+    if (bps < 1) bps = 1;
+    long long blocks = (long long)H->sm_count * bps;
+    const long long need = ((long long)count + TH - 1) / TH;
+    if (blocks > need) blocks = need;
+    ks<<<(unsigned)blocks, TH, smem, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
+                                          H->d_counter + k, ws.tag, o.y_out, o.t_out, o.h_out, o.res, o.stats, o.nstg,
+                                          o.work, dense.sens_S, dense.sens_cnt, dense.sens_Sp);
+    JB_CUDA(cudaGetLastError());
+    H->launches += 1;
+    if (used > 0) {
+      JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
+      JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
+    }
+    used += 1;
+    return 0;
+  }
+#endif
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, smem));
   if (bps < 1) bps = 1;
@@ -906,8 +980,10 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
                                                              double* __restrict__ t_out, double* __restrict__ h_out,
                                                              int* __restrict__ res, long long* __restrict__ stats,
                                                              int* __restrict__ nstg, long long* __restrict__ work,
-                                                             int* __restrict__ sens_iters, const int* __restrict__ order) {
+                                                             int* __restrict__ sens_iters, const int* __restrict__ order,
+                                                             double* __restrict__ Sp_out) {
   constexpr int NY = Ham::NV;
+  const int npy = P.sens_npar * NY;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
     const long long m = order ? order[i] : i;   // rows in H(y0) order: the lanes of a warp are phase-space neighbours
     Traj<NY, SM> T;
@@ -919,10 +995,12 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
     sn.unconverged = 0;
 #pragma unroll
     for (int k = 0; k < NY * NY; k++) sn.S[k] = S0 ? S0[m * NY * NY + k] : ((k / NY == k % NY) ? 1.0 : 0.0);
+    for (int k = 0; k < npy; k++) sn.Sp[k] = 0.0;
     integrate<Ham, NY, SM, VAR>(T, P, nullptr, &sn);
     store_row<NY>(y_out, m, T.y);
 #pragma unroll
     for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = sn.S[k];
+    for (int k = 0; k < npy; k++) Sp_out[m * npy + k] = sn.Sp[k];
     t_out[m] = T.t;
     h_out[m] = T.h;
     res[m] = T.res;
@@ -934,18 +1012,48 @@ __global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_consta
     if (T.res == 0 && sn.unconverged > 0) res[m] = JB200_RES_SENS_UNCONVERGED;   // the state is fine, S is not
   }
 }
+template <int NY>
+__global__ void sens_seed_kernel(const double* __restrict__ S0, long long M, double* __restrict__ S) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M * NY * NY; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % (NY * NY));
+    S[i] = S0 ? S0[i] : ((k / NY == k % NY) ? 1.0 : 0.0);
+  }
+}
 template <class Ham>
 int launch_sens(Handle* H, const double* y0, const double* tspan, const double* S0, long long M, double* y_out, double* S_out,
                 double* t_out, double* h_out, int* res, long long* stats, int* nstg, long long* work, int* sens_iters,
-                cudaStream_t st) {
+                double* Sp_out, cudaStream_t st) {
 #ifdef JB_SLIM
   return fail(JB200_ENOTSUP, "this plugin was built without the sensitivity kernel");
 #else
-  // fixed 3 stages (the common fixed-order configuration): its own lean instantiation; everything else -- other
-  // fixed stage counts, variable order -- runs the all-orders kernel with the order chosen at run time
+  // fixed 3 stages (the common fixed-order configuration): one fused kernel.  Everything else -- variable order (the
+  // reference default), other fixed stage counts -- goes through the order-homogeneous epochs like the plain solve
+  // (epoch_sens_kernel), S riding along in the caller's result matrix.
+  constexpr int NY = Ham::NV;
   const bool fixed3 = H->P.MinNbrStg == 3 && H->P.MaxNbrStg == 3;
-  auto kern = fixed3 ? sens_kernel<Ham, 3, false> : sens_kernel<Ham, 7, true>;
-  const size_t smem = fixed3 ? lc_smem_bytes<Ham::NV, 3>(JB_THREADS) : lc_smem_bytes<Ham::NV, 7>(JB_THREADS);
+  if (!fixed3) {
+    int rc = ws_init<Ham>(H, H->ws, y0, tspan, 2, M, st);
+    if (rc) return rc;
+    EpochWS& ws = H->ws;
+    if (!ws.sens_cnt) JB_CUDA(cudaMalloc(&ws.sens_cnt, sizeof(int) * 2 * ws.cap));
+    JB_CUDA(cudaMemsetAsync(ws.sens_cnt, 0, sizeof(int) * 2 * M, st));
+    const long long gblocks = std::max<long long>(1, std::min<long long>((M * NY * NY + 255) / 256, (long long)H->sm_count * 16));
+    sens_seed_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>(S0, M, S_out);
+    JB_CUDA(cudaGetLastError());
+    H->launches = 2;
+    DenseArgs d{2, nullptr, nullptr, nullptr};
+    d.sens_S = S_out;
+    d.sens_cnt = ws.sens_cnt;
+    d.sens_Sp = Sp_out;
+    if (H->P.sens_npar > 0) JB_CUDA(cudaMemsetAsync(Sp_out, 0, sizeof(double) * (size_t)M * H->P.sens_npar * NY, st));
+    const OutArgs o{y_out, t_out, h_out, res, stats, nstg, work};
+    if ((rc = run_epochs<Ham, true>(H, ws, H->epoch_passes, 0, o, tspan, d, st))) return rc;
+    if (sens_iters) JB_CUDA(cudaMemcpy2DAsync(sens_iters, sizeof(int), ws.sens_cnt, 2 * sizeof(int), sizeof(int), (size_t)M,
+                                              cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  auto kern = sens_kernel<Ham, 3, false>;
+  const size_t smem = lc_smem_bytes<Ham::NV, 3>(JB_THREADS);
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // many small blocks in flight: trajectories differ in length by up to 5x, the block scheduler balances them
   const long long blocks = std::max<long long>(1, (M + JB_THREADS - 1) / JB_THREADS);
@@ -958,7 +1066,7 @@ int launch_sens(Handle* H, const double* y0, const double* tspan, const double* 
     if (ok) order = H->ws.order;
   }
   kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
-                                                  sens_iters, order);
+                                                  sens_iters, order, Sp_out);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
@@ -978,7 +1086,7 @@ struct HamOps {
   void (*destroy)(Handle*) = nullptr;
   int (*dopri)(Handle*, const dp::StepArgs&, cudaStream_t) = nullptr;   // explicit DOPRI853 step (thread-resident Hamiltonians)
   int (*sens)(Handle*, const double*, const double*, const double*, long long, double*, double*, double*, double*, int*,
-              long long*, int*, long long*, int*, cudaStream_t) = nullptr;   // solve with forward sensitivities
+              long long*, int*, long long*, int*, double*, cudaStream_t) = nullptr;   // solve with forward sensitivities
   void (*st_free)(EpochWS&) = nullptr;   // optional: the state of the incremental protocol is not a plain EpochWS
   int (*seulex)(Handle*, const sx::StepArgs&, cudaStream_t) = nullptr;   // SEULEX step (thread-resident Hamiltonians)
   int (*jac_dual)(Handle*, const JacDualArgs&, cudaStream_t) = nullptr;  // evalDynsDual / evalJacDual / third-order ladders

@@ -590,11 +590,19 @@ class RadauTeD(RadauTe):
         r = RadauTeD(dyns, dyns.jacobian, tspan, y0, options, y0d=None);  r.solve()  ->  r.y [M,Ny], r.yd [M,Ny,Ny]
 
     y0d [M,Ny,Ny] is the dual part of the initial state (None: identity, i.e. yd = d y(tfinal) / d y0).  The
-    sensitivity of the final state to the final time is the dynamics there: `r.dydtf = dyns(t, r.y)`.  CUDA tensors
-    only; thread-resident Hamiltonians (built-in or user plugins with N <= 2)."""
+    sensitivity of the final state to the final time is the dynamics there: `r.dydtf = dyns(t, r.y)`.
+    `par_dirs=[k, ...]` (at most 4) adds parameter directions: `r.ypar [M,Ny,len(par_dirs)]` = d y(tfinal) / d par[k] for
+    the parameters of the Hamiltonian -- the reference appends the parameter to the state with zero dynamics and seeds its
+    dual part (ode_solver_test.cpp:630-640, y = [y1, y2, mu]).  `r.yd_full()` returns the reference test's layout
+    [M, Ny, Ny + len(par_dirs) + 1]: state directions, parameter directions, final time.  CUDA tensors only;
+    thread-resident Hamiltonians (built-in or user plugins with N <= 2)."""
 
-    def __init__(self, dyns, jac, tspan, y0, options=None, y0d=None):
+    def __init__(self, dyns, jac, tspan, y0, options=None, y0d=None, par_dirs=()):
         super().__init__(dyns, jac, tspan, y0, options)
+        self.par_dirs = tuple(int(k) for k in par_dirs)
+        if len(self.par_dirs) > 4:
+            raise ValueError("at most 4 parameter directions per solve")
+        self.ypar = None
         if not y0.is_cuda:
             raise _lib.JanusB200Error("RadauTeD runs on CUDA tensors only (no CPU fallback)")
         if self.ntspan != 2:
@@ -616,13 +624,23 @@ class RadauTeD(RadauTe):
         nstg = torch.empty(M, dtype=torch.int32, device=dev)
         work = torch.empty(M, dtype=torch.int64, device=dev)
         it = torch.empty(M, dtype=torch.int32, device=dev)
+        npd = len(self.par_dirs)
+        Sp = torch.empty(M, npd, ny, dtype=torch.float64, device=dev) if npd else None
+        pidx = (C.c_int32 * max(npd, 1))(*self.par_dirs)
         with torch.cuda.device(dev):
-            _lib.check_h(H, H.L.jb200_solve_sens(H.h, _ptr(self.y), _ptr(self.tspan), _ptr(self.y0d), M, _ptr(y_out),
-                                                _ptr(S_out), _ptr(t_out), _ptr(h_out), _ptr(res), _ptr(stats), _ptr(nstg),
-                                                _ptr(work), _ptr(it), _stream_ptr(dev)))
+            _lib.check_h(H, H.L.jb200_solve_sens_par(H.h, _ptr(self.y), _ptr(self.tspan), _ptr(self.y0d), npd, pidx, M,
+                                                    _ptr(y_out), _ptr(S_out), _ptr(Sp), _ptr(t_out), _ptr(h_out), _ptr(res),
+                                                    _ptr(stats), _ptr(nstg), _ptr(work), _ptr(it), _stream_ptr(dev)))
         self.y, self.yd, self.t, self.h, self.nstg, self.work, self.sens_iters = y_out, S_out, t_out, h_out, nstg, work, it
+        self.ypar = Sp.transpose(1, 2).contiguous() if npd else None      # [M, Ny, n_par]
         self.stats = StatsTe.from_tensor(stats)
         self.gpu_launches = 1
         self.res = res.to(torch.float64)
         self.dydtf = self.dyns(self.t, self.y)
         return self.res
+
+    def yd_full(self):
+        """[M, Ny, Ny + n_par + 1]: d y(tfinal) / d (y0 directions, parameters, final time) -- the column layout of the
+        reference's SensitivityTest (its N = D + 1 dual variables)."""
+        cols = [self.yd] + ([self.ypar] if self.ypar is not None else []) + [self.dydtf.unsqueeze(2)]
+        return torch.cat(cols, 2)

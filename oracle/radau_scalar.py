@@ -202,7 +202,8 @@ def sens_step(jac, t, y, z, h, C, T, TI, ValP, lus, Scal, Sm, Nit, FNewt):
         rs = 1.0 / max(1.0, float(np.max(np.abs(Sd))))
         Zs = np.zeros((Ny, s))
         Ws = np.zeros((Ny, s))
-        for _ in range(Nit + 10):
+        nrm_old = 0.0
+        for it in range(Nit + 10):
             F = np.stack([Jq[q] @ (Sd + Zs[:, q]) for q in range(s)], axis=1)
             zz = F @ TI.T                                        # zz_j = sum_q TI[j,q] F_q
             dW = solvrad(zz, Ws, ValP, h, lus)
@@ -213,6 +214,11 @@ def sens_step(jac, t, y, z, h, C, T, TI, ValP, lus, Scal, Sm, Nit, FNewt):
             iters += 1
             if not nrm > 0.1 * FNewt:
                 break
+            if it >= 1:                      # linear iteration: theta / (1 - theta) * |increment| bounds the remainder
+                theta = nrm / nrm_old
+                if theta < 0.99 and theta / (1.0 - theta) * nrm <= 0.1 * FNewt:
+                    break
+            nrm_old = nrm
         out[:, d] = Sd + Zs[:, s - 1]
     return out, iters
 

@@ -175,7 +175,7 @@ extern "C" int hostsim_solve_epochs(int ham_id, const RadauParams* P, const doub
 // sens_kernel<Ham, 7, true> runs
 template <class Ham>
 static void run_sens(const RadauParams& P, const double* y0, const double* tspan, long long M, double* y_out, double* S_out,
-                     long long* stats, int* iters) {
+                     long long* stats, int* iters, double* Sp_out = nullptr) {
   constexpr int NY = Ham::NV;
   for (long long m = 0; m < M; m++) {
     Traj<NY, 7> T;
@@ -184,7 +184,9 @@ static void run_sens(const RadauParams& P, const double* y0, const double* tspan
     sn.iters = 0;
     sn.unconverged = 0;
     for (int k = 0; k < NY * NY; k++) sn.S[k] = (k / NY == k % NY) ? 1.0 : 0.0;
+    for (int k = 0; k < P.sens_npar * NY; k++) sn.Sp[k] = 0.0;
     integrate<Ham, NY, 7, true>(T, P, nullptr, &sn);
+    for (int k = 0; k < P.sens_npar * NY; k++) Sp_out[m * P.sens_npar * NY + k] = sn.Sp[k];
     for (int i = 0; i < NY; i++) y_out[m * NY + i] = T.y[i];
     for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = sn.S[k];
     for (int k = 0; k < 8; k++) stats[m * 8 + k] = T.st[k];
@@ -197,6 +199,21 @@ extern "C" int hostsim_solve_sens(int ham_id, const RadauParams* P, const double
   switch (ham_id) {
     case HAM_HARMONIC: run_sens<HamHarmonic>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
     case HAM_VDP: run_sens<HamVdp>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
+  }
+  return -1;
+}
+
+// with parameter directions d y / d ham_par[par_index[k]] (Sp_out [M, n_par, NY])
+extern "C" int hostsim_solve_sens_par(int ham_id, const RadauParams* P0, const double* y0, const double* tspan, long long M,
+                                      int n_par, const int* par_index, double* y_out, double* S_out, double* Sp_out,
+                                      long long* stats, int* iters) {
+  RadauParams P = *P0;
+  P.sens_npar = n_par;
+  for (int k = 0; k < n_par; k++) P.sens_par[k] = par_index[k];
+  switch (ham_id) {
+    case HAM_HARMONIC: run_sens<HamHarmonic>(P, y0, tspan, M, y_out, S_out, stats, iters, Sp_out); return 0;
+    case HAM_VDP: run_sens<HamVdp>(P, y0, tspan, M, y_out, S_out, stats, iters, Sp_out); return 0;
+    case HAM_VDP_PMP_SMOOTH: run_sens<HamVdpPmp<false>>(P, y0, tspan, M, y_out, S_out, stats, iters, Sp_out); return 0;
   }
   return -1;
 }

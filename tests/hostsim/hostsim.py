@@ -71,8 +71,8 @@ def solve_mlp(par, sign, y0, tspan, opts, oracle_lib):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, work=work)
 
 
-def solve_sens(ham, par, sign, y0, tspan, opts):
-    """forward sensitivities d y / d y0 by the CUDA core's sens_step, on the CPU"""
+def solve_sens(ham, par, sign, y0, tspan, opts, par_dirs=()):
+    """forward sensitivities d y / d y0 (and d y / d par[k], k in par_dirs) by the CUDA core's sens_step, on the CPU"""
     build()
     lib = C.CDLL(_SO)
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
@@ -84,6 +84,14 @@ def solve_sens(ham, par, sign, y0, tspan, opts):
     S = np.empty((M, ny, ny))
     stats = np.empty((M, 8), dtype=np.int64)
     iters = np.empty(M, dtype=np.int32)
+    if par_dirs:
+        Sp = np.empty((M, len(par_dirs), ny))
+        pidx = (C.c_int * len(par_dirs))(*par_dirs)
+        rc = lib.hostsim_solve_sens_par(C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), C.c_int(len(par_dirs)),
+                                        pidx, _dp(y), _dp(S), _dp(Sp), stats.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                        iters.ctypes.data_as(C.POINTER(C.c_int)))
+        assert rc == 0
+        return dict(y=y, sens=S, spar=Sp.transpose(0, 2, 1).copy(), stats=stats, iters=iters)
     rc = lib.hostsim_solve_sens(C.c_int(HAM[ham]), P, _dp(y0), _dp(tspan), C.c_longlong(M), _dp(y), _dp(S),
                                 stats.ctypes.data_as(C.POINTER(C.c_longlong)), iters.ctypes.data_as(C.POINTER(C.c_int)))
     assert rc == 0

@@ -68,6 +68,42 @@ def test_cuda_core_sens_step_on_host_vs_oracle():
     assert np.allclose(hh["sens"][0], np.array([[c, -s], [s, c]]), atol=1e-8)
 
 
+def _hostsim():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import hostsim
+    return hostsim
+
+
+@pytest.mark.parametrize("ham,par,k,sign,mk,y0", [
+    ("vdp", [3.0], 0, +1, lambda p: problems.vdp(p[0], +1), [[1.0, 1.0, 2.0, 0.0], [0.5, -1.0, 1.7, 0.2]]),
+    ("harmonic", [1.3], 0, -1, lambda p: problems.harmonic(p[0], -1), [[0.3, -0.7], [1.0, 0.2]])])
+def test_cuda_core_parameter_direction_on_host_vs_finite_differences(ham, par, k, sign, mk, y0):
+    """d y(tf) / d par_k by the device code (sens_step + ham_dpar: one more hyper-dual variable of H), run on the host,
+    against central differences IN THE PARAMETER of the oracle solver -- the reference's check of its mu direction
+    (tests/cpp/ode_solver_test.cpp:630-700, rtol 1e-3); the state directions and the real part do not notice"""
+    hostsim = _hostsim()
+    op = jb.OptionsTe(RelTol=1e-9, AbsTol=1e-12, MaxNbrStep=100000)
+    y0 = np.array(y0)
+    tf = 4.0
+    ts = np.tile(np.array([0.0, tf]), (2, 1))
+    h = hostsim.solve_sens(ham, par, sign, y0, ts, op, par_dirs=[k])
+    h0 = hostsim.solve_sens(ham, par, sign, y0, ts, op)
+    assert np.array_equal(h["sens"], h0["sens"]) and np.array_equal(h["y"], h0["y"]) and np.array_equal(h["stats"], h0["stats"])
+    oo = RadauOptions(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=100000)
+    for m in range(2):
+        e = 1e-6 * max(1.0, abs(par[k]))
+        pp, pm = list(par), list(par)
+        pp[k] += e
+        pm[k] -= e
+        fp, jp = mk(pp)
+        fm, jm = mk(pm)
+        fd = (radau_solve(fp, jp, 0.0, tf, y0[m].copy(), oo).y - radau_solve(fm, jm, 0.0, tf, y0[m].copy(), oo).y) / (2 * e)
+        assert np.abs(fd).max() > 1e-3
+        assert np.allclose(h["spar"][m, :, 0], fd, rtol=1e-4, atol=1e-5 * np.abs(fd).max())
+
+
 # ------------------------------------------------------------------ GPU
 DEV = "cuda:0"
 
@@ -90,6 +126,104 @@ def test_gpu_real_part_is_bitwise_the_plain_solve(fixed):
     p.solve()
     assert torch.equal(r.y, p.y) and torch.equal(r.stats.raw, p.stats.raw) and torch.equal(r.h, p.h) and torch.equal(r.nstg, p.nstg)
     assert bool((r.sens_iters > 0).all()) and bool(torch.isfinite(r.yd).all())
+
+
+@pytest.mark.gpu
+def test_gpu_variable_order_epochs_equal_the_all_orders_core_bitwise():
+    """variable order runs through the order-homogeneous epochs (epoch_sens_kernel) with S parked in the result matrix
+    between epochs; the same core integrated in one go on the host (hostsim: integrate<Ham, 4, 7, true> + sens_step) must
+    give the same bits: states, counters AND sensitivities"""
+    hostsim = _hostsim()
+    cfg = configs.c2_vdp(M=96)
+    r = gpu_sens(cfg)
+    h = hostsim.solve_sens("vdp", [1000.0], +1, cfg["y0"].numpy(), cfg["tspan"].numpy(), cfg["options"])
+    assert np.array_equal(r.y.cpu().numpy(), h["y"])
+    assert np.array_equal(r.stats.raw.cpu().numpy(), h["stats"])
+    assert np.array_equal(r.yd.cpu().numpy().reshape(96, 16), h["sens"].reshape(96, 16))
+    assert np.array_equal(r.sens_iters.cpu().numpy(), h["iters"])
+    assert len(set(r.nstg.cpu().tolist())) >= 1 and int(r.stats.raw[:, 0].min()) > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixed", [True, False])
+def test_gpu_reference_sensitivity_test_layout(fixed):
+    """the reference's RadauTedTest.SensitivityTest (tests/cpp/ode_solver_test.cpp:620-770): vdP with mu = 1 + 0.001 i,
+    y(0) = (2 + 1e-4 i, 0), tf = 6, RelTol 1e-6 / AbsTol 1e-9, dual directions = the initial state, mu and the final
+    time, each checked against central differences of the solver at the reference's rtol (1e-3 ... 1e-4).  Here in
+    Hamiltonian form (costates ride along), mu as a PARAMETER direction, differences taken with the GPU solver."""
+    M = 8
+    tf = 6.0
+    op = jb.OptionsTe(RelTol=1e-6, AbsTol=1e-9)
+    if fixed:
+        op.MinNbrStg = op.MaxNbrStg = 3
+    fdop = jb.OptionsTe(RelTol=1e-11, AbsTol=1e-13, MaxNbrStep=1000000)
+    ts = torch.tensor([0.0, tf], dtype=torch.float64, device=DEV).repeat(M, 1)
+    for i in (0, 5):
+        mu = 1.0 + 0.001 * i
+        dyn = jb.HamiltonianSystem(jb.VanDerPol(mu), +1)
+        y0 = torch.tensor([1.0, 1.0, 2.0 + 1e-4 * i, 0.0], dtype=torch.float64, device=DEV).repeat(M, 1)
+        r = jb.RadauTeD(dyn, dyn.jacobian, ts, y0, op, par_dirs=[0])
+        assert bool((r.solve() == 0).all())
+        full = r.yd_full()
+        assert tuple(full.shape) == (M, 4, 4 + 1 + 1)
+        # mu direction: central differences in the parameter
+        e = 1e-6
+        yp = jb.RadauTe(jb.HamiltonianSystem(jb.VanDerPol(mu + e), +1), None, ts, y0, fdop)
+        ym = jb.RadauTe(jb.HamiltonianSystem(jb.VanDerPol(mu - e), +1), None, ts, y0, fdop)
+        yp.solve()
+        ym.solve()
+        fd_mu = (yp.y - ym.y) / (2 * e)
+        assert torch.allclose(full[:, :, 4], fd_mu, rtol=1e-3, atol=1e-3 * float(fd_mu.abs().max()))
+        # final-time direction
+        tp, tm = ts.clone(), ts.clone()
+        tp[:, 1] += 1e-6
+        tm[:, 1] -= 1e-6
+        a = jb.RadauTe(dyn, None, tp, y0, fdop)
+        b = jb.RadauTe(dyn, None, tm, y0, fdop)
+        a.solve()
+        b.solve()
+        fd_t = (a.y - b.y) / 2e-6
+        assert torch.allclose(full[:, :, 5], fd_t, rtol=1e-4, atol=1e-4 * float(fd_t.abs().max()))
+        # x1(0) direction
+        hh = 1e-7
+        ypl, ymi = y0.clone(), y0.clone()
+        ypl[:, 2] += hh
+        ymi[:, 2] -= hh
+        a = jb.RadauTe(dyn, None, ts, ypl, fdop)
+        b = jb.RadauTe(dyn, None, ts, ymi, fdop)
+        a.solve()
+        b.solve()
+        fd_x = (a.y - b.y) / (2 * hh)
+        assert torch.allclose(full[:, :, 2], fd_x, rtol=1e-3, atol=1e-3 * float(fd_x.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixed", [True, False])
+def test_gpu_parameter_direction_equals_the_host_run_bitwise(fixed):
+    hostsim = _hostsim()
+    cfg = configs.c2_vdp(M=48, mu=30.0, fixed_order=fixed)
+    cfg["tspan"][:, 1] = 20.0
+    dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+    r = jb.RadauTeD(dyn, dyn.jacobian, cfg["tspan"].to(DEV), cfg["y0"].to(DEV), cfg["options"], par_dirs=[0])
+    r.solve()
+    h = hostsim.solve_sens("vdp", [30.0], +1, cfg["y0"].numpy(), cfg["tspan"].numpy(), cfg["options"], par_dirs=[0])
+    assert np.array_equal(r.y.cpu().numpy(), h["y"]) and np.array_equal(r.yd.cpu().numpy(), h["sens"])
+    assert np.array_equal(r.ypar.cpu().numpy(), h["spar"])
+    with pytest.raises(ValueError, match="out of range"):
+        jb.RadauTeD(dyn, dyn.jacobian, cfg["tspan"].to(DEV), cfg["y0"].to(DEV), cfg["options"], par_dirs=[1]).solve()
+
+
+@pytest.mark.gpu
+def test_gpu_variable_order_large_batch_sorted_epochs():
+    """>= 65,536 rows: the epoch lists are regime-sorted in H(y0) order; a sample must equal the small-batch solve"""
+    cfg = configs.c2_vdp(M=1 << 16)
+    r = gpu_sens(cfg)
+    assert bool((r.res == 0).all())
+    idx = torch.arange(0, 1 << 16, 997)
+    sub = dict(cfg, y0=cfg["y0"][idx], tspan=cfg["tspan"][idx])
+    q = gpu_sens(sub)
+    assert torch.equal(r.y[idx.to(DEV)], q.y) and torch.equal(r.yd[idx.to(DEV)], q.yd)
+    assert torch.equal(r.stats.raw[idx.to(DEV)], q.stats.raw)
 
 
 @pytest.mark.gpu
