@@ -9,15 +9,20 @@
 //                    (2 transposed GEMMs + the 128x16 output product) -> ydot = [sg dH/dx ; dH/dp]
 //   mlp_hess_kernel  4 trajectories x 16 tangent directions per CTA: forward-over-reverse (tangent
 //                    forward 2 GEMMs, tangent reverse 2 GEMMs + output product) -> the 16x16 Jacobian
-// One CTA = 256 threads = two warps per SM sub-partition, each thread owns a 4x8 register tile of
-// the 64x128 layer output (32 independent DFMA chains: the FP64 pipe is the only bound); the
-// activations of the tile stay in shared memory ([feature][row], 3 x 64 KB) from the first layer
-// to the last, weights stream from L2 in 16-row chunks through a cp.async double buffer.
+// One CTA = 256 threads = two warps per SM sub-partition.  The layer products run on the FP64 TENSOR CORES
+// (mma.sync.m8n8k4.f64, "DMMA"): a warp owns a 32-feature x 32-row block of the 64 x 128 layer output = 4 x 4 mma
+// tiles, 32 accumulators per thread; per k-step of 4 it loads 4 weight fragments + 4 activation fragments (one double
+// each, bank-conflict-free through an XOR swizzle of both shared-memory operands) for 16 DMMAs = 128 DFMA-equivalents --
+// 6x fewer shared-memory instructions and 8x fewer issue slots per multiply-add than the register-tiled DFMA GEMM it
+// replaces (54-61 % FP64-pipe active).  The activations of the tile stay in shared memory ([feature][row], 3 x 64 KB)
+// from the first layer to the last, weights stream from L2 in 16-row chunks through a cp.async double buffer.
 //
 // ARITHMETIC CONTRACT (mirrored by oracle/c/radau_oracle.c mlp_eval_mirror): every dot product is
 // ONE fma chain in increasing index order, seeded with the bias (forward) or 0.0 (transposed);
-// tanh = det_tanh; 1 - a^2 = fma(-a, a, 1).  The register tiling changes which thread owns an
-// output, never the order of its sum, so results are bit-identical to the scalar mirror.
+// tanh = det_tanh; 1 - a^2 = fma(-a, a, 1).  DMMA keeps that contract: D = A B + C is, per output, the chain
+// fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0, c)))) -- measured on B200 against scalar fma on 262,144 outputs with a
+// 2^40 dynamic range, all bit-identical (profiles/probes/dmma_order.cu) -- and successive k-steps chain through the
+// accumulator, so results stay bit-identical to the scalar mirror.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -29,8 +34,7 @@ namespace mlp {
 
 constexpr int TR = 64;        // rows per CTA tile
 constexpr int KC = 16;        // weight rows per cp.async chunk (two barriers per chunk: fewer, larger chunks)
-constexpr int THREADS = 256;     // 2 warps per SM sub-partition: a lone warp cannot re-issue DFMAs back to back
-constexpr int RJ = 2;            // row groups per thread: register tile = (2 RJ) rows x 8 columns
+constexpr int THREADS = 256;     // 8 warps = 2 x 4 blocks of 32 rows x 32 features, two warps per SM sub-partition
 constexpr int ACT_WORDS = WD * TR;                                      // one activation buffer
 constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 224 KB
 
@@ -49,20 +53,28 @@ struct Weights {
   const double* W4;    // [128]
 };
 
-// thread -> register tile: rows {r0, r0+1} + 32 j (j < RJ), columns {c0, c0+1} + 32 j (j < 4);
-// within a warp 8 row pairs x 4 column pairs, so every shared-memory access is a full-width or
-// broadcast wavefront
+// Shared-memory operand layout: element (k, i) of a [K][LD] operand (activations: LD = TR rows; weights: LD = WD
+// features) lives at k * LD + (i ^ ((k & 3) << 2)).  A fragment load touches, per half-warp, 4 values of k x 4
+// consecutive i: without the swizzle those 16 doubles share 8 banks (LD * 8 bytes is a multiple of 128), with it they
+// are 16 distinct consecutive doubles = one conflict-free 128-byte wavefront.  Pairs (i even, i + 1) stay adjacent.
+__device__ __forceinline__ int swz(int k, int i) { return i ^ ((k & 3) << 2); }
+__device__ __forceinline__ int aidx(int c, int r) { return c * TR + swz(c, r); }   // activation buffers [feature][row]
+
+// thread -> accumulators: warp w owns rows 32 (w & 1) .., features 32 (w >> 1) ..; mma tile (j, f), j, f < 4, covers rows
+// rb + 8 j .. + 7 and features cb + 8 f .. + 7; this lane holds, of each tile, feature col(f) and the row pair rowp(j), +1
 struct TileMap {
-  int r0, c0;
+  int rb, cb, lq, lr;   // lq = lane >> 2 (fragment row / column index), lr = lane & 3 (k index within a k-step)
   __device__ TileMap() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    r0 = ((lane & 7) + 8 * (warp & 1)) * 2;
-    c0 = ((warp >> 1) * 4 + (lane >> 3)) * 2;
+    rb = 32 * (warp & 1);
+    cb = 32 * (warp >> 1);
+    lq = lane >> 2;
+    lr = lane & 3;
   }
-  __device__ __forceinline__ int row(int j, int e) const { return r0 + 32 * j + e; }   // j < RJ, e < 2
-  __device__ __forceinline__ int col(int j, int e) const { return c0 + 32 * j + e; }   // j < 4
+  __device__ __forceinline__ int rowp(int j) const { return rb + 8 * j + 2 * lr; }   // even row of this lane's pair, j < 4
+  __device__ __forceinline__ int col(int f) const { return cb + 8 * f + lq; }        // f < 4
 };
-constexpr int NR = 2 * RJ;   // rows of the register tile
+constexpr int NJ = 4, NF = 4;   // mma tiles per warp: row tiles x feature tiles
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -72,10 +84,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// acc[ri][ci] += sum_k A[k][row(ri)] * B[k][col(ci)], k = 0..K-1 in order (one fma chain each).
-// A: shared [K][TR]; B: global [K][WD] (row-major, 16-byte aligned); wbuf: shared [2][KC][WD].
+// D (8 features x 8 rows) += A (8 features x 4 k: the weights) * B (4 k x 8 rows: the activations), FP64 tensor cores
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// acc[j][f][e] += sum_k A[k][rowp(j) + e] * B[k][col(f)], k = 0..K-1 in order (one fma chain each).
+// A: shared [K][TR], swizzled; B: global [K][WD] (row-major, 16-byte aligned); wbuf: shared [2][KC][WD], swizzled.
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const double* __restrict__ B, int K,
-                                          double* __restrict__ wbuf, const TileMap& tm, double (&acc)[NR][8]) {
+                                          double* __restrict__ wbuf, const TileMap& tm, double (&acc)[NJ][NF][2]) {
   const int nchunks = K / KC;
   auto issue = [&](int ch) {
     const double* src = B + (size_t)ch * KC * WD;
@@ -83,11 +101,14 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
 #pragma unroll
     for (int t = 0; t < (KC * WD / 2) / THREADS; t++) {
       const int o = (t * THREADS + threadIdx.x) * 2;
-      cp_async16(dst + o, src + o);
+      const int kk = o / WD, c = o % WD;
+      cp_async16(dst + kk * WD + swz(kk, c), src + o);
     }
     cp_async_commit();
   };
   issue(0);
+  // this lane's fragment offsets within a k-step (k = lr): weights (k, cb + 8 f + lq), activations (k, rb + 8 j + lq)
+  const int xs = tm.lr << 2;
   for (int ch = 0; ch < nchunks; ch++) {
     if (ch + 1 < nchunks) {
       issue(ch + 1);
@@ -96,27 +117,19 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
       cp_async_wait<0>();
     }
     __syncthreads();
-    const double* wb = wbuf + (ch & 1) * KC * WD;
-    const double* Ak = A + (size_t)ch * KC * TR;
+    const double* wb = wbuf + (ch & 1) * KC * WD + tm.lr * WD;
+    const double* Ak = A + (size_t)ch * KC * TR + tm.lr * TR;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk++) {
-      double a[NR], b[8];
+    for (int ks = 0; ks < KC / 4; ks++) {   // KC is a multiple of 4, so (k & 3) == lr for every k-step
+      double a[NF], b[NJ];
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double2 av = *reinterpret_cast<const double2*>(Ak + kk * TR + tm.r0 + 32 * j);
-        a[2 * j] = av.x;
-        a[2 * j + 1] = av.y;
-      }
+      for (int f = 0; f < NF; f++) a[f] = wb[ks * 4 * WD + ((tm.cb + 8 * f + tm.lq) ^ xs)];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double2 bv = *reinterpret_cast<const double2*>(wb + kk * WD + tm.c0 + 32 * j);
-        b[2 * j] = bv.x;
-        b[2 * j + 1] = bv.y;
-      }
+      for (int j = 0; j < NJ; j++) b[j] = Ak[ks * 4 * TR + ((tm.rb + 8 * j + tm.lq) ^ xs)];
 #pragma unroll
-      for (int ri = 0; ri < NR; ri++)
+      for (int j = 0; j < NJ; j++)
 #pragma unroll
-        for (int ci = 0; ci < 8; ci++) acc[ri][ci] = fma(b[ci], a[ri], acc[ri][ci]);
+        for (int f = 0; f < NF; f++) dmma(acc[j][f], a[f], b[j]);
     }
     __syncthreads();   // everyone is done with this chunk before it is overwritten
   }
@@ -133,21 +146,30 @@ __device__ __forceinline__ void output_product(const double* __restrict__ D, con
 #pragma unroll
   for (int c = 0; c < OC; c++) g[c] = 0.0;
   for (int i = 0; i < WD; i++) {
-    const double d = D[i * TR + r];
+    const double d = D[aidx(i, r)];
 #pragma unroll
     for (int c = 0; c < OC; c++) g[c] = fma(wbuf[i * NV + cb + c], d, g[c]);
   }
   __syncthreads();
 }
 
-// store the 8x8 register tile raw into a [feature][row] buffer
-__device__ __forceinline__ void store_tile(double* __restrict__ A, const TileMap& tm, const double (&acc)[NR][8]) {
+// store the accumulators raw into a [feature][row] buffer
+__device__ __forceinline__ void store_tile(double* __restrict__ A, const TileMap& tm, const double (&acc)[NJ][NF][2]) {
 #pragma unroll
-  for (int ci = 0; ci < 8; ci++)
+  for (int f = 0; f < NF; f++)
 #pragma unroll
-    for (int j = 0; j < RJ; j++)
-      *reinterpret_cast<double2*>(A + tm.col(ci >> 1, ci & 1) * TR + tm.r0 + 32 * j) =
-          make_double2(acc[2 * j][ci], acc[2 * j + 1][ci]);
+    for (int j = 0; j < NJ; j++)
+      *reinterpret_cast<double2*>(A + aidx(tm.col(f), tm.rowp(j))) = make_double2(acc[j][f][0], acc[j][f][1]);
+}
+
+template <class F>
+__device__ __forceinline__ void seed_acc(double (&acc)[NJ][NF][2], const TileMap& tm, F bias) {
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    const double b = bias(tm.col(f));
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[j][f][0] = acc[j][f][1] = b;
+  }
 }
 
 // a = tanh(a) over a whole buffer: a ROLLED loop (one copy of det_tanh in the instruction stream
@@ -224,94 +246,77 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
 #pragma unroll
       for (int u = 0; u < NV * TR / THREADS; u++) {
         const int o = threadIdx.x + u * THREADS;
-        A2[o] = (io.add || io.add_scalar) ? v[u] + ad[u] : v[u];
+        A2[aidx(o / TR, o & (TR - 1))] = (io.add || io.add_scalar) ? v[u] + ad[u] : v[u];
       }
     }
     __syncthreads();
-    double acc[NR][8];
+    double acc[NJ][NF][2];
     // ---- layer 1: a1 = tanh(W1 v + b1) -> A0
-#pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const double b = Wt.b1[tm.col(ci >> 1, ci & 1)];
-#pragma unroll
-      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
-    }
+    seed_acc(acc, tm, [&](int c) { return Wt.b1[c]; });
     gemm_tile(A2, Wt.W1t, NV, wbuf, tm, acc);
     store_tile(A0, tm, acc);
     __syncthreads();
     tanh_buffer(A0);
     __syncthreads();
     // ---- layer 2 -> A1
-#pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const double b = Wt.b2[tm.col(ci >> 1, ci & 1)];
-#pragma unroll
-      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
-    }
+    seed_acc(acc, tm, [&](int c) { return Wt.b2[c]; });
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
     store_tile(A1, tm, acc);
     __syncthreads();
     tanh_buffer(A1);
     __syncthreads();
     // ---- layer 3: a3 = tanh(.), d3 = W4 (1 - a3^2) -> A2
-#pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const double b = Wt.b3[tm.col(ci >> 1, ci & 1)];
-#pragma unroll
-      for (int ri = 0; ri < NR; ri++) acc[ri][ci] = b;
-    }
+    seed_acc(acc, tm, [&](int c) { return Wt.b3[c]; });
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
     store_tile(A2, tm, acc);
     __syncthreads();
     tanh_buffer(A2);
     __syncthreads();
     for (int o = threadIdx.x; o < ACT_WORDS; o += THREADS) {
-      const int r = o & (TR - 1), c = o / TR;
+      const int c = o / TR, r = swz(c, o & (TR - 1));   // physical slot o holds logical (feature c, row r)
       const double a3 = A2[o];
       if (io.act && s_traj[r] >= 0) io.act[((size_t)s_traj[r] * 5 + 2) * WD + c] = a3;
       A2[o] = s_w4[c] * fma(-a3, a3, 1.0);
     }
     __syncthreads();
     // ---- reverse through layer 3: q2 = W3^T d3, d2 = q2 (1 - a2^2) -> A1 (in place)
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    seed_acc(acc, tm, [](int) { return 0.0; });
     gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int ri = 0; ri < NR; ri++) {
-        const int r = tm.row(ri >> 1, ri & 1);
-        const double a2 = A1[c * TR + r], q2 = acc[ri][ci];
-        if (io.act && s_traj[r] >= 0) {
-          io.act[((size_t)s_traj[r] * 5 + 1) * WD + c] = a2;
-          io.act[((size_t)s_traj[r] * 5 + 4) * WD + c] = q2;
+      for (int j = 0; j < NJ; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int r = tm.rowp(j) + e;
+          const double a2 = A1[aidx(c, r)], q2 = acc[j][f][e];
+          if (io.act && s_traj[r] >= 0) {
+            io.act[((size_t)s_traj[r] * 5 + 1) * WD + c] = a2;
+            io.act[((size_t)s_traj[r] * 5 + 4) * WD + c] = q2;
+          }
+          A1[aidx(c, r)] = q2 * fma(-a2, a2, 1.0);
         }
-        A1[c * TR + r] = q2 * fma(-a2, a2, 1.0);
-      }
     }
     __syncthreads();
     // ---- reverse through layer 2: q1 = W2^T d2, d1 = q1 (1 - a1^2) -> A0 (in place)
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    seed_acc(acc, tm, [](int) { return 0.0; });
     gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int ri = 0; ri < NR; ri++) {
-        const int r = tm.row(ri >> 1, ri & 1);
-        const double a1 = A0[c * TR + r], q1 = acc[ri][ci];
-        if (io.act && s_traj[r] >= 0) {
-          io.act[((size_t)s_traj[r] * 5 + 0) * WD + c] = a1;
-          io.act[((size_t)s_traj[r] * 5 + 3) * WD + c] = q1;
+      for (int j = 0; j < NJ; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int r = tm.rowp(j) + e;
+          const double a1 = A0[aidx(c, r)], q1 = acc[j][f][e];
+          if (io.act && s_traj[r] >= 0) {
+            io.act[((size_t)s_traj[r] * 5 + 0) * WD + c] = a1;
+            io.act[((size_t)s_traj[r] * 5 + 3) * WD + c] = q1;
+          }
+          A0[aidx(c, r)] = q1 * fma(-a1, a1, 1.0);
         }
-        A0[c * TR + r] = q1 * fma(-a1, a1, 1.0);
-      }
     }
     __syncthreads();
     // ---- g = W1^T d1 ; ydot = [sign dH/dx ; dH/dp]
@@ -346,14 +351,14 @@ struct HessIO {
   double sign;
 };
 
-// the epilogue operands of one layer (saved activations of this thread's 8 columns x RJ
-// trajectories), loaded BEFORE the layer's GEMM so that their L2 latency hides behind it
-__device__ __forceinline__ void prefetch_act(const double* const (&actj)[RJ], int layer, const TileMap& tm,
-                                             double (&v)[RJ][8]) {
+// the epilogue operands of one layer (saved activations of this thread's 4 features x 2 trajectory slots), loaded
+// BEFORE the layer's GEMM so that their L2 latency hides behind it
+__device__ __forceinline__ void prefetch_act(const double* const (&actj)[2], int layer, const TileMap& tm,
+                                             double (&v)[2][NF]) {
 #pragma unroll
-  for (int j = 0; j < RJ; j++)
+  for (int jj = 0; jj < 2; jj++)
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) v[j][ci] = __ldg(actj[j] + layer * WD + tm.col(ci >> 1, ci & 1));
+    for (int f = 0; f < NF; f++) v[jj][f] = __ldg(actj[jj] + layer * WD + tm.col(f));
 }
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, const HessIO io) {
@@ -373,107 +378,95 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
       s_traj[threadIdx.x] = q < n ? (io.list ? io.list[q] : q) : -1;
     }
     __syncthreads();
-    // rows of this thread: row r = r0 + 32 j + e  ->  trajectory slot r / 16 = (r0 >> 4) + 2 j,
-    // tangent direction k = (r0 & 15) + e
-    const int k0 = tm.r0 & 15;
-    const double* actj[RJ];
+    // rows of this thread: row r = rowp(j) + e = rb + 8 j + 2 lr + e  ->  trajectory slot r / 16 = (rb >> 4) + (j >> 1),
+    // tangent direction k = r & 15 = 8 (j & 1) + 2 lr + e
+    const double* actj[2];
 #pragma unroll
-    for (int j = 0; j < RJ; j++) {
-      const int sl = (tm.r0 >> 4) + 2 * j;
-      actj[j] = io.act + (size_t)(s_traj[sl] < 0 ? s_traj[0] : s_traj[sl]) * 5 * WD;
+    for (int jj = 0; jj < 2; jj++) {
+      const int sl = (tm.rb >> 4) + jj;
+      actj[jj] = io.act + (size_t)(s_traj[sl] < 0 ? s_traj[0] : s_traj[sl]) * 5 * WD;
     }
     // ---- ta1[c][row] = (1 - a1^2) W1[c][k] -> A0
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double a1 = actj[j][0 * WD + c];
+      for (int j = 0; j < NJ; j++) {
+        const double a1 = actj[j >> 1][0 * WD + c];
         const double e1 = fma(-a1, a1, 1.0);
-        *reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 32 * j) =
+        const int k0 = 8 * (j & 1) + 2 * tm.lr;
+        *reinterpret_cast<double2*>(A0 + aidx(c, tm.rowp(j))) =
             make_double2(e1 * Wt.W1[c * NV + k0], e1 * Wt.W1[c * NV + k0 + 1]);
       }
     }
     __syncthreads();
-    double acc[NR][8];
+    double acc[NJ][NF][2];
     // ---- ta2 = (1 - a2^2) (W2 ta1) -> A1
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
-    double pa[RJ][8], pq[RJ][8];
+    seed_acc(acc, tm, [](int) { return 0.0; });
+    double pa[2][NF], pq[2][NF];
     prefetch_act(actj, 1, tm, pa);
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double a2 = pa[j][ci];
+      for (int j = 0; j < NJ; j++) {
+        const double a2 = pa[j >> 1][f];
         const double e2 = fma(-a2, a2, 1.0);
-        *reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j) = make_double2(e2 * acc[2 * j][ci], e2 * acc[2 * j + 1][ci]);
+        *reinterpret_cast<double2*>(A1 + aidx(c, tm.rowp(j))) = make_double2(e2 * acc[j][f][0], e2 * acc[j][f][1]);
       }
     }
     __syncthreads();
     // ---- ta3 = (1 - a3^2) (W3 ta2);  td3 = W4 ((-2 a3) ta3) -> A2
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    seed_acc(acc, tm, [](int) { return 0.0; });
     prefetch_act(actj, 2, tm, pa);
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
       const double w4 = s_w4[c];
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double a3 = pa[j][ci];
+      for (int j = 0; j < NJ; j++) {
+        const double a3 = pa[j >> 1][f];
         const double e3 = fma(-a3, a3, 1.0), m3 = -2.0 * a3;
-        const double t0 = e3 * acc[2 * j][ci], t1 = e3 * acc[2 * j + 1][ci];
-        *reinterpret_cast<double2*>(A2 + c * TR + tm.r0 + 32 * j) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
+        const double t0 = e3 * acc[j][f][0], t1 = e3 * acc[j][f][1];
+        *reinterpret_cast<double2*>(A2 + aidx(c, tm.rowp(j))) = make_double2(w4 * (m3 * t0), w4 * (m3 * t1));
       }
     }
     __syncthreads();
     // ---- td2 = (W3^T td3)(1 - a2^2) + q2 ((-2 a2) ta2) -> A1 (in place)
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    seed_acc(acc, tm, [](int) { return 0.0; });
     prefetch_act(actj, 1, tm, pa);
     prefetch_act(actj, 4, tm, pq);
     gemm_tile(A2, Wt.W3, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double a2 = pa[j][ci], q2 = pq[j][ci];
+      for (int j = 0; j < NJ; j++) {
+        const double a2 = pa[j >> 1][f], q2 = pq[j >> 1][f];
         const double e2 = fma(-a2, a2, 1.0), m2 = -2.0 * a2;
-        double2* p = reinterpret_cast<double2*>(A1 + c * TR + tm.r0 + 32 * j);
+        double2* p = reinterpret_cast<double2*>(A1 + aidx(c, tm.rowp(j)));
         const double2 ta2 = *p;
-        *p = make_double2(fma(q2, m2 * ta2.x, acc[2 * j][ci] * e2), fma(q2, m2 * ta2.y, acc[2 * j + 1][ci] * e2));
+        *p = make_double2(fma(q2, m2 * ta2.x, acc[j][f][0] * e2), fma(q2, m2 * ta2.y, acc[j][f][1] * e2));
       }
     }
     __syncthreads();
     // ---- td1 = (W2^T td2)(1 - a1^2) + q1 ((-2 a1) ta1) -> A0 (in place)
-#pragma unroll
-    for (int ri = 0; ri < NR; ri++)
-#pragma unroll
-      for (int ci = 0; ci < 8; ci++) acc[ri][ci] = 0.0;
+    seed_acc(acc, tm, [](int) { return 0.0; });
     prefetch_act(actj, 0, tm, pa);
     prefetch_act(actj, 3, tm, pq);
     gemm_tile(A1, Wt.W2, WD, wbuf, tm, acc);
 #pragma unroll
-    for (int ci = 0; ci < 8; ci++) {
-      const int c = tm.col(ci >> 1, ci & 1);
+    for (int f = 0; f < NF; f++) {
+      const int c = tm.col(f);
 #pragma unroll
-      for (int j = 0; j < RJ; j++) {
-        const double a1 = pa[j][ci], q1 = pq[j][ci];
+      for (int j = 0; j < NJ; j++) {
+        const double a1 = pa[j >> 1][f], q1 = pq[j >> 1][f];
         const double e1 = fma(-a1, a1, 1.0), m1 = -2.0 * a1;
-        double2* p = reinterpret_cast<double2*>(A0 + c * TR + tm.r0 + 32 * j);
+        double2* p = reinterpret_cast<double2*>(A0 + aidx(c, tm.rowp(j)));
         const double2 ta1 = *p;
-        *p = make_double2(fma(q1, m1 * ta1.x, acc[2 * j][ci] * e1), fma(q1, m1 * ta1.y, acc[2 * j + 1][ci] * e1));
+        *p = make_double2(fma(q1, m1 * ta1.x, acc[j][f][0] * e1), fma(q1, m1 * ta1.y, acc[j][f][1] * e1));
       }
     }
     __syncthreads();
