@@ -32,11 +32,24 @@
 namespace jb {
 namespace mlp {
 
-constexpr int TR = 64;        // rows per CTA tile
-constexpr int KC = 16;        // weight rows per cp.async chunk (two barriers per chunk: fewer, larger chunks)
-constexpr int THREADS = 256;     // 8 warps = 2 x 4 blocks of 32 rows x 32 features, two warps per SM sub-partition
+// Tile shape (JB_MLP_CFG):
+//   2            64 rows per CTA, 512 threads = 16 warps (4 per SM sub-partition), 224 KB, one CTA per SM: the GEMM loops
+//                saturate the FP64 tensor pipe with 2 warps per sub-partition already; the phases between them (tanh sweeps =
+//                dependent fma chains, epilogues, output product, chunk barriers) need the extra warps to hide latency
+//   1            32 rows per CTA, 256 threads, 112 KB, TWO CTAs per SM (one CTA's pipe-light phase overlaps the other's GEMM):
+//                twice the L2 -> shared-memory weight traffic per row (every CTA streams all weights per tile)
+//   0 (default)  64 rows, 256 threads, one CTA per SM.  Measured on config 4 (2^20 rows, with the branch-free tanh): 0 / 1 / 2 =
+//                1008.8 / 1009.1 / 1023.6 ms per solve -- the tile kernels are no longer what separates the shapes
+#ifndef JB_MLP_CFG
+#define JB_MLP_CFG 0
+#endif
+constexpr int TR = JB_MLP_CFG == 1 ? 32 : 64;          // rows per CTA tile
+constexpr int KC = JB_MLP_CFG == 1 ? 8 : 16;           // weight rows per cp.async chunk
+constexpr int CTAS_PER_SM = JB_MLP_CFG == 1 ? 2 : 1;
+constexpr int THREADS = JB_MLP_CFG == 2 ? 512 : 256;   // warps = 4 feature blocks (32 features each) x WR row blocks
+constexpr int WR = THREADS / 32 / 4;
 constexpr int ACT_WORDS = WD * TR;                                      // one activation buffer
-constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 224 KB
+constexpr size_t SMEM_BYTES = sizeof(double) * (3 * ACT_WORDS + 2 * KC * WD);   // 112 KB (TR = 32) / 224 KB (TR = 64)
 
 // device-resident weights of one Hamiltonian (both orientations of every matrix, k-major for the
 // GEMM that consumes it)
@@ -60,21 +73,23 @@ struct Weights {
 __device__ __forceinline__ int swz(int k, int i) { return i ^ ((k & 3) << 2); }
 __device__ __forceinline__ int aidx(int c, int r) { return c * TR + swz(c, r); }   // activation buffers [feature][row]
 
-// thread -> accumulators: warp w owns rows 32 (w & 1) .., features 32 (w >> 1) ..; mma tile (j, f), j, f < 4, covers rows
-// rb + 8 j .. + 7 and features cb + 8 f .. + 7; this lane holds, of each tile, feature col(f) and the row pair rowp(j), +1
+// thread -> accumulators: warp w owns rows (TR / WR) (w % WR) .., features 32 (w / WR) ..; mma tile (j, f), j < NJ, f < NF,
+// covers rows rb + 8 j .. + 7 and features cb + 8 f .. + 7; this lane holds, of each tile, feature col(f) and the row
+// pair rowp(j), +1
 struct TileMap {
   int rb, cb, lq, lr;   // lq = lane >> 2 (fragment row / column index), lr = lane & 3 (k index within a k-step)
   __device__ TileMap() {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    rb = 32 * (warp & 1);
-    cb = 32 * (warp >> 1);
+    rb = (TR / WR) * (warp % WR);
+    cb = 32 * (warp / WR);
     lq = lane >> 2;
     lr = lane & 3;
   }
-  __device__ __forceinline__ int rowp(int j) const { return rb + 8 * j + 2 * lr; }   // even row of this lane's pair, j < 4
+  __device__ __forceinline__ int rowp(int j) const { return rb + 8 * j + 2 * lr; }   // even row of this lane's pair, j < NJ
   __device__ __forceinline__ int col(int f) const { return cb + 8 * f + lq; }        // f < 4
 };
-constexpr int NJ = 4, NF = 4;   // mma tiles per warp: row tiles x feature tiles
+constexpr int NJ = TR / WR / 8, NF = 4;   // mma tiles per warp: row tiles x feature tiles
+constexpr int NSL = (NJ + 1) / 2;      // Hessian kernel: trajectory slots (16 tangent rows each) a thread's rows belong to
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -172,18 +187,18 @@ __device__ __forceinline__ void seed_acc(double (&acc)[NJ][NF][2], const TileMap
   }
 }
 
-// a = tanh(a) over a whole buffer: a ROLLED loop (one copy of det_tanh in the instruction stream
-// instead of 32 per layer), TI independent elements in flight per thread -- det_tanh is one long
+// a = tanh(a) over a whole buffer: a ROLLED loop (one copy of det_tanh_t in the instruction stream
+// instead of 32 per layer), TI independent elements in flight per thread -- det_tanh_t is one long
 // dependent FMA chain, the FP64 pipe needs ~16 of them per sub-partition to stay busy
 constexpr int TI = 8;
-__device__ __forceinline__ void tanh_buffer(double* __restrict__ A) {
+__device__ __forceinline__ void tanh_buffer(double* __restrict__ A, const double* __restrict__ tab) {
 #pragma unroll 1
   for (int o = threadIdx.x; o < ACT_WORDS; o += TI * THREADS) {
     double t[TI];
 #pragma unroll
     for (int u = 0; u < TI; u++) t[u] = A[o + u * THREADS];
 #pragma unroll
-    for (int u = 0; u < TI; u++) t[u] = det_tanh(t[u]);
+    for (int u = 0; u < TI; u++) t[u] = det_tanh_t(t[u], tab);
 #pragma unroll
     for (int u = 0; u < TI; u++) A[o + u * THREADS] = t[u];
   }
@@ -206,17 +221,17 @@ struct GradIO {
   double sign;             // costate sign: ydot = [sign dH/dx ; dH/dp]
 };
 
-__global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, const GradIO io) {
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM) mlp_grad_kernel(const Weights Wt, const GradIO io) {
   extern __shared__ __align__(16) double smem[];
   double* A0 = smem;
   double* A1 = A0 + ACT_WORDS;
   double* A2 = A1 + ACT_WORDS;
   double* wbuf = A2 + ACT_WORDS;
   __shared__ int s_traj[TR], s_stage[TR];
-  __shared__ double s_w4[WD];
+  __shared__ double s_tab[32];   // 2^(j/32) for det_tanh_t: a run-time-indexed table belongs in shared memory
   const int n_rows = io.n_rows_dev ? *io.n_rows_dev : io.n_rows;
   const TileMap tm;
-  if (threadIdx.x < WD) s_w4[threadIdx.x] = Wt.W4[threadIdx.x];
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = det_exp2_tab()[threadIdx.x];
   for (int tile = blockIdx.x; (long long)tile * TR < n_rows; tile += gridDim.x) {
     const int base = tile * TR;
     if (threadIdx.x < TR) {
@@ -256,27 +271,27 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_grad_kernel(const Weights Wt, 
     gemm_tile(A2, Wt.W1t, NV, wbuf, tm, acc);
     store_tile(A0, tm, acc);
     __syncthreads();
-    tanh_buffer(A0);
+    tanh_buffer(A0, s_tab);
     __syncthreads();
     // ---- layer 2 -> A1
     seed_acc(acc, tm, [&](int c) { return Wt.b2[c]; });
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
     store_tile(A1, tm, acc);
     __syncthreads();
-    tanh_buffer(A1);
+    tanh_buffer(A1, s_tab);
     __syncthreads();
     // ---- layer 3: a3 = tanh(.), d3 = W4 (1 - a3^2) -> A2
     seed_acc(acc, tm, [&](int c) { return Wt.b3[c]; });
     gemm_tile(A1, Wt.W3t, WD, wbuf, tm, acc);
     store_tile(A2, tm, acc);
     __syncthreads();
-    tanh_buffer(A2);
+    tanh_buffer(A2, s_tab);
     __syncthreads();
     for (int o = threadIdx.x; o < ACT_WORDS; o += THREADS) {
       const int c = o / TR, r = swz(c, o & (TR - 1));   // physical slot o holds logical (feature c, row r)
       const double a3 = A2[o];
       if (io.act && s_traj[r] >= 0) io.act[((size_t)s_traj[r] * 5 + 2) * WD + c] = a3;
-      A2[o] = s_w4[c] * fma(-a3, a3, 1.0);
+      A2[o] = __ldg(Wt.W4 + c) * fma(-a3, a3, 1.0);
     }
     __syncthreads();
     // ---- reverse through layer 3: q2 = W3^T d3, d2 = q2 (1 - a2^2) -> A1 (in place)
@@ -353,36 +368,35 @@ struct HessIO {
 
 // the epilogue operands of one layer (saved activations of this thread's 4 features x 2 trajectory slots), loaded
 // BEFORE the layer's GEMM so that their L2 latency hides behind it
-__device__ __forceinline__ void prefetch_act(const double* const (&actj)[2], int layer, const TileMap& tm,
-                                             double (&v)[2][NF]) {
+__device__ __forceinline__ void prefetch_act(const double* const (&actj)[NSL], int layer, const TileMap& tm,
+                                             double (&v)[NSL][NF]) {
 #pragma unroll
-  for (int jj = 0; jj < 2; jj++)
+  for (int jj = 0; jj < NSL; jj++)
 #pragma unroll
     for (int f = 0; f < NF; f++) v[jj][f] = __ldg(actj[jj] + layer * WD + tm.col(f));
 }
 
-__global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, const HessIO io) {
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM) mlp_hess_kernel(const Weights Wt, const HessIO io) {
   extern __shared__ __align__(16) double smem[];
   double* A0 = smem;
   double* A1 = A0 + ACT_WORDS;
   double* A2 = A1 + ACT_WORDS;
   double* wbuf = A2 + ACT_WORDS;
-  __shared__ int s_traj[4];
-  __shared__ double s_w4[WD];
+  constexpr int TPT = TR / 16;   // trajectories per tile (16 tangent rows each)
+  __shared__ int s_traj[TPT];
   const int n = io.n_dev ? *io.n_dev : io.n;
   const TileMap tm;
-  if (threadIdx.x < WD) s_w4[threadIdx.x] = Wt.W4[threadIdx.x];
-  for (int tile = blockIdx.x; (long long)tile * 4 < n; tile += gridDim.x) {
-    if (threadIdx.x < 4) {
-      const int q = tile * 4 + threadIdx.x;
+  for (int tile = blockIdx.x; (long long)tile * TPT < n; tile += gridDim.x) {
+    if (threadIdx.x < TPT) {
+      const int q = tile * TPT + threadIdx.x;
       s_traj[threadIdx.x] = q < n ? (io.list ? io.list[q] : q) : -1;
     }
     __syncthreads();
     // rows of this thread: row r = rowp(j) + e = rb + 8 j + 2 lr + e  ->  trajectory slot r / 16 = (rb >> 4) + (j >> 1),
     // tangent direction k = r & 15 = 8 (j & 1) + 2 lr + e
-    const double* actj[2];
+    const double* actj[NSL];
 #pragma unroll
-    for (int jj = 0; jj < 2; jj++) {
+    for (int jj = 0; jj < NSL; jj++) {
       const int sl = (tm.rb >> 4) + jj;
       actj[jj] = io.act + (size_t)(s_traj[sl] < 0 ? s_traj[0] : s_traj[sl]) * 5 * WD;
     }
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
     double acc[NJ][NF][2];
     // ---- ta2 = (1 - a2^2) (W2 ta1) -> A1
     seed_acc(acc, tm, [](int) { return 0.0; });
-    double pa[2][NF], pq[2][NF];
+    double pa[NSL][NF], pq[NSL][NF];
     prefetch_act(actj, 1, tm, pa);
     gemm_tile(A0, Wt.W2t, WD, wbuf, tm, acc);
 #pragma unroll
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_hess_kernel(const Weights Wt, 
 #pragma unroll
     for (int f = 0; f < NF; f++) {
       const int c = tm.col(f);
-      const double w4 = s_w4[c];
+      const double w4 = __ldg(Wt.W4 + c);
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         const double a3 = pa[j >> 1][f];

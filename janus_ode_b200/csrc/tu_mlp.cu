@@ -355,7 +355,7 @@ static int ensure(Handle* H, Work& C, long long M, bool need_state) {
 static int launch_grad(Handle* H, const GradIO& io, int n_rows, cudaStream_t st) {
   if (n_rows <= 0) return 0;
   const int tiles = (n_rows + TR - 1) / TR;
-  const int grid = tiles < H->sm_count ? tiles : H->sm_count;
+  const int grid = tiles < H->sm_count * CTAS_PER_SM ? tiles : H->sm_count * CTAS_PER_SM;
   mlp_grad_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ctx_of(H)->W, io);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;
@@ -363,8 +363,8 @@ static int launch_grad(Handle* H, const GradIO& io, int n_rows, cudaStream_t st)
 }
 static int launch_hess(Handle* H, const HessIO& io, int n, cudaStream_t st) {
   if (n <= 0) return 0;
-  const int tiles = (n + 3) / 4;
-  const int grid = tiles < H->sm_count ? tiles : H->sm_count;
+  const int tiles = (n + TR / 16 - 1) / (TR / 16);
+  const int grid = tiles < H->sm_count * CTAS_PER_SM ? tiles : H->sm_count * CTAS_PER_SM;
   mlp_hess_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ctx_of(H)->W, io);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;

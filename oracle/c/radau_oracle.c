@@ -114,12 +114,50 @@ static double det_exp(double t) {
   return q * scale;
 }
 static double det_pow(double x, double y) { return det_exp(y * det_log(x)); }
-static double det_tanh(double x) {   /* csrc/detmath.cuh det_tanh */
-  const double ax = fabs(x);
-  if (ax > 20.0) return x > 0 ? 1.0 : -1.0;
-  const double e = det_exp(-2.0 * ax);
-  const double th = (1.0 - e) / (1.0 + e);
-  return x < 0 ? -th : th;
+static const double DET_EXP2_TAB[32] = {   /* 2^(j/32), correctly rounded: csrc/detmath.cuh JB_EXP2_TAB_VALUES */
+  0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+  0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+  0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+  0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+  0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+  0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+  0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+  0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+static double det_tanh(double x) {   /* csrc/detmath.cuh det_tanh_t, operation by operation */
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  const double SHIFT = 6755399441055744.0;
+  double ax = fabs(x);
+  ax = ax > 20.0 ? 20.0 : ax;
+  const double ns = fma(ax, -9.2332482616893657e+01, SHIFT);
+  const double nd = ns - SHIFT;
+  double r = fma(nd, -(LN2_HI / 32.0), -2.0 * ax);
+  r = fma(nd, -(LN2_LO / 32.0), r);
+  int64_t nb;
+  memcpy(&nb, &ns, 8);
+  const int n = (int)(uint32_t)(nb & 0xffffffffLL);
+  const int j = n & 31, k = n >> 5;
+  double p = 1.0 / 720.0;
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double q = p * DET_EXP2_TAB[j];
+  int64_t qb;
+  memcpy(&qb, &q, 8);
+  qb += ((int64_t)k << 52);
+  double e;
+  memcpy(&e, &qb, 8);
+  const double num = 1.0 - e, d = 1.0 + e;
+  double y = fma(fma(32.0 / 99.0, d, -48.0 / 33.0), d, 70.0 / 33.0);
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  double th = num * y;
+  th = fma(fma(-d, th, num), y, th);
+  th = x < 0 ? -th : th;
+  return x != x ? x : th;
 }
 static double POW(double x, double y) { return g_mirror ? det_pow(x, y) : pow(x, y); }
 
@@ -1576,4 +1614,7 @@ int oracle_max_threads(void) {
 /* deterministic pow (mirror of csrc/detmath.cuh) exposed for the bitwise test */
 void oracle_det_pow(const double *x, const double *y, long long n, double *out) {
   for (long long i = 0; i < n; i++) out[i] = det_pow(x[i], y[i]);
+}
+void oracle_det_tanh(const double *x, long long n, double *out) {
+  for (long long i = 0; i < n; i++) out[i] = det_tanh(x[i]);
 }

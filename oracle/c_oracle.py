@@ -97,6 +97,13 @@ def det_pow(x, y):
     return out
 
 
+def det_tanh(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().oracle_det_tanh(_dp(x), C.c_longlong(x.size), _dp(out))
+    return out
+
+
 def solve(problem, par, sign, y0, tspan, opts, nthreads=0, arith="reference"):
     """y0 [M,Ny], tspan [M,2] -> dict(y, t, h, res, stats[M,8], nstg)."""
     set_arith(arith)

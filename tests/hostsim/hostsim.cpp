@@ -203,6 +203,11 @@ extern "C" int hostsim_solve_sens(int ham_id, const RadauParams* P, const double
   return -1;
 }
 
+// the device's deterministic tanh (csrc/detmath.cuh det_tanh), run on the host
+extern "C" void hostsim_det_tanh(const double* x, long long n, double* out) {
+  for (long long i = 0; i < n; i++) out[i] = det_tanh(x[i]);
+}
+
 // with parameter directions d y / d ham_par[par_index[k]] (Sp_out [M, n_par, NY])
 extern "C" int hostsim_solve_sens_par(int ham_id, const RadauParams* P0, const double* y0, const double* tspan, long long M,
                                       int n_par, const int* par_index, double* y_out, double* S_out, double* Sp_out,

@@ -71,6 +71,15 @@ def solve_mlp(par, sign, y0, tspan, opts, oracle_lib):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, work=work)
 
 
+def det_tanh(x):
+    build()
+    lib = C.CDLL(_SO)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib.hostsim_det_tanh(_dp(x), C.c_longlong(x.size), _dp(out))
+    return out
+
+
 def solve_sens(ham, par, sign, y0, tspan, opts, par_dirs=()):
     """forward sensitivities d y / d y0 (and d y / d par[k], k in par_dirs) by the CUDA core's sens_step, on the CPU"""
     build()
