@@ -345,7 +345,7 @@ int jb200_create(const jb200_opts* o, int ham_id, const double* ham_params, int 
   if (const char* fe = std::getenv("JB200_FIXED_EPOCHS")) H->fixed_epochs = atoi(fe) != 0;
   if (const char* ps = std::getenv("JB200_PRESORT")) H->presort = atoi(ps) != 0;
   if (const char* eh = std::getenv("JB200_EPOCH_HORDER")) H->epoch_horder = atoi(eh);
-  H->P.key_fine = H->epoch_horder == 3;
+  H->P.key_fine = 0;   // per batch: EpochWS::key_fine (solver_impl.cuh params_for)
   *handle = H;
   return 0;
 }

@@ -432,7 +432,14 @@ struct EpochWS {
   void* sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int* sens_cnt = nullptr;   // [cap, 2] counters of the sensitivity iteration (epoch_sens_kernel), allocated on first use
+  int key_fine = 0;          // this batch's epoch lists are also ordered by the current step size (regime_key `fine`)
 };
+// the handle's parameters with this workspace's scheduling choice
+inline RadauParams params_for(const RadauParams& P, const EpochWS& ws) {
+  RadauParams Q = P;
+  Q.key_fine = ws.key_fine;
+  return Q;
+}
 inline void ws_free(EpochWS& ws) {
   cudaFree(ws.parked); cudaFree(ws.tag); cudaFree(ws.lists); cudaFree(ws.counts);
   cudaFree(ws.order); cudaFree(ws.nsel); cudaFree(ws.sort_tmp); cudaFree(ws.sens_cnt);
@@ -476,7 +483,8 @@ struct Handle {
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool fixed_epochs = false;
   bool presort = true;     // fused fixed-order kernel: batch pre-sorted by H(y0) (JB200_PRESORT=0 disables)
-  int epoch_horder = 2;    // epoch lists: 0 regime-key sort, 1 stage count then H(y0) order, 2 regime key then H(y0) order
+  int epoch_horder = 4;    // epoch lists: 0 regime-key sort, 1 stage count then H(y0) order, 2 regime key then H(y0) order,
+                           // 3 regime key then current step size, 4 (default) = 2 or 3 chosen per batch (ws_init: coherence_kernel)
   int epoch_passes = 12;   // attempted steps per trajectory per epoch (flat optimum 8..24 on B200)
   // workspace of jb200_solve_host
   long long cap = 0;
@@ -609,7 +617,7 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
     long long blocks = (long long)H->sm_count * bps;
     const long long need = ((long long)count + TH - 1) / TH;
     if (blocks > need) blocks = need;
-    ks<<<(unsigned)blocks, TH, smem, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
+    ks<<<(unsigned)blocks, TH, smem, st>>>(params_for(H->P, ws), (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
                                           H->d_counter + k, ws.tag, o.y_out, o.t_out, o.h_out, o.res, o.stats, o.nstg,
                                           o.work, dense.sens_S, dense.sens_cnt, dense.sens_Sp);
     JB_CUDA(cudaGetLastError());
@@ -629,7 +637,7 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
   long long blocks = (long long)H->sm_count * bps;
   const long long need = ((long long)count + TH - 1) / TH;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, TH, smem, st>>>(H->P, (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
+  kern<<<(unsigned)blocks, TH, smem, st>>>(params_for(H->P, ws), (Parked<Ham::NV>*)ws.parked, ws.lists + base, count, max_passes,
                                         H->d_counter + k, ws.tag, o.y_out, o.t_out, o.h_out, o.res, o.stats, o.nstg,
                                         o.work, tspan, dense, stop_on_accept);
   JB_CUDA(cudaGetLastError());
@@ -657,7 +665,7 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     for (int k = 0; k < 4; k++) {
       size_t bytes = ws.sort_tmp_bytes;
       JB_CUDA(cub::DeviceSelect::If(ws.sort_tmp, bytes, ws.order, ws.lists + (size_t)k * M, ws.nsel + k, (int)M,
-                                    StagePred{ws.tag, k, H->P.key_fine ? KEY_FINE_BITS : 0}, st));
+                                    StagePred{ws.tag, k, ws.key_fine ? KEY_FINE_BITS : 0}, st));
     }
     int cnt[4];
     JB_CUDA(cudaMemcpyAsync(cnt, ws.nsel, sizeof cnt, cudaMemcpyDeviceToHost, st));
@@ -674,7 +682,7 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
   }
   // regime key major; minor: H(y0) (stable radix sort of the H-ordered rows, horder 2) or the current step size (the fine
   // key bits, rows taken in index order, horder 3)
-  const bool key_then_h = (H->epoch_horder == 2 || H->epoch_horder == 3) && ws.have_order;
+  const bool key_then_h = (H->epoch_horder >= 2) && ws.have_order;
   static const bool trace = std::getenv("JB200_EPOCH_TRACE") != nullptr;   // developer aid: per-epoch timeline on stderr
   cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
   if (trace) for (auto& e : tev) cudaEventCreate(&e);
@@ -682,7 +690,7 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
     if (trace) cudaEventRecord(tev[0], st);
     JB_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * NKEYS, st));
     JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long) * 4, st));
-    const int shift = H->P.key_fine ? KEY_FINE_BITS : 0;
+    const int shift = ws.key_fine ? KEY_FINE_BITS : 0;
     hist_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.tag, M, ws.counts, shift);
     JB_CUDA(cudaGetLastError());
     JB_CUDA(cudaMemcpyAsync(hist.data(), ws.counts, sizeof(int) * NKEYS, cudaMemcpyDeviceToHost, st));
@@ -738,6 +746,44 @@ int run_epochs(Handle* H, EpochWS& ws, int max_passes, int stop_on_accept, const
   return 0;
 }
 
+// Is the H(y0) order a phase-space order for THIS batch?  Per state component: sum of squared differences between rows that are
+// adjacent in the H order (near) and between rows half a batch apart in it (far).  For a one-parameter family of initial
+// states (the reference's examples spread one coordinate: radaute_hamiltonian_example.cpp:108-112) every component is a
+// smooth function of H, near / far ~ 1 / M^2; for a cloud with more degrees of freedom rows of equal H are unrelated in the
+// other directions and near / far = O(1) for at least one component.
+template <int NY>
+__global__ void coherence_kernel(const double* __restrict__ y0, const int* __restrict__ order, long long M,
+                                 double* __restrict__ acc /* [2][NY] */) {
+  double nr[NY], fr[NY];
+#pragma unroll
+  for (int c = 0; c < NY; c++) nr[c] = fr[c] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i + 1 < M; i += (long long)gridDim.x * blockDim.x) {
+    double a[NY], b[NY], f[NY];
+    load_row<NY>(y0, order[i], a);
+    load_row<NY>(y0, order[i + 1], b);
+    load_row<NY>(y0, order[(i + M / 2) % M], f);
+#pragma unroll
+    for (int c = 0; c < NY; c++) {
+      const double dn = a[c] - b[c], df = a[c] - f[c];
+      if (dn - dn == 0.0 && df - df == 0.0) {
+        nr[c] = fma(dn, dn, nr[c]);
+        fr[c] = fma(df, df, fr[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NY; c++) {
+    for (int off = 16; off >= 1; off >>= 1) {
+      nr[c] += __shfl_xor_sync(0xffffffffu, nr[c], off);
+      fr[c] += __shfl_xor_sync(0xffffffffu, fr[c], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&acc[c], nr[c]);
+      atomicAdd(&acc[NY + c], fr[c]);
+    }
+  }
+}
+
 template <class Ham>
 int ws_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int ntspan, long long M, cudaStream_t st) {
   constexpr int NY = Ham::NV;
@@ -745,18 +791,39 @@ int ws_init(Handle* H, EpochWS& ws, const double* y0, const double* tspan, int n
   int rc = ws_reserve(ws, M, sizeof(Parked<NY>));
   if (rc) return rc;
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
-  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(H->P, y0, tspan, ntspan, M, (Parked<NY>*)ws.parked, ws.tag);
-  JB_CUDA(cudaGetLastError());
   ws.use_order = ws.have_order = false;
-  if (H->epoch_horder == 3 && M >= (1 << 16)) {
-    iota_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.order, M);
-    JB_CUDA(cudaGetLastError());
-    ws.use_order = ws.have_order = true;
-  } else if (H->epoch_horder && M >= (1 << 16)) {
+  ws.key_fine = H->epoch_horder == 3;
+  bool iota = H->epoch_horder == 3 && M >= (1 << 16);
+  if (!iota && H->epoch_horder && M >= (1 << 16)) {
     bool ok = false;
     if ((rc = build_order<Ham>(H, ws, y0, M, st, ok))) return rc;
     ws.use_order = ws.have_order = ok;
+    if (ok && H->epoch_horder == 4) {
+      // adaptive (default): keep the H(y0) order only if it is a phase-space order for this batch, else order the epoch lists
+      // by the current step size -- scheduling only, the results do not depend on it
+      double* acc = (double*)ws.sort_tmp;   // free again: build_order's sort has been issued on this stream
+      double h_acc[2 * NY];
+      JB_CUDA(cudaMemsetAsync(acc, 0, sizeof h_acc, st));
+      coherence_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>(y0, ws.order, M, acc);
+      JB_CUDA(cudaGetLastError());
+      JB_CUDA(cudaMemcpyAsync(h_acc, acc, sizeof h_acc, cudaMemcpyDeviceToHost, st));
+      JB_CUDA(cudaStreamSynchronize(st));
+      double worst = 0.0;
+      for (int c = 0; c < NY; c++)
+        if (h_acc[NY + c] > 0.0) worst = std::max(worst, h_acc[c] / h_acc[NY + c]);
+      if (worst > 1e-2) {
+        ws.key_fine = 1;
+        iota = true;
+      }
+    }
   }
+  if (iota) {
+    iota_kernel<<<(unsigned)gblocks, 256, 0, st>>>(ws.order, M);
+    JB_CUDA(cudaGetLastError());
+    ws.use_order = ws.have_order = true;
+  }
+  init_kernel<Ham><<<(unsigned)gblocks, 256, 0, st>>>(params_for(H->P, ws), y0, tspan, ntspan, M, (Parked<NY>*)ws.parked, ws.tag);
+  JB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -826,7 +893,7 @@ int state_step(Handle* H, EpochWS& ws, const double* htry, cudaStream_t st) {
   const long long M = ws.M;
   if (M <= 0) return 0;
   const long long gblocks = std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)H->sm_count * 8));
-  rearm_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>(H->P, (Parked<NY>*)ws.parked, ws.tag, M, htry);
+  rearm_kernel<NY><<<(unsigned)gblocks, 256, 0, st>>>(params_for(H->P, ws), (Parked<NY>*)ws.parked, ws.tag, M, htry);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   const OutArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
