@@ -231,6 +231,14 @@ int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, do
                         double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
                         void* stream);
 
+/* The same step with a dual part: replaces Dopri853TeD (/root/reference/src/cpp/dopri853ted.hpp:26-734, TensorDual state through
+ * dy()).  yd [M,Ny,nd] (1 <= nd <= 8) is the dual part of y, updated in place across the accepted step: the stages are
+ * differentiated one by one, K_s' = J(Y_s) (S + h sum_j a_sj K_j').  Step-size and error control look at the real part only:
+ * x, y, dydx, hnext, hdid are those of jb200_dopri853_step bit for bit.                                                    */
+int jb200_dopri853_step_dual(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,
+                             double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
+                             double* yd, int32_t nd, void* stream);
+
 /* batched small dense LU factor + solve, n in {2,3,4} (one thread per system) or 16 (16 lanes per
  * system, one matrix row per lane): A [M,n,n], b [M,n] -> x [M,n].
  * Aim/bim/xim == NULL selects the real path, otherwise complex (separate re/im planes).    */

@@ -615,6 +615,24 @@ int jb200_dopri853_step(void* handle, int64_t M, int64_t norm_M, double atol, do
   return ops->dopri(H, a, (cudaStream_t)stream);
 }
 
+int jb200_dopri853_step_dual(void* handle, int64_t M, int64_t norm_M, double atol, double rtol, int aliased, double* x, double* y,
+                             double* dydx, double* errold, double* hnext, const double* htry, double* hdid, int32_t* nrej,
+                             double* yd, int32_t nd, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  if (!x || !y || !dydx || !errold || !hnext || !htry || !hdid || !yd) return fail(JB200_EINVAL, "null buffer");
+  if (nd < 1 || nd > dp::NDMAX) return fail(JB200_EINVAL, "1 <= nd <= 8 dual directions per call");
+  if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->dopri) return fail(JB200_ENOTSUP, "DOPRI853 is available for the thread-resident Hamiltonians only");
+  dp::StepArgs a{(long long)M, (long long)(norm_M > 0 ? norm_M : M), atol, rtol, x, y, dydx, errold, hnext, aliased, htry, hdid,
+                 (int*)nrej};
+  a.yd = yd;
+  a.nd = nd;
+  return ops->dopri(H, a, (cudaStream_t)stream);
+}
+
 int jb200_eval_jac_dual(void* handle, const double* y, const double* yd, int ND, int64_t M, double* f, double* J, double* T,
                         double* fd, double* Jd, void* stream) {
   Handle* H = (Handle*)handle;

@@ -35,11 +35,15 @@ struct StepArgs {
   const double* htry;                       // [M]
   double* hdid;                             // [M]
   int* nrej;                                // [M] rejected attempts of this call (may be nullptr)
+  double* yd = nullptr;                     // [M,NY,nd] dual part of y (forward sensitivities), updated in place; nullptr: none
+  int nd = 0;
 };
+constexpr int NDMAX = 8;                    // dual directions per call
 
 template <class Ham>
 JB_HD void dopri_step_one(const double* par, double sign, long long norm_M, double atol, double rtol, bool aliased, double& x,
-                          double* y, double* dydx, double& errold, double& hnext, double htry, double& hdid, int& nrej) {
+                          double* y, double* dydx, double& errold, double& hnext, double htry, double& hdid, int& nrej,
+                          double* ybase = nullptr) {
   constexpr int NY = Ham::NV;
   const double EPS_ = 2.220446049250313e-16;
   double h = htry;
@@ -50,6 +54,10 @@ JB_HD void dopri_step_one(const double* par, double sign, long long norm_M, doub
   bool reject = h > EPS_;
   while (reject) {
     double k4[NY], k5[NY], k6[NY], k7[NY], k8[NY], k9[NY], k10[NY], k2[NY], k3[NY], yt[NY];
+    if (ybase) {   // the state this attempt starts from (the dual pass repeats the accepted attempt)
+#pragma unroll
+      for (int i = 0; i < NY; i++) ybase[i] = y[i];
+    }
 #pragma unroll
     for (int i = 0; i < NY; i++) yt[i] = y[i] + h * (A2_1 * dydx[i]);
     ham_dyns<Ham>(yt, par, sign, k2);
@@ -143,6 +151,66 @@ JB_HD void dopri_step_one(const double* par, double sign, long long norm_M, doub
     x = x + h;
   }
   hdid = h;
+}
+
+// Dual part of one ACCEPTED step (the reference's Dopri853TeD, /root/reference/src/cpp/dopri853ted.hpp:26-734: TensorDual
+// state through dy()): an explicit Runge-Kutta step differentiates stage by stage,
+//   Y_s' = S + h sum_j a_sj K_j',   K_s' = J(Y_s) Y_s',   S_new = S + h sum_j b_j K_j',
+// J(Y_s) from the hyper-dual evaluation of H at the stage points (which are recomputed here from the step's base state, its
+// derivative k1 and the accepted h).  Step size and error control see the real part only, so the states are those of
+// dopri_step_one bit for bit.  Sd [NY][nd] row-major, nd <= NDMAX.
+template <class Ham>
+JB_HD void dopri_dual_one(const double* par, double sign, const double* yb, const double* k1, double h, double* Sd, int nd) {
+  constexpr int NY = Ham::NV;
+  const double A[11][11] = {
+      {A2_1},
+      {A3_1, A3_2},
+      {A4_1, 0, A4_3},
+      {A5_1, 0, A5_3, A5_4},
+      {A6_1, 0, 0, A6_4, A6_5},
+      {A7_1, 0, 0, A7_4, A7_5, A7_6},
+      {A8_1, 0, 0, A8_4, A8_5, A8_6, A8_7},
+      {A9_1, 0, 0, A9_4, A9_5, A9_6, A9_7, A9_8},
+      {A10_1, 0, 0, A10_4, A10_5, A10_6, A10_7, A10_8, A10_9},
+      {A11_1, 0, 0, A11_4, A11_5, A11_6, A11_7, A11_8, A11_9, A11_10},
+      {A12_1, 0, 0, A12_4, A12_5, A12_6, A12_7, A12_8, A12_9, A12_10, A12_11}};
+  const double B[12] = {B1, 0, 0, 0, 0, B6, B7, B8, B9, B10, B11, B12};
+  double K[12][NY], Kd[12][NY * NDMAX], J[NY * NY];
+  for (int i = 0; i < NY; i++) K[0][i] = k1[i];
+  ham_jac<Ham>(yb, par, sign, J);
+  for (int i = 0; i < NY; i++)
+    for (int d = 0; d < nd; d++) {
+      double acc = 0.0;
+      for (int j = 0; j < NY; j++) acc = fma(J[i * NY + j], Sd[j * nd + d], acc);
+      Kd[0][i * NDMAX + d] = acc;
+    }
+  for (int s = 1; s < 12; s++) {
+    double Y[NY], Yd[NY * NDMAX];
+    for (int i = 0; i < NY; i++) {
+      double acc = 0.0;
+      for (int j = 0; j < s; j++) acc = fma(A[s - 1][j], K[j][i], acc);
+      Y[i] = fma(h, acc, yb[i]);
+      for (int d = 0; d < nd; d++) {
+        double ad = 0.0;
+        for (int j = 0; j < s; j++) ad = fma(A[s - 1][j], Kd[j][i * NDMAX + d], ad);
+        Yd[i * NDMAX + d] = fma(h, ad, Sd[i * nd + d]);
+      }
+    }
+    ham_dyns<Ham>(Y, par, sign, K[s]);
+    ham_jac<Ham>(Y, par, sign, J);
+    for (int i = 0; i < NY; i++)
+      for (int d = 0; d < nd; d++) {
+        double acc = 0.0;
+        for (int j = 0; j < NY; j++) acc = fma(J[i * NY + j], Yd[j * NDMAX + d], acc);
+        Kd[s][i * NDMAX + d] = acc;
+      }
+  }
+  for (int i = 0; i < NY; i++)
+    for (int d = 0; d < nd; d++) {
+      double acc = 0.0;
+      for (int j = 0; j < 12; j++) acc = fma(B[j], Kd[j][i * NDMAX + d], acc);
+      Sd[i * nd + d] = fma(h, acc, Sd[i * nd + d]);
+    }
 }
 
 }  // namespace dp

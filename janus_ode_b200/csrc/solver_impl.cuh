@@ -970,6 +970,22 @@ __global__ void __launch_bounds__(128) dopri_kernel(const __grid_constant__ Rada
     load_row<NY>(a.dydx, m, d);
     double x = a.x[m], errold = a.errold[m], hnext = a.hnext[m], hdid;
     int nrej;
+#ifndef JB_SLIM
+    if (a.yd) {   // with the dual part: repeat the accepted attempt stage by stage on [Y, Y'] (dopri853.cuh dopri_dual_one)
+      double yb[NY], k1[NY];
+#pragma unroll
+      for (int i = 0; i < NY; i++) { yb[i] = y[i]; k1[i] = d[i]; }
+      const double x0 = x;
+      dp::dopri_step_one<Ham>(P.ham_par, P.sign, a.norm_M, a.atol, a.rtol, a.aliased != 0, x, y, d, errold, hnext, a.htry[m], hdid,
+                              nrej, yb);
+      if (x != x0 && hdid == hdid) {
+        double Sd[NY * dp::NDMAX];
+        for (int k = 0; k < NY * a.nd; k++) Sd[k] = a.yd[m * NY * a.nd + k];
+        dp::dopri_dual_one<Ham>(P.ham_par, P.sign, yb, k1, hdid, Sd, a.nd);
+        for (int k = 0; k < NY * a.nd; k++) a.yd[m * NY * a.nd + k] = Sd[k];
+      }
+    } else
+#endif
     dp::dopri_step_one<Ham>(P.ham_par, P.sign, a.norm_M, a.atol, a.rtol, a.aliased != 0, x, y, d, errold, hnext, a.htry[m], hdid, nrej);
     store_row<NY>(a.y, m, y);
     store_row<NY>(a.dydx, m, d);

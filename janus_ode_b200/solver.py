@@ -574,12 +574,34 @@ class Dopri853Te:
         self.xold = self.x.clone()
         H = self._handle
         with torch.cuda.device(dev):
-            _lib.check_h(H, H.L.jb200_dopri853_step(H.h, self.M, self.norm_M, self.atol, self.rtol,
-                                                   1 if self.gpu_launches else 0, _ptr(self.x),
-                                                   _ptr(self.y), _ptr(self.dydx), _ptr(self.errold), _ptr(self.hnext),
-                                                   _ptr(h), _ptr(self.hdid), _ptr(self.nrej), _stream_ptr(dev)))
+            if getattr(self, "yd", None) is not None:
+                _lib.check_h(H, H.L.jb200_dopri853_step_dual(H.h, self.M, self.norm_M, self.atol, self.rtol,
+                                                            1 if self.gpu_launches else 0, _ptr(self.x), _ptr(self.y),
+                                                            _ptr(self.dydx), _ptr(self.errold), _ptr(self.hnext), _ptr(h),
+                                                            _ptr(self.hdid), _ptr(self.nrej), _ptr(self.yd),
+                                                            self.yd.shape[2], _stream_ptr(dev)))
+            else:
+                _lib.check_h(H, H.L.jb200_dopri853_step(H.h, self.M, self.norm_M, self.atol, self.rtol,
+                                                       1 if self.gpu_launches else 0, _ptr(self.x),
+                                                       _ptr(self.y), _ptr(self.dydx), _ptr(self.errold), _ptr(self.hnext),
+                                                       _ptr(h), _ptr(self.hdid), _ptr(self.nrej), _stream_ptr(dev)))
         self.gpu_launches += 1
         return self
+
+
+class Dopri853TeD(Dopri853Te):
+    """Dopri853Te with a dual part, shaped like the reference's C++ `Dopri853TeD` (TensorDual state,
+    /root/reference/src/cpp/dopri853ted.hpp:26-734): `yd [M,Ny,Nd]` (default: identity, Nd = Ny <= 8) is propagated across every
+    accepted step by differentiating the stages (`jb200_dopri853_step_dual`); `s.y` and all step sizes are those of Dopri853Te
+    bit for bit."""
+
+    def __init__(self, yy, dydxx, xx, atoll, rtoll, dens=False, derivs=None, norm_M=None, yd=None):
+        super().__init__(yy, dydxx, xx, atoll, rtoll, dens, derivs, norm_M)
+        if yd is None:
+            yd = torch.eye(self.D, dtype=torch.float64, device=self.y.device).repeat(self.M, 1, 1)
+        if yd.dim() != 3 or yd.shape[0] != self.M or yd.shape[1] != self.D or not (1 <= yd.shape[2] <= 8):
+            raise ValueError(f"yd must be [M,{self.D},Nd] with 1 <= Nd <= 8")
+        self.yd = yd.to(self.y.device, torch.float64).contiguous().clone()
 
 
 class RadauTeD(RadauTe):

@@ -8,6 +8,7 @@
 
 #include "../../janus_ode_b200/csrc/radau_core.cuh"
 #include "../../janus_ode_b200/csrc/seulex.cuh"
+#include "../../janus_ode_b200/csrc/dopri853.cuh"
 
 using namespace jb;
 
@@ -199,6 +200,42 @@ extern "C" int hostsim_solve_sens(int ham_id, const RadauParams* P, const double
   switch (ham_id) {
     case HAM_HARMONIC: run_sens<HamHarmonic>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
     case HAM_VDP: run_sens<HamVdp>(*P, y0, tspan, M, y_out, S_out, stats, iters); return 0;
+  }
+  return -1;
+}
+
+// ---- explicit DOPRI853 with a dual part (csrc/dopri853.cuh dopri_step_one + dopri_dual_one), integrated to xf on the host
+template <class Ham>
+static void run_dopri_dual(const double* par, double sign, const double* y0, long long M, double x0, double xf, double atol,
+                           double rtol, double h0, double* y_out, double* S_out, int* steps) {
+  constexpr int NY = Ham::NV;
+  for (long long m = 0; m < M; m++) {
+    double y[NY], d[NY], Sd[NY * NY], x = x0, errold = 1.0e-4, hnext = h0, hdid = 0.0;
+    for (int i = 0; i < NY; i++) y[i] = y0[m * NY + i];
+    for (int k = 0; k < NY * NY; k++) Sd[k] = (k / NY == k % NY) ? 1.0 : 0.0;
+    ham_dyns<Ham>(y, par, sign, d);
+    int n = 0, nrej;
+    bool aliased = false;
+    while (xf - x > 1e-14 * (1.0 + fabs(xf)) && n < 100000) {
+      const double htry = h0 < xf - x ? h0 : xf - x;   // the caller's htry every call (the reference's hnext never grows)
+      double yb[NY], k1[NY];
+      for (int i = 0; i < NY; i++) k1[i] = d[i];
+      const double xb = x;
+      dp::dopri_step_one<Ham>(par, sign, M, atol, rtol, aliased, x, y, d, errold, hnext, htry, hdid, nrej, yb);
+      if (!(hdid == hdid) || x == xb) break;
+      if (S_out) dp::dopri_dual_one<Ham>(par, sign, yb, k1, hdid, Sd, NY);
+      n++;   // aliased stays false: a clean stepper (the reference's y / yout aliasing corrupts the state after a rejection)
+    }
+    for (int i = 0; i < NY; i++) y_out[m * NY + i] = y[i];
+    if (S_out) for (int k = 0; k < NY * NY; k++) S_out[m * NY * NY + k] = Sd[k];
+    steps[m] = n;
+  }
+}
+extern "C" int hostsim_dopri_dual(int ham_id, const double* par, double sign, const double* y0, long long M, double x0, double xf,
+                                  double atol, double rtol, double h0, double* y_out, double* S_out, int* steps) {
+  switch (ham_id) {
+    case HAM_HARMONIC: run_dopri_dual<HamHarmonic>(par, sign, y0, M, x0, xf, atol, rtol, h0, y_out, S_out, steps); return 0;
+    case HAM_VDP: run_dopri_dual<HamVdp>(par, sign, y0, M, x0, xf, atol, rtol, h0, y_out, S_out, steps); return 0;
   }
   return -1;
 }

@@ -71,6 +71,23 @@ def solve_mlp(par, sign, y0, tspan, opts, oracle_lib):
     return dict(y=y, t=t, h=h, res=res, stats=stats, nstg=nstg, work=work)
 
 
+def dopri_dual(ham, par, sign, y0, x0, xf, atol, rtol, h0=0.01, dual=True):
+    """csrc/dopri853.cuh on the host: integrate to xf with repeated accepted steps, optionally with the dual part d y / d y0"""
+    build()
+    lib = C.CDLL(_SO)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, ny = y0.shape
+    y = np.empty_like(y0)
+    S = np.empty((M, ny, ny)) if dual else None
+    steps = np.zeros(M, dtype=np.int32)
+    d = C.c_double
+    rc = lib.hostsim_dopri_dual(C.c_int(HAM[ham]), _dp(par), d(sign), _dp(y0), C.c_longlong(M), d(x0), d(xf), d(atol), d(rtol),
+                                d(h0), _dp(y), _dp(S) if dual else None, steps.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return dict(y=y, sens=S, steps=steps)
+
+
 def det_tanh(x):
     build()
     lib = C.CDLL(_SO)

@@ -112,3 +112,70 @@ def test_gpu_large_batch_and_norm_M():
     with pytest.raises(jb.JanusB200Error):
         jb.Dopri853Te(torch.zeros(4, 16, dtype=torch.float64, device="cuda"), None, 0.0, 1e-6, 1e-6, False,
                       jb.HamiltonianSystem(jb.MlpHamiltonian(), -1)).step(0.1)
+
+
+# ------------------------------------------------------------------ dual part (the reference's Dopri853TeD)
+def _hostsim():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import hostsim
+    return hostsim
+
+
+def test_cuda_core_dual_part_on_host_vs_finite_differences():
+    """csrc/dopri853.cuh dopri_dual_one (the stages differentiated one by one, J from hyper-dual numbers), run on the host:
+    d y(tf) / d y0 against central differences of the same stepper -- how the reference checks its dual solvers
+    (tests/cpp/ode_solver_test.cpp:620-770) -- and the real part is untouched"""
+    hostsim = _hostsim()
+    y0 = np.array([[1.0, 1.0, 2.0, 0.0], [0.5, -1.0, 1.7, 0.2]])
+    kw = dict(atol=1e-7, rtol=1e-7, h0=0.02)
+    r = hostsim.dopri_dual("vdp", [1.0], +1, y0, 0.0, 3.0, **kw)
+    r0 = hostsim.dopri_dual("vdp", [1.0], +1, y0, 0.0, 3.0, dual=False, **kw)
+    assert np.array_equal(r["y"], r0["y"]) and np.array_equal(r["steps"], r0["steps"]) and (r["steps"] >= 150).all()
+    S = np.zeros((2, 4, 4))
+    for d in range(4):
+        e = 1e-6
+        yp, ym = y0.copy(), y0.copy()
+        yp[:, d] += e
+        ym[:, d] -= e
+        S[:, :, d] = (hostsim.dopri_dual("vdp", [1.0], +1, yp, 0.0, 3.0, dual=False, **kw)["y"]
+                      - hostsim.dopri_dual("vdp", [1.0], +1, ym, 0.0, 3.0, dual=False, **kw)["y"]) / (2 * e)
+    assert np.allclose(r["sens"], S, rtol=1e-4, atol=1e-4 * np.abs(S).max())
+    # ... and the implicit solver's sensitivities of the same problem (independent algorithm)
+    ts = np.tile(np.array([0.0, 3.0]), (2, 1))
+    h = hostsim.solve_sens("vdp", [1.0], +1, y0, ts, jb.OptionsTe(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=100000))
+    assert np.allclose(r["sens"], h["sens"], rtol=1e-3, atol=1e-3 * np.abs(h["sens"]).max())
+
+
+@pytest.mark.gpu
+def test_gpu_dual_part():
+    torch.manual_seed(1)
+    M = 512
+    y0 = torch.tensor([1.0, 1.0, 2.0, 0.0], dtype=torch.float64).repeat(M, 1)
+    y0[:, 2] += 0.5 * torch.rand(M, dtype=torch.float64)
+    y0 = y0.cuda()
+    dyn = jb.HamiltonianSystem(jb.VanDerPol(1.0), +1)
+    x0 = torch.zeros(M, dtype=torch.float64, device="cuda")
+    mk = lambda y, cls, **kw: cls(y, None, x0, 1.0, 1.0, False, dyn, norm_M=1, **kw)     # error control off: no rejected attempts
+    s, p = mk(y0, jb.Dopri853TeD), mk(y0, jb.Dopri853Te)
+    fd = []
+    for d in range(4):
+        yp, ym = y0.clone(), y0.clone()
+        yp[:, d] += 1e-6
+        ym[:, d] -= 1e-6
+        fd.append((mk(yp, jb.Dopri853Te), mk(ym, jb.Dopri853Te)))
+    for _ in range(150):
+        for o in [s, p] + [q for pair in fd for q in pair]:
+            o.step(0.02)
+    assert int(s.nrej.sum()) == 0
+    assert torch.equal(s.y, p.y) and torch.equal(s.x, p.x) and torch.equal(s.dydx, p.dydx)      # real part untouched
+    S = torch.stack([(a.y - b.y) / 2e-6 for a, b in fd], 2)
+    assert torch.allclose(s.yd, S, rtol=1e-5, atol=1e-5 * float(S.abs().max()))
+    # a non-identity dual part is propagated linearly
+    S0 = torch.randn(M, 4, 3, dtype=torch.float64, device="cuda")
+    t = mk(y0, jb.Dopri853TeD, yd=S0)
+    for _ in range(150):
+        t.step(0.02)
+    assert torch.allclose(t.yd, s.yd @ S0, rtol=1e-9, atol=1e-9)
+    with pytest.raises(ValueError):
+        mk(y0, jb.Dopri853TeD, yd=torch.zeros(M, 4, 9, dtype=torch.float64, device="cuda"))
