@@ -167,6 +167,15 @@ int jb200_eval_jac_dual(void* handle, const double* y, const double* yd, int ND,
 int jb200_seulex_step(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry,
                       double* y, double* x, double* theta, int32_t* k_targ, double* hnext, double* hdid,
                       int32_t* flags, double* yjac, int32_t* k_out, int32_t* nrej, void* stream);
+
+/* The same step with a dual part: replaces SeulexTed.step / SeulexTedState (/root/reference/src/python/seulexted.py:12-95,
+ * 238-1396: TensorDual y, TensorMatDual dfdy, LUDual solves).  yd [M,Ny,nd] (1 <= nd <= 8) = the dual part of state.y, updated
+ * in place; sjac [M,Ny,nd] = the dual part of the state the kept Jacobian was evaluated at (the reference keeps dfdy.d
+ * itself), initialise to yd.  The accepted attempt is replayed on [y, y']: (I/hh - A) delta' = J(y_n) y_n' + A' delta with
+ * A' = dJ/dy . sjac from the third-order jet of H; the extrapolation is linear.  Real part = jb200_seulex_step bit for bit. */
+int jb200_seulex_step_dual(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry, double* y,
+                           double* x, double* theta, int32_t* k_targ, double* hnext, double* hdid, int32_t* flags, double* yjac,
+                           int32_t* k_out, int32_t* nrej, double* yd, double* sjac, int32_t nd, void* stream);
 int jb200_seulex_init(double atol, double rtol, int KMAXX, double* theta0, int32_t* k_targ0);
 
 /* jb200_solve_host with a compact result set for the PCIe link: counters as int32 [M,8] (they are bounded by

@@ -4,8 +4,8 @@ from ._lib import JanusB200Error, LIB_PATH
 from .hamiltonians import Hamiltonian, Harmonic, MlpHamiltonian, VanDerPol, VdpAug, VdpPmp
 from .options import STAT_NAMES, LinearEvents, OptionsTe, StatsTe
 from .user import compile_hamiltonian
-from .solver import Dopri853Te, Dopri853TeD, SeulexState, SeulexT, HamiltonianSystem, RadauState, RadauT, RadauTe, RadauTeD, det_pow, fp64_dmma_tflops, fp64_peak_tflops, lu_solve
+from .solver import Dopri853Te, Dopri853TeD, SeulexState, SeulexT, SeulexTedState, SeulexTed, HamiltonianSystem, RadauState, RadauT, RadauTe, RadauTeD, det_pow, fp64_dmma_tflops, fp64_peak_tflops, lu_solve
 
 __all__ = ["JanusB200Error", "LIB_PATH", "Hamiltonian", "Harmonic", "VanDerPol", "VdpAug", "VdpPmp", "MlpHamiltonian",
            "STAT_NAMES", "OptionsTe", "StatsTe", "HamiltonianSystem", "RadauState", "RadauT", "RadauTe", "det_pow",
-           "fp64_peak_tflops", "fp64_dmma_tflops", "lu_solve", "compile_hamiltonian", "Dopri853Te", "Dopri853TeD", "RadauTeD", "SeulexState", "SeulexT", "LinearEvents"]
+           "fp64_peak_tflops", "fp64_dmma_tflops", "lu_solve", "compile_hamiltonian", "Dopri853Te", "Dopri853TeD", "RadauTeD", "SeulexState", "SeulexT", "SeulexTedState", "SeulexTed", "LinearEvents"]

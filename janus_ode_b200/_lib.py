@@ -34,7 +34,7 @@ _plugins = {}
 # every symbol include/janus_b200.h declares
 SYMBOLS = ("jb200_opts_default", "jb200_create", "jb200_destroy", "jb200_ny", "jb200_solve", "jb200_solve_dense",
            "jb200_solve_host", "jb200_solve_host_compact", "jb200_set_events", "jb200_solve_out", "jb200_state_create", "jb200_state_step", "jb200_state_read", "jb200_state_destroy",
-           "jb200_last_launches", "jb200_eval_dyns", "jb200_eval_jac", "jb200_eval_jac_dual", "jb200_lu_solve", "jb200_dopri853_step", "jb200_dopri853_step_dual", "jb200_seulex_step", "jb200_seulex_init", "jb200_solve_sens", "jb200_solve_sens_par",
+           "jb200_last_launches", "jb200_eval_dyns", "jb200_eval_jac", "jb200_eval_jac_dual", "jb200_lu_solve", "jb200_dopri853_step", "jb200_dopri853_step_dual", "jb200_seulex_step", "jb200_seulex_step_dual", "jb200_seulex_init", "jb200_solve_sens", "jb200_solve_sens_par",
            "jb200_det_pow", "jb200_fp64_peak", "jb200_dmma_peak", "jb200_last_error", "jb200_version")
 
 
@@ -87,6 +87,8 @@ def _load(path):
         L.jb200_eval_jac_dual.argtypes = [vp, dp, dp, C.c_int, i64, dp, dp, dp, dp, dp, vp]
         L.jb200_seulex_step.argtypes = [vp, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp,
                                         dp, dp, vp]
+        L.jb200_seulex_step_dual.argtypes = [vp, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp,
+                                             dp, dp, dp, dp, dp, C.c_int32, vp]
         L.jb200_seulex_init.argtypes = [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.jb200_det_pow.argtypes = [dp, dp, i64, dp, vp]
         L.jb200_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

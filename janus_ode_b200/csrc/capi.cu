@@ -662,6 +662,26 @@ int jb200_seulex_step(void* handle, int64_t M, double atol, double rtol, int KMA
   return ops->seulex(H, a, (cudaStream_t)stream);
 }
 
+int jb200_seulex_step_dual(void* handle, int64_t M, double atol, double rtol, int KMAXX, int quirks, const double* htry, double* y,
+                           double* x, double* theta, int32_t* k_targ, double* hnext, double* hdid, int32_t* flags, double* yjac,
+                           int32_t* k_out, int32_t* nrej, double* yd, double* sjac, int32_t nd, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail(JB200_EINVAL, "null handle");
+  if (M <= 0) return 0;
+  if (!htry || !y || !x || !theta || !k_targ || !hnext || !hdid || !flags || !yjac || !yd || !sjac) return fail(JB200_EINVAL, "null buffer");
+  if (nd < 1 || nd > sx::NDMAX) return fail(JB200_EINVAL, "1 <= nd <= 8 dual directions per call");
+  if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");
+  if (KMAXX < 2 || KMAXX + 1 > sx::IMAXX_CAP) return fail(JB200_EINVAL, "KMAXX must be in [2, 15]");
+  const HamOps* ops = ham_ops(H->ham_id);
+  if (!ops || !ops->seulex) return fail(JB200_ENOTSUP, "SEULEX is available for the thread-resident Hamiltonians only");
+  sx::StepArgs a{(long long)M, atol, rtol, KMAXX, quirks, htry, y, x, theta, (int*)k_targ, hnext, hdid, (int*)flags, yjac,
+                 (int*)k_out, (int*)nrej};
+  a.yd = yd;
+  a.sjac = sjac;
+  a.nd = nd;
+  return ops->seulex(H, a, (cudaStream_t)stream);
+}
+
 int jb200_seulex_init(double atol, double rtol, int KMAXX, double* theta0, int32_t* k_targ0) {
   if (!theta0 || !k_targ0) return fail(JB200_EINVAL, "null argument");
   if (!(atol >= 0) || !(rtol >= 0) || (atol == 0 && rtol == 0)) return fail(JB200_EINVAL, "atol, rtol must be >= 0 and not both 0");

@@ -391,8 +391,8 @@ struct Sens {
                        // not to be trusted -- reported to the caller instead of silently propagated
 };
 
-template <class Ham, int NY, int S, int SM>
-JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, const double* rscal, Sens<NY>& sn) {
+template <class Ham, int NY, int S, int SM, bool PAR>
+JB_HD void sens_step_t(Traj<NY, SM>& T, const RadauParams& P, const double* z, const double* rscal, Sens<NY>& sn) {
   using Tab = RadauTab<S>;
   constexpr int ND = Sens<NY>::ND;
   constexpr int si = (S - 1) / 2;
@@ -408,13 +408,13 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
     ham_jac<Ham>(yq, P.ham_par, P.sign, &Jq[q * NY * NY]);
   }
   T.work += (long long)S * Ham::FLOPS_J;
-  for (int d = 0; d < ND + P.sens_npar; d++) {
+  for (int d = 0; d < ND + (PAR ? P.sens_npar : 0); d++) {
     double Sd[NY], smax = 1.0;
-    double gq[S * NY];   // source term of a parameter direction at the stage points (unused for a state direction)
-    if (d < ND) {
+    double gq[PAR ? S * NY : 1];   // source term of a parameter direction at the stage points (unused for a state direction)
+    if (!PAR || d < ND) {
 #pragma unroll
       for (int i = 0; i < NY; i++) Sd[i] = sn.S[i * ND + d];
-    } else {
+    } else if constexpr (PAR) {
 #pragma unroll
       for (int i = 0; i < NY; i++) Sd[i] = sn.Sp[(d - ND) * NY + i];
 #pragma unroll
@@ -444,7 +444,7 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < NY; j++) acc = fma(Jq[q * NY * NY + i * NY + j], Sd[j] + Zs[q * NY + j], acc);
-            Fq[q * NY + i] = (d < ND) ? acc : acc + gq[q * NY + i];
+            Fq[q * NY + i] = (!PAR || d < ND) ? acc : acc + gq[PAR ? q * NY + i : 0];
           }
 #pragma unroll
         for (int j = 0; j < S; j++)
@@ -513,7 +513,7 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
       nrm_old = nrm;
       if (it == Nit - 1) sn.unconverged += 1;
     }
-    if (d < ND) {
+    if (!PAR || d < ND) {
 #pragma unroll
       for (int i = 0; i < NY; i++) sn.S[i * ND + d] = Sd[i] + Zs[(S - 1) * NY + i];
     } else {
@@ -521,6 +521,13 @@ JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, con
       for (int i = 0; i < NY; i++) sn.Sp[(d - ND) * NY + i] = Sd[i] + Zs[(S - 1) * NY + i];
     }
   }
+}
+
+// the state directions alone keep the lean instantiation (no parameter source term in its inner loop)
+template <class Ham, int NY, int S, int SM>
+JB_HD void sens_step(Traj<NY, SM>& T, const RadauParams& P, const double* z, const double* rscal, Sens<NY>& sn) {
+  if (P.sens_npar > 0) sens_step_t<Ham, NY, S, SM, true>(T, P, z, rscal, sn);
+  else sens_step_t<Ham, NY, S, SM, false>(T, P, z, rscal, sn);
 }
 
 // factorisation of the rolled high-order steppers: real block in registers, complex blocks in a rolled loop into the

@@ -39,7 +39,13 @@ struct StepArgs {
   int* flags;           // [M]  F_*
   double* yjac;         // [M,NY] state the kept Jacobian was evaluated at
   int *k_out, *nrej;    // [M], [M]  (may be nullptr)
+  // dual part (the reference's SeulexTed): yd [M,NY,nd] = d y / d (directions), updated in place across the step;
+  // sjac [M,NY,nd] = the dual part of the state the kept Jacobian was evaluated at.  nullptr: none
+  double* yd = nullptr;
+  double* sjac = nullptr;
+  int nd = 0;
 };
+constexpr int NDMAX = 8;   // dual directions per call
 
 JB_HD int nseq_of(int i) {  // 2, 3, 4, 6, 8, 12, 16, 24, ...
   return (i & 1) ? (3 << (i >> 1)) : (2 << (i >> 1));
@@ -54,7 +60,8 @@ JB_HD double coeff_of(int k, int l) { return 1.0 / ((double)nseq_of(k) / (double
 template <class Ham>
 JB_HD void seulex_step_one(const double* par, double sign, double atol, double rtol, int KMAXX, int quirks, double htry,
                            double* y, double& x_io, double& theta_io, int& ktarg_io, double& hnext_io, double& hdid_out,
-                           int& flags_io, double* yjac, int& k_out, int& nrej_out) {
+                           int& flags_io, double* yjac, int& k_out, int& nrej_out, bool* jac_fresh = nullptr,
+                           double* h_taken = nullptr) {
   constexpr int NY = Ham::NV;
   const double EPS_ = 2.220446049250313e-16;
   const int IMAXX = KMAXX + 1;
@@ -273,6 +280,90 @@ JB_HD void seulex_step_one(const double* par, double sign, double atol, double r
   flags_io = (first_step ? F_FIRST : 0) | (last_step ? F_LAST : 0) | (reject ? F_REJECT : 0) | (prev_reject ? F_PREV_REJECT : 0);
   k_out = k;
   nrej_out = nrej;
+  if (jac_fresh) *jac_fresh = calcjac;
+  if (h_taken) *h_taken = forward ? h_att : -h_att;
+}
+
+// Dual part of one ACCEPTED step (the reference's SeulexTed, /root/reference/src/python/seulexted.py:238-1396: TensorDual
+// state, TensorMatDual Jacobian and LUDual solves through dy / polyextr).  The accepted attempt -- table rows 0..k over
+// h_att from ysav with the iteration matrix A = J(yjac) -- is replayed on [y, y']:
+//   (I / hh - A) delta = f(y_n)   =>   (I / hh - A) delta' = J(y_n) y_n' + A' delta,     A' = dJ/dy (yjac) . Sjac,
+// A' from the third-order jet of H (dual3.cuh, the reference's evalJacDual), J(y_n) from hyper-dual numbers, the same
+// real LU; the Aitken-Neville extrapolation is linear, so the dual table is extrapolated with the same coefficients.
+// Order and step-size control look at the real part only: the states are those of seulex_step_one bit for bit.
+// Sd [NY][nd] (in: dual part at the start of the step, out: at its end), Sj [NY][nd] dual part of yjac; nd <= NDMAX.
+template <class Ham>
+JB_HD void seulex_dual_one(const double* par, double sign, const double* ysav, const double* yjac, const double* Sj, double h_att,
+                           int k, double* Sd, int nd) {
+  constexpr int NY = Ham::NV;
+  double A[NY * NY], Ad[NY * NY * NDMAX], f0[NY];
+  {
+    double Jd[NY * NY * NDMAX], yd[NY * NDMAX];
+    for (int i = 0; i < NY; i++)
+      for (int d = 0; d < nd; d++) yd[i * nd + d] = Sj[i * nd + d];
+    ham_jac_dual<Ham>(yjac, par, sign, yd, nd, f0, A, nullptr, nullptr, Jd);
+    for (int e = 0; e < NY * NY; e++)
+      for (int d = 0; d < nd; d++) Ad[e * NDMAX + d] = Jd[e * nd + d];
+  }
+  double tabd[IMAXX_CAP][NY * NDMAX], outd[NY * NDMAX];
+  for (int kk = 0; kk <= k; kk++) {
+    const int nsteps = nseq_of(kk);
+    const double hh = h_att / nsteps, rhh = 1.0 / hh;
+    RLU<NY> lu;
+    for (int i = 0; i < NY; i++)
+      for (int j = 0; j < NY; j++) lu.a[i * NY + j] = (i == j) ? (-A[i * NY + j] + rhh) : -A[i * NY + j];
+    rlu_factor<NY>(lu);
+    double yt[NY], ytd[NY * NDMAX], delta[NY], deltad[NY * NDMAX], J[NY * NY];
+    for (int i = 0; i < NY; i++) {
+      yt[i] = ysav[i];
+      for (int d = 0; d < nd; d++) ytd[i * NDMAX + d] = Sd[i * nd + d];
+    }
+    for (int nn = 0; nn < nsteps; nn++) {
+      if (nn > 0)
+        for (int i = 0; i < NY; i++) {
+          yt[i] = yt[i] + delta[i];
+          for (int d = 0; d < nd; d++) ytd[i * NDMAX + d] += deltad[i * NDMAX + d];
+        }
+      ham_dyns<Ham>(yt, par, sign, delta);
+      rlu_solve<NY>(lu, delta);
+      ham_jac<Ham>(yt, par, sign, J);
+      for (int d = 0; d < nd; d++) {
+        double rhs[NY];
+        for (int i = 0; i < NY; i++) {
+          double acc = 0.0;
+          for (int j = 0; j < NY; j++) acc = fma(J[i * NY + j], ytd[j * NDMAX + d], acc);
+          for (int j = 0; j < NY; j++) acc = fma(Ad[(i * NY + j) * NDMAX + d], delta[j], acc);
+          rhs[i] = acc;
+        }
+        rlu_solve<NY>(lu, rhs);
+        for (int i = 0; i < NY; i++) deltad[i * NDMAX + d] = rhs[i];
+      }
+    }
+    double seqd[NY * NDMAX];
+    for (int i = 0; i < NY; i++)
+      for (int d = 0; d < nd; d++) seqd[i * NDMAX + d] = ytd[i * NDMAX + d] + deltad[i * NDMAX + d];
+    if (kk == 0) {
+      for (int e = 0; e < NY * NDMAX; e++) outd[e] = seqd[e];
+    } else {
+      for (int e = 0; e < NY * NDMAX; e++) tabd[kk - 1][e] = seqd[e];
+      for (int j = kk - 1; j > 0; j--) {
+        const double c = coeff_of(kk, j);
+        for (int i = 0; i < NY; i++)
+          for (int d = 0; d < nd; d++) {
+            const int e = i * NDMAX + d;
+            tabd[j - 1][e] = fma(c, tabd[j][e] - tabd[j - 1][e], tabd[j][e]);
+          }
+      }
+      const double c0 = coeff_of(kk, 0);
+      for (int i = 0; i < NY; i++)
+        for (int d = 0; d < nd; d++) {
+          const int e = i * NDMAX + d;
+          outd[e] = fma(c0, tabd[0][e] - outd[e], tabd[0][e]);
+        }
+    }
+  }
+  for (int i = 0; i < NY; i++)
+    for (int d = 0; d < nd; d++) Sd[i * nd + d] = outd[i * NDMAX + d];
 }
 
 }  // namespace sx

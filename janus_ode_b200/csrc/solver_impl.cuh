@@ -1015,6 +1015,22 @@ __global__ void __launch_bounds__(128) seulex_kernel(const __grid_constant__ Rad
     load_row<NY>(a.yjac, m, yj);
     double x = a.x[m], theta = a.theta[m], hnext = a.hnext[m], hdid;
     int k_targ = a.k_targ[m], flags = a.flags[m], k, nrej;
+#ifndef JB_SLIM
+    if (a.yd) {   // with the dual part: replay the accepted attempt on [y, y'] (seulex.cuh seulex_dual_one)
+      double ysav[NY], Sd[NY * sx::NDMAX], Sj[NY * sx::NDMAX], h_taken = 0.0;
+      bool fresh = false;
+#pragma unroll
+      for (int i = 0; i < NY; i++) ysav[i] = y[i];
+      sx::seulex_step_one<Ham>(P.ham_par, P.sign, a.atol, a.rtol, a.KMAXX, a.quirks, a.htry[m], y, x, theta, k_targ, hnext, hdid,
+                               flags, yj, k, nrej, &fresh, &h_taken);
+      const long long o = m * NY * a.nd;
+      for (int e = 0; e < NY * a.nd; e++) Sd[e] = a.yd[o + e];
+      // a Jacobian evaluated during this call was taken at (a state derived from) the start of the step
+      for (int e = 0; e < NY * a.nd; e++) Sj[e] = fresh ? Sd[e] : a.sjac[o + e];
+      if (nrej <= 200 && h_taken != 0.0) sx::seulex_dual_one<Ham>(P.ham_par, P.sign, ysav, yj, Sj, h_taken, k, Sd, a.nd);
+      for (int e = 0; e < NY * a.nd; e++) { a.yd[o + e] = Sd[e]; a.sjac[o + e] = Sj[e]; }
+    } else
+#endif
     sx::seulex_step_one<Ham>(P.ham_par, P.sign, a.atol, a.rtol, a.KMAXX, a.quirks, a.htry[m], y, x, theta, k_targ, hnext, hdid,
                              flags, yj, k, nrej);
     store_row<NY>(a.y, m, y);

@@ -530,6 +530,47 @@ class SeulexT:
         return state
 
 
+class SeulexTedState(SeulexState):
+    """SeulexState with a dual part, the role of the reference's SeulexTedState(yin, xin, params, nparams_step, atoll, rtoll,
+    KMAXX) (/root/reference/src/python/seulexted.py:12-95, whose y is a TensorDual seeded with the identity): `yd [M,D,Nd]`
+    (default: identity, Nd = D <= 8) rides along; `state.y` stays the real part."""
+
+    def __init__(self, yin, xin, atoll, rtoll, KMAXX=13, yd=None, ft=None):
+        super().__init__(yin, xin, atoll, rtoll, KMAXX, 0.0, ft)
+        if yd is None:
+            yd = torch.eye(self.D, dtype=torch.float64, device=self.y.device).repeat(self.M, 1, 1)
+        if yd.dim() != 3 or yd.shape[0] != self.M or yd.shape[1] != self.D or not (1 <= yd.shape[2] <= 8):
+            raise ValueError(f"yd must be [M,{self.D},Nd] with 1 <= Nd <= 8")
+        self.yd = yd.to(self.y.device, torch.float64).contiguous().clone()
+        self._sjac = self.yd.clone()
+
+    _FIELDS = SeulexState._FIELDS + ("yd", "_sjac")
+
+
+class SeulexTed(SeulexT):
+    """`state = SeulexTed().step(htry, dyns, state)` on a SeulexTedState: the step of SeulexT plus the dual part of y
+    propagated across it (`jb200_seulex_step_dual`; /root/reference/src/python/seulexted.py:238-1396).  The real part --
+    states, orders, step sizes -- is SeulexT's bit for bit."""
+
+    def step(self, htry, dyns, state: SeulexTedState) -> SeulexTedState:
+        if not isinstance(dyns, HamiltonianSystem):
+            raise TypeError("dyns must be a janus_ode_b200.HamiltonianSystem")
+        if state.D != dyns.hamiltonian.Ny:
+            raise ValueError(f"state.y must be [M,{dyns.hamiltonian.Ny}]")
+        dev = state.y.device
+        ht = torch.as_tensor(htry, dtype=torch.float64, device=dev).reshape(-1).expand(state.M).contiguous()
+        H = dyns._h()
+        state._dyns = dyns
+        state.xold = state.x.clone()
+        with torch.cuda.device(dev):
+            _lib.check_h(H, H.L.jb200_seulex_step_dual(H.h, state.M, state.atol, state.rtol, state.KMAXX, self.quirks, _ptr(ht),
+                                                       _ptr(state.y), _ptr(state.x), _ptr(state.theta), _ptr(state.k_targ),
+                                                       _ptr(state.hnext), _ptr(state.hdid), _ptr(state.flags),
+                                                       _ptr(state._yjac), _ptr(state.k), _ptr(state.nrej), _ptr(state.yd),
+                                                       _ptr(state._sjac), state.yd.shape[2], _stream_ptr(dev)))
+        return state
+
+
 class Dopri853Te:
     """Explicit Dormand-Prince 8(5,3) stepper for non-stiff batches with the reference's object shape
     (/root/reference/src/python/dopri853te.py:4-5, 290-315):

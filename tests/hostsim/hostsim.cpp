@@ -240,6 +240,48 @@ extern "C" int hostsim_dopri_dual(int ham_id, const double* par, double sign, co
   return -1;
 }
 
+// ---- SEULEX with a dual part (csrc/seulex.cuh seulex_step_one + seulex_dual_one), integrated to xf on the host
+template <class Ham>
+static void run_seulex_dual(const double* par, double sign, const double* y0, long long M, double x0, double xf, double atol,
+                            double rtol, int KMAXX, double h0, double* y_out, double* S_out, int* steps) {
+  constexpr int NY = Ham::NV;
+  const double jac_redo = std::fmin(1.0e-4, rtol);
+  const double logfact = -std::log10(rtol + atol) * 0.6 + 0.5;
+  const int kt0 = (int)std::floor(std::fmax(1.0, std::fmin((double)(KMAXX - 1), std::nearbyint(logfact))));
+  for (long long m = 0; m < M; m++) {
+    double y[NY], yj[NY], Sd[NY * NY], Sj[NY * NY], x = x0, theta = 2.0 * jac_redo, hnext = -1.0e99, hdid = 0.0;
+    int k_targ = kt0, flags = sx::F_FIRST, k = 0, nrej = 0, n = 0;
+    for (int i = 0; i < NY; i++) y[i] = yj[i] = y0[m * NY + i];
+    for (int e = 0; e < NY * NY; e++) Sd[e] = Sj[e] = (e / NY == e % NY) ? 1.0 : 0.0;
+    double htry = h0;
+    while (xf - x > 1e-14 * (1.0 + std::fabs(xf)) && n < 100000) {
+      if (htry > xf - x) htry = xf - x;
+      double ysav[NY], h_taken = 0.0;
+      bool fresh = false;
+      for (int i = 0; i < NY; i++) ysav[i] = y[i];
+      sx::seulex_step_one<Ham>(par, sign, atol, rtol, KMAXX, 0, htry, y, x, theta, k_targ, hnext, hdid, flags, yj, k, nrej, &fresh,
+                               &h_taken);
+      if (S_out) {
+        if (fresh) for (int e = 0; e < NY * NY; e++) Sj[e] = Sd[e];
+        if (nrej <= 200 && h_taken != 0.0) sx::seulex_dual_one<Ham>(par, sign, ysav, yj, Sj, h_taken, k, Sd, NY);
+      }
+      htry = hnext;
+      n++;
+    }
+    for (int i = 0; i < NY; i++) y_out[m * NY + i] = y[i];
+    if (S_out) for (int e = 0; e < NY * NY; e++) S_out[m * NY * NY + e] = Sd[e];
+    steps[m] = n;
+  }
+}
+extern "C" int hostsim_seulex_dual(int ham_id, const double* par, double sign, const double* y0, long long M, double x0, double xf,
+                                   double atol, double rtol, int KMAXX, double h0, double* y_out, double* S_out, int* steps) {
+  switch (ham_id) {
+    case HAM_HARMONIC: run_seulex_dual<HamHarmonic>(par, sign, y0, M, x0, xf, atol, rtol, KMAXX, h0, y_out, S_out, steps); return 0;
+    case HAM_VDP: run_seulex_dual<HamVdp>(par, sign, y0, M, x0, xf, atol, rtol, KMAXX, h0, y_out, S_out, steps); return 0;
+  }
+  return -1;
+}
+
 // the device's deterministic tanh (csrc/detmath.cuh det_tanh), run on the host
 extern "C" void hostsim_det_tanh(const double* x, long long n, double* out) {
   for (long long i = 0; i < n; i++) out[i] = det_tanh(x[i]);

@@ -88,6 +88,23 @@ def dopri_dual(ham, par, sign, y0, x0, xf, atol, rtol, h0=0.01, dual=True):
     return dict(y=y, sens=S, steps=steps)
 
 
+def seulex_dual(ham, par, sign, y0, x0, xf, atol, rtol, KMAXX=12, h0=0.01, dual=True):
+    """csrc/seulex.cuh on the host: the reference's driver loop (htry = hnext, clipped to xf), optionally with d y / d y0"""
+    build()
+    lib = C.CDLL(_SO)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    M, ny = y0.shape
+    y = np.empty_like(y0)
+    S = np.empty((M, ny, ny)) if dual else None
+    steps = np.zeros(M, dtype=np.int32)
+    d = C.c_double
+    rc = lib.hostsim_seulex_dual(C.c_int(HAM[ham]), _dp(par), d(sign), _dp(y0), C.c_longlong(M), d(x0), d(xf), d(atol), d(rtol),
+                                 C.c_int(KMAXX), d(h0), _dp(y), _dp(S) if dual else None, steps.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return dict(y=y, sens=S, steps=steps)
+
+
 def det_tanh(x):
     build()
     lib = C.CDLL(_SO)

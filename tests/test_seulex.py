@@ -131,3 +131,74 @@ def test_gpu_seulex_integrates_a_batch_to_the_final_time():
     r.solve()
     rel = (st.y - r.y).abs().max(1).values / r.y.abs().max(1).values
     assert float(rel.max()) < 1e-4
+
+
+# ------------------------------------------------------------------ dual part (the reference's SeulexTed / SeulexTedState)
+def _hostsim():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import hostsim
+    return hostsim
+
+
+@pytest.mark.parametrize("mu,tf", [(5.0, 3.0), (1000.0, 50.0)])
+def test_cuda_core_dual_part_on_host_vs_finite_differences(mu, tf):
+    """csrc/seulex.cuh seulex_dual_one (the accepted attempt replayed on [y, y'], A' from the third-order jet of H), run on the
+    host through the reference's driver loop: d y(tf) / d y0 against central differences of the same stepper -- the reference's
+    own check of its dual solvers (tests/cpp/ode_solver_test.cpp:620-770, rtol 1e-3 ... 1e-4) -- and against the Radau
+    sensitivities of the same problem; the real part does not notice the dual part"""
+    import janus_ode_b200 as jb
+    hostsim = _hostsim()
+    y0 = np.array([[1.0, 1.0, 2.0, 0.0], [0.5, -1.0, 1.7, 0.2]])
+    kw = dict(atol=1e-9, rtol=1e-9, h0=0.01)
+    r = hostsim.seulex_dual("vdp", [mu], +1, y0, 0.0, tf, **kw)
+    r0 = hostsim.seulex_dual("vdp", [mu], +1, y0, 0.0, tf, dual=False, **kw)
+    assert np.array_equal(r["y"], r0["y"]) and np.array_equal(r["steps"], r0["steps"]) and (r["steps"] > 5).all()
+    S = np.zeros((2, 4, 4))
+    for d in range(4):
+        e = 1e-6
+        yp, ym = y0.copy(), y0.copy()
+        yp[:, d] += e
+        ym[:, d] -= e
+        S[:, :, d] = (hostsim.seulex_dual("vdp", [mu], +1, yp, 0.0, tf, dual=False, **kw)["y"]
+                      - hostsim.seulex_dual("vdp", [mu], +1, ym, 0.0, tf, dual=False, **kw)["y"]) / (2 * e)
+    assert np.allclose(r["sens"], S, rtol=1e-5, atol=1e-6 * np.abs(S).max())
+    ts = np.tile(np.array([0.0, tf]), (2, 1))
+    h = hostsim.solve_sens("vdp", [mu], +1, y0, ts, jb.OptionsTe(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=100000))
+    assert np.allclose(r["sens"], h["sens"], rtol=1e-5, atol=1e-6 * np.abs(h["sens"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mu,tf", [(5.0, 3.0), (1000.0, 50.0)])
+def test_gpu_dual_part(mu, tf):
+    import torch
+    import janus_ode_b200 as jb
+    hostsim = _hostsim()
+    M = 64
+    g = torch.Generator().manual_seed(3)
+    y0 = torch.tensor([1.0, 1.0, 2.0, 0.0], dtype=torch.float64).repeat(M, 1)
+    y0[:, 2] += 0.5 * torch.rand(M, generator=g, dtype=torch.float64)
+    dyn = jb.HamiltonianSystem(jb.VanDerPol(mu), +1)
+
+    def run(state, solver):
+        htry = torch.full((M,), 0.01, dtype=torch.float64, device="cuda")
+        n = 0
+        while bool(((tf - state.x) > 1e-14 * (1 + tf)).any()) and n < 10000:
+            live = (tf - state.x) > 1e-14 * (1 + tf)
+            state[live] = solver.step(torch.minimum(htry, tf - state.x)[live], dyn, state[live])
+            htry = state.hnext.clone()
+            n += 1
+        return state
+
+    x0 = torch.zeros(M, dtype=torch.float64, device="cuda")
+    sd = run(jb.SeulexTedState(y0.cuda(), x0, 1e-9, 1e-9, KMAXX=12), jb.SeulexTed())
+    sp = run(jb.SeulexState(y0.cuda(), x0, 1e-9, 1e-9, KMAXX=12), jb.SeulexT())
+    assert torch.equal(sd.y, sp.y) and torch.equal(sd.x, sp.x) and torch.equal(sd.hnext, sp.hnext)      # real part untouched
+    h = hostsim.seulex_dual("vdp", [mu], +1, y0.numpy(), 0.0, tf, 1e-9, 1e-9, KMAXX=12, h0=0.01)
+    assert np.array_equal(sd.y.cpu().numpy(), h["y"])
+    assert np.allclose(sd.yd.cpu().numpy(), h["sens"], rtol=1e-12, atol=1e-12 * np.abs(h["sens"]).max())
+    # the implicit Radau path's sensitivities of the same rows
+    ts = torch.tensor([0.0, tf], dtype=torch.float64).repeat(M, 1).cuda()
+    r = jb.RadauTeD(dyn, dyn.jacobian, ts, y0.cuda(), jb.OptionsTe(RelTol=1e-10, AbsTol=1e-13, MaxNbrStep=100000))
+    r.solve()
+    assert torch.allclose(sd.yd, r.yd, rtol=1e-5, atol=1e-6 * float(r.yd.abs().max()))
