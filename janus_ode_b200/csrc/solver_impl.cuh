@@ -961,7 +961,7 @@ int launch_jac(Handle* H, const double* y, long long M, double* J, cudaStream_t 
 
 // one table of entry points per Hamiltonian: what capi.cu dispatches on
 // explicit DOPRI853: one call = one accepted step of every trajectory (dopri853.cuh)
-template <class Ham>
+template <class Ham, bool DUAL>   // DUAL: its own kernel, so that the plain stepper keeps its small stack frame
 __global__ void __launch_bounds__(128) dopri_kernel(const __grid_constant__ RadauParams P, const dp::StepArgs a) {
   constexpr int NY = Ham::NV;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(128) dopri_kernel(const __grid_constant__ Rada
     double x = a.x[m], errold = a.errold[m], hnext = a.hnext[m], hdid;
     int nrej;
 #ifndef JB_SLIM
-    if (a.yd) {   // with the dual part: repeat the accepted attempt stage by stage on [Y, Y'] (dopri853.cuh dopri_dual_one)
+    if constexpr (DUAL) {   // with the dual part: repeat the accepted attempt stage by stage on [Y, Y'] (dopri853.cuh dopri_dual_one)
       double yb[NY], k1[NY];
 #pragma unroll
       for (int i = 0; i < NY; i++) { yb[i] = y[i]; k1[i] = d[i]; }
@@ -999,14 +999,20 @@ __global__ void __launch_bounds__(128) dopri_kernel(const __grid_constant__ Rada
 template <class Ham>
 int launch_dopri(Handle* H, const dp::StepArgs& a, cudaStream_t st) {
   const long long blocks = std::max<long long>(1, std::min<long long>((a.M + 127) / 128, (long long)H->sm_count * 8));
-  dopri_kernel<Ham><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+#ifndef JB_SLIM
+  if (a.yd) dopri_kernel<Ham, true><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  else
+#else
+  if (a.yd) return fail(JB200_ENOTSUP, "this plugin was built without the dual steppers");
+#endif
+  dopri_kernel<Ham, false><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
 }
 
 // SEULEX: one call = one step() of every trajectory (seulex.cuh)
-template <class Ham>
+template <class Ham, bool DUAL>
 __global__ void __launch_bounds__(128) seulex_kernel(const __grid_constant__ RadauParams P, const sx::StepArgs a) {
   constexpr int NY = Ham::NV;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.M; m += (long long)gridDim.x * blockDim.x) {
@@ -1016,7 +1022,7 @@ __global__ void __launch_bounds__(128) seulex_kernel(const __grid_constant__ Rad
     double x = a.x[m], theta = a.theta[m], hnext = a.hnext[m], hdid;
     int k_targ = a.k_targ[m], flags = a.flags[m], k, nrej;
 #ifndef JB_SLIM
-    if (a.yd) {   // with the dual part: replay the accepted attempt on [y, y'] (seulex.cuh seulex_dual_one)
+    if constexpr (DUAL) {   // with the dual part: replay the accepted attempt on [y, y'] (seulex.cuh seulex_dual_one)
       double ysav[NY], Sd[NY * sx::NDMAX], Sj[NY * sx::NDMAX], h_taken = 0.0;
       bool fresh = false;
 #pragma unroll
@@ -1051,7 +1057,8 @@ int launch_seulex(Handle* H, const sx::StepArgs& a, cudaStream_t st) {
   return fail(JB200_ENOTSUP, "this plugin was built without the SEULEX kernel");
 #else
   const long long blocks = std::max<long long>(1, std::min<long long>((a.M + 127) / 128, (long long)H->sm_count * 8));
-  seulex_kernel<Ham><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  if (a.yd) seulex_kernel<Ham, true><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
+  else seulex_kernel<Ham, false><<<(unsigned)blocks, 128, 0, st>>>(H->P, a);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
   return 0;
