@@ -67,10 +67,14 @@ struct Weights {
 };
 
 // Shared-memory operand layout: element (k, i) of a [K][LD] operand (activations: LD = TR rows; weights: LD = WD
-// features) lives at k * LD + (i ^ ((k & 3) << 2)).  A fragment load touches, per half-warp, 4 values of k x 4
-// consecutive i: without the swizzle those 16 doubles share 8 banks (LD * 8 bytes is a multiple of 128), with it they
-// are 16 distinct consecutive doubles = one conflict-free 128-byte wavefront.  Pairs (i even, i + 1) stay adjacent.
-__device__ __forceinline__ int swz(int k, int i) { return i ^ ((k & 3) << 2); }
+// features) lives at k * LD + (i ^ x(k)), x(k) = 8 (k & 1) + 4 ((k >> 1) & 1).  A fragment load touches, per half-warp, 4
+// values of k x 4 consecutive i: without the swizzle those 16 doubles share 8 banks (LD * 8 bytes is a multiple of 128), with
+// it they are 16 distinct consecutive doubles = one conflict-free 128-byte wavefront.  Pairs (i even, i + 1) stay adjacent,
+// and putting the LOW bit of k on the 64-byte bit makes the epilogue stores conflict-free too: a quarter-warp stores the row
+// pairs of two neighbouring features, which land in different halves of the 128-byte bank row (with x(k) = 4 (k & 3) they
+// shared one: 3.7- / 7.6-way store conflicts in the first DMMA version).
+__device__ __forceinline__ int swz_x(int k) { return ((k & 1) << 3) | ((k & 2) << 1); }
+__device__ __forceinline__ int swz(int k, int i) { return i ^ swz_x(k); }
 __device__ __forceinline__ int aidx(int c, int r) { return c * TR + swz(c, r); }   // activation buffers [feature][row]
 
 // thread -> accumulators: warp w owns rows (TR / WR) (w % WR) .., features 32 (w / WR) ..; mma tile (j, f), j < NJ, f < NF,
@@ -123,7 +127,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
   };
   issue(0);
   // this lane's fragment offsets within a k-step (k = lr): weights (k, cb + 8 f + lq), activations (k, rb + 8 j + lq)
-  const int xs = tm.lr << 2;
+  const int xs = swz_x(tm.lr);
   for (int ch = 0; ch < nchunks; ch++) {
     if (ch + 1 < nchunks) {
       issue(ch + 1);
@@ -150,22 +154,36 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
   }
 }
 
-// out[row][j] = sum_i W1[i][j] * D[i][row], j < 16: 64 x 16 outputs, OC per thread
-// (thread -> row = tid % 64, columns (tid / 64) * OC ..).  W1 (natural [128][16]) is staged in wbuf.
-constexpr int OC = NV * TR / THREADS;
-__device__ __forceinline__ void output_product(const double* __restrict__ D, const double* __restrict__ W1g,
-                                               double* __restrict__ wbuf, double (&g)[OC]) {
-  for (int o = threadIdx.x; o < WD * NV; o += THREADS) wbuf[o] = W1g[o];
-  __syncthreads();
-  const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
-#pragma unroll
-  for (int c = 0; c < OC; c++) g[c] = 0.0;
-  for (int i = 0; i < WD; i++) {
-    const double d = D[aidx(i, r)];
-#pragma unroll
-    for (int c = 0; c < OC; c++) g[c] = fma(wbuf[i * NV + cb + c], d, g[c]);
+// out[row][j] = sum_i W1[i][j] * D[i][row], j < 16, on the tensor cores as well: 2 feature tiles x TR / 8 row tiles, OPT of
+// them per warp (the same row tile, so the activation fragment is loaded once); the weight fragments W1[i][j] (natural
+// [128][16], 16 KB, the same for every CTA) come straight from L1 / L2.  Chain order: i increasing, seeded with 0.
+constexpr int ORT = TR / 8;                          // row tiles
+constexpr int OPT = (2 * ORT) / (THREADS / 32);      // tiles per warp: 2 (same row tile, both feature tiles) or 1
+static_assert(OPT == 1 || OPT == 2, "output product tiling");
+struct OutTile {
+  int rt, jt0;
+  __device__ OutTile() {
+    const int warp = threadIdx.x >> 5;
+    rt = warp % ORT;
+    jt0 = OPT == 2 ? 0 : warp / ORT;
   }
-  __syncthreads();
+  // this lane's results: feature(t) = 8 (jt0 + t) + lq, rows row0 + e, e < 2
+  __device__ __forceinline__ int feature(int t, const TileMap& tm) const { return 8 * (jt0 + t) + tm.lq; }
+  __device__ __forceinline__ int row0(const TileMap& tm) const { return 8 * rt + 2 * tm.lr; }
+};
+__device__ __forceinline__ void output_product(const double* __restrict__ D, const double* __restrict__ W1g, const TileMap& tm,
+                                               const OutTile& ot, double (&g)[OPT][2]) {
+#pragma unroll
+  for (int t = 0; t < OPT; t++) g[t][0] = g[t][1] = 0.0;
+  const int xs = swz_x(tm.lr);
+  const double* Dk = D + tm.lr * TR;
+  const double* Wk = W1g + tm.lr * NV + tm.lq;
+#pragma unroll 8
+  for (int ks = 0; ks < WD / 4; ks++) {
+    const double b = Dk[ks * 4 * TR + ((8 * ot.rt + tm.lq) ^ xs)];
+#pragma unroll
+    for (int t = 0; t < OPT; t++) dmma(g[t], __ldg(Wk + ks * 4 * NV + 8 * (ot.jt0 + t)), b);
+  }
 }
 
 // store the accumulators raw into a [feature][row] buffer
@@ -335,18 +353,22 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) mlp_grad_kernel(const We
     }
     __syncthreads();
     // ---- g = W1^T d1 ; ydot = [sign dH/dx ; dH/dp]
-    double g[OC];
-    output_product(A0, Wt.W1, wbuf, g);
     {
-      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
-      const int m = s_traj[r];
-      if (m >= 0) {
-        const int st = s_stage[r];
+      const OutTile ot;
+      double g[OPT][2];
+      output_product(A0, Wt.W1, tm, ot, g);
 #pragma unroll
-        for (int c = 0; c < OC; c++) {
-          const int e = cb + c;
-          const double v = (e < NH) ? io.sign * g[c] : g[c];
-          io.out[(size_t)(st * NV + e) * io.out_se + (size_t)m * io.out_sr] = v;
+      for (int e2 = 0; e2 < 2; e2++) {
+        const int r = ot.row0(tm) + e2;
+        const int m = s_traj[r];
+        if (m >= 0) {
+          const int st = s_stage[r];
+#pragma unroll
+          for (int t = 0; t < OPT; t++) {
+            const int e = ot.feature(t, tm);
+            const double v = (e < NH) ? io.sign * g[t][e2] : g[t][e2];
+            io.out[(size_t)(st * NV + e) * io.out_se + (size_t)m * io.out_sr] = v;
+          }
         }
       }
     }
@@ -485,19 +507,23 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) mlp_hess_kernel(const We
     }
     __syncthreads();
     // ---- Hvv[jj][k] = sum_i W1[i][jj] td1[i][row(slot, k)];  J[r][c] = (r < N ? sign : 1) Hvv[r][vc(c)]
-    double g[OC];
-    output_product(A0, Wt.W1, wbuf, g);
     {
-      const int r = threadIdx.x & (TR - 1), cb = (threadIdx.x / TR) * OC;
-      const int slot = r >> 4, k = r & 15;
-      const int m = s_traj[slot];
-      if (m >= 0) {
-        const int cc = (k + NH) & (NV - 1);   // column of y whose v-index is k
+      const OutTile ot;
+      double g[OPT][2];
+      output_product(A0, Wt.W1, tm, ot, g);
 #pragma unroll
-        for (int c = 0; c < OC; c++) {
-          const int jj = cb + c;
-          const double v = (jj < NH) ? io.sign * g[c] : g[c];
-          io.J[(size_t)(jj * NV + cc) * io.J_se + (size_t)m * io.J_sr] = v;
+      for (int e2 = 0; e2 < 2; e2++) {
+        const int r = ot.row0(tm) + e2;
+        const int slot = r >> 4, k = r & 15;
+        const int m = s_traj[slot];
+        if (m >= 0) {
+          const int cc = (k + NH) & (NV - 1);   // column of y whose v-index is k
+#pragma unroll
+          for (int t = 0; t < OPT; t++) {
+            const int jj = ot.feature(t, tm);
+            const double v = (jj < NH) ? io.sign * g[t][e2] : g[t][e2];
+            io.J[(size_t)(jj * NV + cc) * io.J_se + (size_t)m * io.J_sr] = v;
+          }
         }
       }
     }

@@ -225,6 +225,7 @@ JB_HD void ph_init(const State& S, const RadauParams& P, long long i, const doub
   const double* tspan = S.tspan + (size_t)i * S.ntspan;
   const long long M = S.M;
   TrajS s;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) S.y[(size_t)e * M + i] = y0[i * MN + e];
   for (int e = 0; e < S.SM * MN; e++) S.cont[(size_t)e * M + i] = 0.0;
   for (int k = 0; k < 8; k++) s.st[k] = 0;
@@ -267,6 +268,7 @@ JB_HD void ph_init_b(const State& S, long long i) {
   const long long M = S.M;
   TrajS& s = S.sc[i];
   bool nanf = false;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     const double v = S.f0[(size_t)e * M + i];
     nanf = nanf || (v != v);
@@ -379,6 +381,7 @@ JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long lo
     finish(s);
     return;
   }
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     const double sc = fma(P.RelTol1[si][e], fabs(S.y[(size_t)e * M + i]), P.AbsTol1[si][e]);
     S.rscal[(size_t)e * M + i] = 1.0 / sc;
@@ -394,6 +397,7 @@ JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long lo
 #pragma unroll
     for (int q = 0; q < S_; q++) {
       const double cq = Tab::C(q) * hquot;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
       for (int e = 0; e < MN; e++) {
         double zq = (cq - Tab::C(0) + 1.0) * S.cont[(size_t)((S_ - 1) * MN + e) * M + i];
 #pragma unroll
@@ -402,6 +406,7 @@ JB_HD void attempt_begin(const State& S, const RadauParams& P, TrajS& s, long lo
         S.z[(size_t)(q * MN + e) * M + i] = zq;
       }
     }
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) {
       double zz[S_];
 #pragma unroll
@@ -498,11 +503,13 @@ JB_HD void dense_output_g(const State& S, TrajS& s, long long i) {
     if (s.PosNeg * (s.t - tn) < 0) break;
     if (s.t == tn) {
       tout[s.nout] = s.t;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
       for (int e = 0; e < MN; e++) yout[s.nout * MN + e] = S.y[(size_t)e * M + i];
       s.nout += 1;
       break;
     }
     const double sg = (tn - s.t) / s.h_old;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) {
       double yi = (sg - (Tab::C(0) - 1.0)) * S.cont[(size_t)((S_ - 1) * MN + e) * M + i];
 #pragma unroll
@@ -518,6 +525,7 @@ JB_HD void dense_output_g(const State& S, TrajS& s, long long i) {
 JB_HD void dense_finish_g(const State& S, const TrajS& s, long long i) {
   if (s.nout >= 1) {
     S.tout[(size_t)i * S.ntspan + s.nout - 1] = s.t;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) S.yout[((size_t)i * S.ntspan + s.nout - 1) * MN + e] = S.y[(size_t)e * S.M + i];
   }
 }
@@ -562,6 +570,7 @@ JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long lon
     }
     s.h_old = s.h;
     s.t = s.t + s.h;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) {
       double zz[S_], cc[S_];
 #pragma unroll
@@ -608,6 +617,7 @@ JB_HD void controller_a(const State& S, const RadauParams& P, TrajS& s, long lon
 JB_HD double scaled_err(const State& S, const RadauParams& P, long long i) {
   const long long M = S.M;
   double sum = 0.0;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     const double v = S.ev[(size_t)e * M + i] * S.rscal[(size_t)e * M + i];
     sum = fma(v, v, sum);
@@ -622,6 +632,7 @@ JB_HD void estrad_a(const State& S, const RadauParams& P, TrajS& s, long long i)
   const long long M = S.M;
   const double rh = 1.0 / s.h;
   s.work += W_tail(S_, MN, (int)FLOPS_F);
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     double sum = S.z[(size_t)e * M + i] * (Tab::Dd(0) * rh);
 #pragma unroll
@@ -644,6 +655,7 @@ JB_HD void estrad_a(const State& S, const RadauParams& P, TrajS& s, long long i)
 template <int S_>
 JB_HD void estrad_b(const State& S, const RadauParams& P, TrajS& s, long long i) {
   const long long M = S.M;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) S.ev[(size_t)e * M + i] = S.ev[(size_t)e * M + i] + S.temp[(size_t)e * M + i];
   rlu_solve_g(S.L0a(i), S.L0rd(i), S.L0piv(i), 1, M, S.ev + i);
   s.err = scaled_err(S, P, i);
@@ -683,6 +695,7 @@ JB_HD bool newton_pre(const State& S, const RadauParams& P, TrajS& s, long long 
     return false;
   }
   s.st[ST_FCN] += S_;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     double fq[S_];
 #pragma unroll
@@ -697,11 +710,13 @@ JB_HD bool newton_pre(const State& S, const RadauParams& P, TrajS& s, long long 
   }
   {  // Solvrad right-hand sides
     const double valp0 = Tab::ValP(0) * rh;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) S.z[(size_t)e * M + i] = fma(-valp0, S.w[(size_t)e * M + i], S.z[(size_t)e * M + i]);
 #pragma unroll
     for (int q = 1; q <= (S_ - 1) / 2; q++) {
       const int q2 = 2 * q - 1, q3 = 2 * q;
       const double v2 = Tab::ValP(q2) * rh, v3 = Tab::ValP(q3) * rh;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
       for (int e = 0; e < MN; e++) {
         const double w2 = S.w[(size_t)(q2 * MN + e) * M + i], w3 = S.w[(size_t)(q3 * MN + e) * M + i];
         const double a = fma(v3, w3, fma(-v2, w2, S.z[(size_t)(q2 * MN + e) * M + i]));
@@ -737,6 +752,7 @@ JB_HD void newton_post(const State& S, const RadauParams& P, TrajS& s, long long
 #pragma unroll
   for (int q = 0; q < S_; q++) {
     double sum = 0.0;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
     for (int e = 0; e < MN; e++) {
       const double v = S.z[(size_t)(q * MN + e) * M + i] * S.rscal[(size_t)e * M + i];
       sum = fma(v, v, sum);
@@ -780,6 +796,7 @@ JB_HD void newton_post(const State& S, const RadauParams& P, TrajS& s, long long
     }
   }
   s.OldNrm = fmax(NewNrm, EPS);
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     double ww[S_];
 #pragma unroll
@@ -853,6 +870,7 @@ JB_HD void ph_accept_b(const State& S, const RadauParams& P, long long i) {
   TrajS s = S.sc[i];
   if (s.phase != PH_F0_EVAL) return;
   bool nanf = false;
+#pragma unroll 8   // 8 components in flight: the loads of a one-thread-per-trajectory phase kernel must overlap
   for (int e = 0; e < MN; e++) {
     const double v = S.f0[(size_t)e * M + i];
     nanf = nanf || (v != v);
