@@ -378,7 +378,10 @@ __device__ __forceinline__ void zluc_solve(int block, double* br, double* bi) {
 template <int N, int S>
 struct HiRoll {
 #if defined(JB_LC_SMEM) && defined(JB_ROLL_HI)
-  static constexpr bool on = (S >= 5) && (N <= 4);
+#ifndef JB_ROLL_HI_MIN
+#define JB_ROLL_HI_MIN 5
+#endif
+  static constexpr bool on = (S >= JB_ROLL_HI_MIN) && (N <= 4);
 #else
   static constexpr bool on = false;
 #endif
