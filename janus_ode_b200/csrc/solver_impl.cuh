@@ -236,14 +236,20 @@ static __global__ void scatter_kernel(const unsigned short* __restrict__ tag, lo
   }
 }
 
+// Epoch kernels: ONE 256-thread CTA per SM (8 warps, the register file's limit at 255 registers per thread).  Measured on
+// config 2 (profiles/r02_epoch_cta_ab.txt): 2 x 128 threads 90.4 ms per solve, 1 x 256 for the 5/7-stage kernels 88.9, for all
+// epoch kernels 88.3; fewer warps (1 x 128, 2 x 64) 120 ms.
+#ifndef JB_THREADS_EPOCH
+#define JB_THREADS_EPOCH 256
+#endif
 #ifndef JB_MINB_EPOCH
-#define JB_MINB_EPOCH 2   // resident CTAs/SM for the 1- and 3-stage epoch kernels
+#define JB_MINB_EPOCH 1   // resident CTAs/SM for the 1- and 3-stage epoch kernels
 #endif
 #ifndef JB_MINB_HI
-#define JB_MINB_HI 2      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
+#define JB_MINB_HI 1      // resident CTAs/SM for the 5- and 7-stage epoch kernels (state spills to local memory)
 #endif
 #ifndef JB_THREADS_HI
-#define JB_THREADS_HI 128
+#define JB_THREADS_HI 256
 #endif
 // ---- pre-sort of a batch by the value of the Hamiltonian at the initial state (a scheduling hint only).
 // Trajectories that start as neighbours in phase space take nearly the same step sequence, so a warp built from
@@ -273,7 +279,7 @@ __global__ void hkey_kernel(const __grid_constant__ RadauParams P, const double*
 
 template <int S>
 struct EpochCfg {
-  static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS;
+  static constexpr int threads = S >= 5 ? JB_THREADS_HI : JB_THREADS_EPOCH;
   static constexpr int minb = S >= 5 ? JB_MINB_HI : JB_MINB_EPOCH;
 };
 
