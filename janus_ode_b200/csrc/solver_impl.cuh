@@ -599,9 +599,13 @@ struct OutArgs {
 template <class Ham, int S, bool VAR>
 int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int max_passes, int stop_on_accept,
                  const OutArgs& o, const double* tspan, const DenseArgs& dense, cudaStream_t main_st, int& used) {
-  // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams
+  // first non-empty bucket runs on the caller's stream, the others fork onto auxiliary streams -- unless the list is large
+  // enough to fill the GPU by itself (JB200_SERIAL_ROWS, developer A/B): then it queues behind the others on the main stream,
+  // so that the kernels of different stage counts (67 / 96 / 134 KB of code) do not share SMs and instruction caches
+  static const long long serial_rows = std::getenv("JB200_SERIAL_ROWS") ? atoll(std::getenv("JB200_SERIAL_ROWS")) : 0;
+  const bool fork = used > 0 && !(serial_rows > 0 && count >= serial_rows);
   cudaStream_t st = main_st;
-  if (used > 0) {
+  if (fork) {
     st = H->aux[used - 1];
     JB_CUDA(cudaStreamWaitEvent(st, H->ev_fork, 0));
   }
@@ -628,11 +632,11 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
                                           o.work, dense.sens_S, dense.sens_cnt, dense.sens_Sp);
     JB_CUDA(cudaGetLastError());
     H->launches += 1;
-    if (used > 0) {
+    if (fork) {
       JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
       JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
     }
-    used += 1;
+    if (fork || used == 0) used += 1;
     return 0;
   }
 #endif
@@ -648,11 +652,11 @@ int launch_epoch(Handle* H, EpochWS& ws, int k, long long base, int count, int m
                                         o.work, tspan, dense, stop_on_accept);
   JB_CUDA(cudaGetLastError());
   H->launches += 1;
-  if (used > 0) {
+  if (fork) {
     JB_CUDA(cudaEventRecord(H->ev_join[used - 1], st));
     JB_CUDA(cudaStreamWaitEvent(main_st, H->ev_join[used - 1], 0));
   }
-  used += 1;
+  if (fork || used == 0) used += 1;
   return 0;
 }
 

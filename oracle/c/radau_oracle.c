@@ -60,60 +60,6 @@ static int g_mirror = 0;
 #define FMA(a, b, c) (g_mirror ? fma((a), (b), (c)) : ((a) * (b) + (c)))
 
 /* ---- deterministic log/exp/pow: same sequence as csrc/detmath.cuh ---- */
-static double det_log(double x) {
-  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-  int64_t b;
-  memcpy(&b, &x, 8);
-  int e = (int)((b >> 52) & 0x7ff) - 1023;
-  int64_t mb = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
-  double m;
-  memcpy(&m, &mb, 8);
-  if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
-  const double r = (m - 1.0) / (m + 1.0);
-  const double r2 = r * r;
-  double p = 1.0 / 23.0;
-  p = fma(p, r2, 1.0 / 21.0);
-  p = fma(p, r2, 1.0 / 19.0);
-  p = fma(p, r2, 1.0 / 17.0);
-  p = fma(p, r2, 1.0 / 15.0);
-  p = fma(p, r2, 1.0 / 13.0);
-  p = fma(p, r2, 1.0 / 11.0);
-  p = fma(p, r2, 1.0 / 9.0);
-  p = fma(p, r2, 1.0 / 7.0);
-  p = fma(p, r2, 1.0 / 5.0);
-  p = fma(p, r2, 1.0 / 3.0);
-  const double t = r + r;
-  const double logm = fma(t * r2, p, t);
-  const double ed = (double)e;
-  return fma(ed, LN2_HI, fma(ed, LN2_LO, logm));
-}
-static double det_exp(double t) {
-  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-  const double INV_LN2 = 1.44269504088896338700e+00;
-  const double kd = floor(fma(t, INV_LN2, 0.5));
-  double r = fma(-kd, LN2_HI, t);
-  r = fma(-kd, LN2_LO, r);
-  double q = 1.0 / 6227020800.0;
-  q = fma(q, r, 1.0 / 479001600.0);
-  q = fma(q, r, 1.0 / 39916800.0);
-  q = fma(q, r, 1.0 / 3628800.0);
-  q = fma(q, r, 1.0 / 362880.0);
-  q = fma(q, r, 1.0 / 40320.0);
-  q = fma(q, r, 1.0 / 5040.0);
-  q = fma(q, r, 1.0 / 720.0);
-  q = fma(q, r, 1.0 / 120.0);
-  q = fma(q, r, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  q = fma(q, r, 1.0);
-  const int64_t k = (int64_t)kd;
-  const int64_t sb = (k + 1023) << 52;
-  double scale;
-  memcpy(&scale, &sb, 8);
-  return q * scale;
-}
-static double det_pow(double x, double y) { return det_exp(y * det_log(x)); }
 static const double DET_EXP2_TAB[32] = {   /* 2^(j/32), correctly rounded: csrc/detmath.cuh JB_EXP2_TAB_VALUES */
   0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
   0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
@@ -123,6 +69,73 @@ static const double DET_EXP2_TAB[32] = {   /* 2^(j/32), correctly rounded: csrc/
   0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
   0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
   0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+static const double DET_LOG_INVC[32] = {   /* csrc/detmath.cuh JB_LOG_INVC_VALUES */
+  0x1.f81f81f81f820p-1, 0x1.e9131abf0b767p-1, 0x1.dae6076b981dbp-1, 0x1.cd85689039b0bp-1,
+  0x1.c0e070381c0e0p-1, 0x1.b4e81b4e81b4fp-1, 0x1.a98ef606a63bep-1, 0x1.9ec8e951033d9p-1,
+  0x1.948b0fcd6e9e0p-1, 0x1.8acb90f6bf3aap-1, 0x1.8181818181818p-1, 0x1.78a4c8178a4c8p-1,
+  0x1.702e05c0b8170p-1, 0x1.6816816816817p-1, 0x1.6058160581606p-1, 0x1.58ed2308158edp-1,
+  0x1.51d07eae2f815p-1, 0x1.4afd6a052bf5bp-1, 0x1.446f86562d9fbp-1, 0x1.3e22cbce4a902p-1,
+  0x1.3813813813814p-1, 0x1.323e34a2b10bfp-1, 0x1.2c9fb4d812ca0p-1, 0x1.27350b8812735p-1,
+  0x1.21fb78121fb78p-1, 0x1.1cf06ada2811dp-1, 0x1.1811811811812p-1, 0x1.135c81135c811p-1,
+  0x1.0ecf56be69c90p-1, 0x1.0a6810a6810a7p-1, 0x1.0624dd2f1a9fcp-1, 0x1.0204081020408p-1};
+static const double DET_LOG_LOGC[32] = {   /* csrc/detmath.cuh JB_LOG_LOGC_VALUES */
+  0x1.fc0a8b0fc03c4p-7, 0x1.77458f632dcffp-5, 0x1.341d7961bd1d0p-4, 0x1.a926d3a4ad562p-4,
+  0x1.0d77e7cd08e5bp-3, 0x1.44d2b6ccb7d1cp-3, 0x1.7ab890210d907p-3, 0x1.af3c94e80bff3p-3,
+  0x1.e27076e2af2e8p-3, 0x1.0a324e27390e2p-2, 0x1.22941fbcf7966p-2, 0x1.3a64c556945eap-2,
+  0x1.51aad872df82ep-2, 0x1.686c81e9b14adp-2, 0x1.7eaf83b82afc2p-2, 0x1.947941c2116fbp-2,
+  0x1.a9cec9a9a084ap-2, 0x1.beb4d9da71b7ap-2, 0x1.d32fe7e00ebd5p-2, 0x1.e744261d68789p-2,
+  0x1.faf588f78f31dp-2, 0x1.0723e5c1cdf41p-1, 0x1.109f39e2d4c96p-1, 0x1.19ee6b467c96fp-1,
+  0x1.23130d7bebf43p-1, 0x1.2c0e9ed448e8cp-1, 0x1.34e289d9ce1d2p-1, 0x1.3d9026a7156fbp-1,
+  0x1.4618bc21c5ec2p-1, 0x1.4e7d811b75bb0p-1, 0x1.56bf9d5b3f399p-1, 0x1.5ee02a9241676p-1};
+static double det_log(double x) {   /* csrc/detmath.cuh det_log, operation by operation */
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  int64_t b;
+  memcpy(&b, &x, 8);
+  const int e = (int)((b >> 52) & 0x7ff) - 1023;
+  const int j = (int)((b >> 47) & 31);
+  int64_t mb = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+  double m;
+  memcpy(&m, &mb, 8);
+  const double r = fma(m, DET_LOG_INVC[j], -1.0);
+  double p = -1.0 / 8.0;
+  p = fma(p, r, 1.0 / 7.0);
+  p = fma(p, r, -1.0 / 6.0);
+  p = fma(p, r, 1.0 / 5.0);
+  p = fma(p, r, -1.0 / 4.0);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double ed = (double)e;
+  const double hi = fma(ed, LN2_HI, DET_LOG_LOGC[j]);
+  const double lo = fma(r * r, p, fma(ed, LN2_LO, r));
+  return hi + lo;
+}
+static double det_exp(double t) {   /* csrc/detmath.cuh det_exp, operation by operation */
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  const double SHIFT = 6755399441055744.0;
+  const double ns = fma(t, 4.6166241308446828e+01, SHIFT);
+  const double nd = ns - SHIFT;
+  double r = fma(nd, -(LN2_HI / 32.0), t);
+  r = fma(nd, -(LN2_LO / 32.0), r);
+  int64_t nb;
+  memcpy(&nb, &ns, 8);
+  const int n = (int)(uint32_t)(nb & 0xffffffffLL);
+  const int j = n & 31, k = n >> 5;
+  double q = 1.0 / 720.0;
+  q = fma(q, r, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  q = q * DET_EXP2_TAB[j];
+  int64_t qb;
+  memcpy(&qb, &q, 8);
+  qb += ((int64_t)k << 52);
+  double out;
+  memcpy(&out, &qb, 8);
+  return out;
+}
+static double det_pow(double x, double y) { return det_exp(y * det_log(x)); }
 static double det_tanh(double x) {   /* csrc/detmath.cuh det_tanh_t, operation by operation */
   const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
   const double SHIFT = 6755399441055744.0;
