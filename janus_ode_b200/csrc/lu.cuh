@@ -25,6 +25,15 @@
 
 namespace jb {
 
+// JB_LU_BRANCH: skip a column's row exchange when this thread's pivot is the diagonal -- in a coherent warp (rows ordered by
+// H(y0) / step size) the lanes mostly agree, so the whole select network of that column is skipped; a lane that does need
+// the exchange runs the same selects as before (same arithmetic, same bits).  Measured: see profiles/r02_lu_branch_ab.txt
+#if defined(JB_LU_BRANCH)
+#define JB_LU_IF(c) if (c)
+#else
+#define JB_LU_IF(c)
+#endif
+
 template <int N>
 struct RLU {
   double a[N * N];  // L\U row-major
@@ -51,6 +60,7 @@ JB_HD void rlu_factor(RLU<N>& L) {
       if (v > best) { best = v; p = i; }
     }
     L.piv[k] = p;
+    JB_LU_IF(p != k)
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       const bool sw = (p == i);
@@ -77,6 +87,7 @@ template <int N>
 JB_HD void rlu_solve(const RLU<N>& L, double* b) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
+    JB_LU_IF(L.piv[k] != k)
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       const bool sw = (L.piv[k] == i);
@@ -113,6 +124,7 @@ JB_HD void zlu_factor(ZLU<N>& L) {
       if (v > best) { best = v; p = i; }
     }
     L.piv[k] = p;
+    JB_LU_IF(p != k)
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       const bool sw = (p == i);
@@ -152,6 +164,7 @@ template <int N>
 JB_HD void zlu_solve(const ZLU<N>& L, double* br, double* bi) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
+    JB_LU_IF(L.piv[k] != k)
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       const bool sw = (L.piv[k] == i);
@@ -243,6 +256,7 @@ JB_HD void zlu_solve(const ZLUS<N>& S, double* br, double* bi) {
   const int b0 = S.base;
 #pragma unroll
   for (int k = 0; k < N; k++) {
+    JB_LU_IF(S.piv[k] != k)
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       const bool sw = (S.piv[k] == i);
