@@ -10,6 +10,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 namespace jb {
 namespace mlp {
 
@@ -32,10 +34,21 @@ __device__ __forceinline__ int half_argmax(unsigned mask, double v, int l, int k
   return idx;
 }
 
+// compile-time loop 0 .. N-1: the column index of a factorisation step must be a constant for the row arrays to stay in
+// registers -- with `#pragma unroll` the compiler unrolled the first columns and left a rolled remainder, whose run-time
+// index put the rows in local memory
+template <int K, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (K < N) {
+    f(std::integral_constant<int, K>{});
+    static_for<K + 1, N>(f);
+  }
+}
+
 // real: lane l holds row l in a[16]; on return a = row l of L\U, rd = 1/U_ll, piv = pivot row of step l
 __device__ __forceinline__ void rlu16_factor(unsigned mask, int l, double (&a)[16], double& rd, int& piv) {
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
+  static_for<0, 16>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
     const int p = half_argmax(mask, fabs(a[k]), l, k);
     if (l == k) piv = p;
     if (__any_sync(mask, p != k)) {
@@ -53,13 +66,13 @@ __device__ __forceinline__ void rlu16_factor(unsigned mask, int l, double (&a)[1
       const double u = __shfl_sync(mask, a[j], k, 16);
       if (below) a[j] = fma(-lm, u, a[j]);
     }
-  }
+  });
 }
 
 __device__ __forceinline__ void zlu16_factor(unsigned mask, int l, double (&re)[16], double (&im)[16], double& rdre,
                                              double& rdim, int& piv) {
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
+  static_for<0, 16>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
     const int p = half_argmax(mask, fabs(re[k]) + fabs(im[k]), l, k);
     if (l == k) piv = p;
     if (__any_sync(mask, p != k)) {
@@ -92,7 +105,7 @@ __device__ __forceinline__ void zlu16_factor(unsigned mask, int l, double (&re)[
         im[j] = fma(-li, ur, fma(-lr, ui, im[j]));
       }
     }
-  }
+  });
 }
 
 

@@ -106,6 +106,14 @@ __global__ void prep_kernel(const State S, const __grid_constant__ RadauParams P
 
 // DecomRC (radaute_impl.hpp:1502-1625) for the trajectories ph_prep left pending: 16 lanes per
 // trajectory, one matrix row per lane (lu16.cuh); block = 256 threads = 16 trajectories
+// x if p else y, as bit logic: written as a ternary on `c == l` inside an unrolled loop over c, the compiler turns the
+// initialisation of a row into "negate every entry, then add to entry [l]" -- a run-time-indexed store that drags the whole
+// row array into local memory (every later access an LDL / STL)
+__device__ __forceinline__ double bit_select(bool p, double x, double y) {
+  const long long m = -(long long)p;
+  return __longlong_as_double((__double_as_longlong(x) & m) | (__double_as_longlong(y) & ~m));
+}
+
 template <int S_>
 __device__ __forceinline__ void decomrc16(const State& S, long long i, double h, unsigned mask, int l) {
   using Tab = RadauTab<S_>;
@@ -125,7 +133,7 @@ __device__ __forceinline__ void decomrc16(const State& S, long long i, double h,
     double a[16], rd = 0.0;
     int piv = 0;
 #pragma unroll
-    for (int c = 0; c < 16; c++) a[c] = (c == l) ? (valp0 - J[c]) : -J[c];
+    for (int c = 0; c < 16; c++) a[c] = bit_select(c == l, valp0 - J[c], -J[c]);
     rlu16_factor(mask, l, a, rd, piv);
     double2* dst = reinterpret_cast<double2*>(S.L0a(i) + l * 16);
 #pragma unroll
@@ -140,8 +148,8 @@ __device__ __forceinline__ void decomrc16(const State& S, long long i, double h,
     int piv = 0;
 #pragma unroll
     for (int c = 0; c < 16; c++) {
-      re[c] = (c == l) ? (al - J[c]) : -J[c];
-      im[c] = (c == l) ? be : 0.0;
+      re[c] = bit_select(c == l, al - J[c], -J[c]);
+      im[c] = bit_select(c == l, be, 0.0);
     }
     zlu16_factor(mask, l, re, im, rdre, rdim, piv);
     double2* dr = reinterpret_cast<double2*>(S.Lre(i, q - 1) + l * 16);
@@ -157,22 +165,28 @@ __device__ __forceinline__ void decomrc16(const State& S, long long i, double h,
   }
 }
 
+// One instantiation per stage count (a half-warp whose trajectory has another stage count leaves at once): with the four
+// decomrc16<S> bodies behind a switch in ONE kernel the compiler kept the row arrays in local memory (286 STL + 202 LDL in the
+// SASS, ~50 kB of local traffic per trajectory); alone, each body keeps its rows in registers.
+template <int S_>
 __global__ void __launch_bounds__(256) lu16_kernel(const State S, const int* __restrict__ lu_list, int n) {
   const int slot = blockIdx.x * 16 + (threadIdx.x >> 4);
   if (slot >= n) return;   // whole half-warp leaves together
   const unsigned mask = 0xffffu << (threadIdx.x & 16);
   const int l = threadIdx.x & 15;
   const long long i = lu_list[slot];
+  if (S.sc[i].NbrStg != S_) return;   // uniform over the 16 lanes
   const double h = S.sc[i].h;
-  const int ns = S.sc[i].NbrStg;
   __syncwarp(mask);
   if (l == 0) S.sc[i].flags &= ~PF_LU_PENDING;
-  switch (ns) {
-    case 1: decomrc16<1>(S, i, h, mask, l); break;
-    case 3: decomrc16<3>(S, i, h, mask, l); break;
-    case 5: decomrc16<5>(S, i, h, mask, l); break;
-    default: decomrc16<7>(S, i, h, mask, l); break;
-  }
+  decomrc16<S_>(S, i, h, mask, l);
+}
+static void launch_lu16(const State& S, const int* lu_list, int n, int min_stg, int max_stg, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n + 15) / 16);
+  if (min_stg <= 1 && max_stg >= 1) lu16_kernel<1><<<grid, 256, 0, st>>>(S, lu_list, n);
+  if (min_stg <= 3 && max_stg >= 3) lu16_kernel<3><<<grid, 256, 0, st>>>(S, lu_list, n);
+  if (min_stg <= 5 && max_stg >= 5) lu16_kernel<5><<<grid, 256, 0, st>>>(S, lu_list, n);
+  if (min_stg <= 7 && max_stg >= 7) lu16_kernel<7><<<grid, 256, 0, st>>>(S, lu_list, n);
 }
 // one Newton iteration = newton_pre_kernel (z = TI f, right-hand sides; one thread per trajectory)
 //                      -> solve16_kernel (Solvrad's triangular solves; 16 lanes per trajectory, lu16.cuh)
@@ -414,8 +428,8 @@ static int run_passes(Handle* H, Work* C, State& S, bool stop_on_accept, cudaStr
     for (int it = 0;; it++) {
       if ((rc = read_counters(C, st))) return rc;
       if (it == 0 && C->h_cnt[C_LU] > 0) {
-        lu16_kernel<<<(unsigned)((C->h_cnt[C_LU] + 15) / 16), 256, 0, st>>>(S, C->d_lu, C->h_cnt[C_LU]);
-        H->launches += 1;
+        launch_lu16(S, C->d_lu, C->h_cnt[C_LU], H->P.MinNbrStg, H->P.MaxNbrStg, st);
+        H->launches += (H->P.MaxNbrStg - H->P.MinNbrStg) / 2 + 1;
       }
       const int n_rows = C->h_cnt[cur ? C_ROWS_B : C_ROWS_A], n_traj = C->h_cnt[cur ? C_TRAJ_B : C_TRAJ_A];
       if (n_traj == 0) break;
