@@ -112,8 +112,21 @@ __device__ __forceinline__ DenseOut make_dout(const DenseArgs& d, const double* 
   return o;
 }
 
+// CTA shape of the fused kernels.  Fixed 1 / 3 stages: ONE 384-thread CTA per SM (12 warps at 168 registers; measured on config 2,
+// fixed s = 3, profiles/r02_fixed_cta_ab.txt: 3 x 128 threads 48.4 ms, 1 x 384 47.3 ms, 2 x 192 48.4, 1 x 256 54.3); the others 2 x 128.
+template <int SM, bool VAR>
+struct FusedCfg {
+#ifdef JB_FUSED_CLASSIC
+  static constexpr int threads = JB_THREADS;
+  static constexpr int minb = VAR ? JB_MINB_VAR : (SM <= 3 ? JB_MINB_FIXED : 2);
+#else
+  static constexpr int threads = (!VAR && SM <= 3) ? 384 : JB_THREADS;
+  static constexpr int minb = (!VAR && SM <= 3) ? 1 : (VAR ? JB_MINB_VAR : 2);
+#endif
+};
+
 template <class Ham, int SM, bool VAR, bool DENSE>
-__global__ void __launch_bounds__(JB_THREADS, VAR ? JB_MINB_VAR : (SM <= 3 ? JB_MINB_FIXED : 2)) radau_kernel(const __grid_constant__ RadauParams P,
+__global__ void __launch_bounds__(FusedCfg<SM, VAR>::threads, FusedCfg<SM, VAR>::minb) radau_kernel(const __grid_constant__ RadauParams P,
                                                     const double* __restrict__ y0,
                                                     const double* __restrict__ tspan, long long M,
                                                     double* __restrict__ y_out, double* __restrict__ t_out,
@@ -562,12 +575,13 @@ int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, 
   auto kern = dense.nout ? radau_kernel<Ham, SM, VAR, true> : radau_kernel<Ham, SM, VAR, false>;
 #endif
   int bps = 0;
-  const size_t smem = lc_smem_bytes<Ham::NV, SM>(JB_THREADS);
+  constexpr int TH = FusedCfg<SM, VAR>::threads;
+  const size_t smem = lc_smem_bytes<Ham::NV, SM>(TH);
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, JB_THREADS, smem));
+  JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TH, smem));
   if (bps < 1) bps = 1;
   long long blocks = (long long)H->sm_count * bps;
-  const long long need = (M + JB_THREADS - 1) / JB_THREADS;
+  const long long need = (M + TH - 1) / TH;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   JB_CUDA(cudaMemsetAsync(H->d_counter, 0, sizeof(unsigned long long), st));
@@ -580,8 +594,8 @@ int launch_radau(Handle* H, const double* y0, const double* tspan, long long M, 
     if ((rc = build_order<Ham>(H, H->ws, y0, M, st, ok))) return rc;
     if (ok) order = H->ws.order;
   }
-  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense,
-                                                  H->d_counter, order);
+  kern<<<(unsigned)blocks, TH, smem, st>>>(H->P, y0, tspan, M, y_out, t_out, h_out, res, stats, nstg, work, dense,
+                                          H->d_counter, order);
   JB_CUDA(cudaGetLastError());
   H->launches = order ? 2 : 1;   // + the CUB radix-sort passes (library kernels)
   return 0;
