@@ -443,6 +443,16 @@ static bool tspan_strictly_monotonic(const double* tspan, int64_t M) {
   for (int64_t m = 0; m < M; m++) ok = ok && (tspan[2 * m + 1] != tspan[2 * m]);
   return ok;
 }
+// the check on a second host thread while the GPU solves; if no thread can be started it runs here and now
+static std::future<bool> check_tspan_async(const double* tspan, int64_t M) {
+  try {
+    return std::async(std::launch::async, tspan_strictly_monotonic, tspan, M);
+  } catch (...) {
+    std::promise<bool> p;
+    p.set_value(tspan_strictly_monotonic(tspan, M));
+    return p.get_future();
+  }
+}
 
 int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_t M, double* y_out, double* t_out,
                      double* h_out, int32_t* res, int64_t* stats, int32_t* nstg, int64_t* work) {
@@ -462,7 +472,7 @@ int jb200_solve_host(void* handle, const double* y0, const double* tspan, int64_
   JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
   // tspan must be strictly monotonic (radaute_impl.hpp:54-59): checked on the host copy while the GPU works (the pass over
   // 16 bytes per row costs ~1.5 ms per million rows on one core -- 2 % of the solve if it ran in front of it)
-  auto span_ok = std::async(std::launch::async, tspan_strictly_monotonic, tspan, M);
+  auto span_ok = check_tspan_async(tspan, M);
   const DenseArgs none{2, nullptr, nullptr, nullptr};
   rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, H->d_work, none, st);
   if (!span_ok.get()) {
@@ -497,7 +507,7 @@ int jb200_solve_host_compact(void* handle, const double* y0, const double* tspan
   const int ny = H->ny;
   JB_CUDA(cudaMemcpyAsync(H->d_y0, y0, sizeof(double) * M * ny, cudaMemcpyHostToDevice, st));
   JB_CUDA(cudaMemcpyAsync(H->d_ts, tspan, sizeof(double) * M * 2, cudaMemcpyHostToDevice, st));
-  auto span_ok = std::async(std::launch::async, tspan_strictly_monotonic, tspan, M);   // overlaps the solve (see jb200_solve_host)
+  auto span_ok = check_tspan_async(tspan, M);   // overlaps the solve (see jb200_solve_host)
   const DenseArgs none{2, nullptr, nullptr, nullptr};
   rc = solve_dev(H, H->d_y0, H->d_ts, M, H->d_y, H->d_t, H->d_h, H->d_res, H->d_stats, H->d_nstg, work ? H->d_work : nullptr,
                  none, st);
