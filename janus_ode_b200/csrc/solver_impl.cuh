@@ -1103,8 +1103,12 @@ int launch_jac_dual(Handle* H, const JacDualArgs& a, cudaStream_t st) {
 
 // forward sensitivities (radau_core.cuh: Sens / sens_step): one thread = one trajectory with its Ny x Ny
 // sensitivity matrix, all stage counts inside one kernel (order selection at run time)
+#ifndef JB_SENS_THREADS
+#define JB_SENS_THREADS 128
+#define JB_SENS_MINB 2
+#endif
 template <class Ham, int SM, bool VAR>
-__global__ void __launch_bounds__(JB_THREADS, 2) sens_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
+__global__ void __launch_bounds__(JB_SENS_THREADS, JB_SENS_MINB) sens_kernel(const __grid_constant__ RadauParams P, const double* __restrict__ y0,
                                                              const double* __restrict__ tspan, const double* __restrict__ S0,
                                                              long long M, double* __restrict__ y_out, double* __restrict__ S_out,
                                                              double* __restrict__ t_out, double* __restrict__ h_out,
@@ -1183,10 +1187,10 @@ int launch_sens(Handle* H, const double* y0, const double* tspan, const double* 
     return 0;
   }
   auto kern = sens_kernel<Ham, 3, false>;
-  const size_t smem = lc_smem_bytes<Ham::NV, 3>(JB_THREADS);
+  const size_t smem = lc_smem_bytes<Ham::NV, 3>(JB_SENS_THREADS);
   if (smem > 48 * 1024) JB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // many small blocks in flight: trajectories differ in length by up to 5x, the block scheduler balances them
-  const long long blocks = std::max<long long>(1, (M + JB_THREADS - 1) / JB_THREADS);
+  const long long blocks = std::max<long long>(1, (M + JB_SENS_THREADS - 1) / JB_SENS_THREADS);
   const int* order = nullptr;
   if (H->presort && M >= (1 << 16) && M <= 2000000000LL) {
     int rc = ws_reserve(H->ws, M, sizeof(double));
@@ -1195,7 +1199,7 @@ int launch_sens(Handle* H, const double* y0, const double* tspan, const double* 
     if ((rc = build_order<Ham>(H, H->ws, y0, M, st, ok))) return rc;
     if (ok) order = H->ws.order;
   }
-  kern<<<(unsigned)blocks, JB_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
+  kern<<<(unsigned)blocks, JB_SENS_THREADS, smem, st>>>(H->P, y0, tspan, S0, M, y_out, S_out, t_out, h_out, res, stats, nstg, work,
                                                   sens_iters, order, Sp_out);
   JB_CUDA(cudaGetLastError());
   H->launches = 1;
