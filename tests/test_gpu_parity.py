@@ -270,3 +270,23 @@ def test_full_size_1m_properties():
     # vdP limit cycle: |x1| <= ~2.1 for every trajectory that has completed a jump
     assert np.abs(a["y"][:, 2]).max() < 3.01
 
+
+@pytest.mark.gpu
+def test_epoch_list_ordering_is_scheduling_only(monkeypatch):
+    """the per-batch ordering decision (JB200_EPOCH_HORDER=4: H(y0) order for a one-parameter family, step-size order for a
+    cloud; solver_impl.cuh ws_init / coherence_kernel) and both fixed policies give the same bits on both kinds of batch"""
+    from janus_ode_b200 import configs
+    for k, mk in enumerate((configs.c2_vdp, configs.c2_vdp_cloud)):
+        cfg = mk(M=1 << 16)
+        cfg["tspan"][:, 1] = 40.0
+        outs = []
+        for j, h in enumerate(("4", "2", "3")):
+            monkeypatch.setenv("JB200_EPOCH_HORDER", h)
+            op = jb.OptionsTe(RelTol=1e-6, AbsTol=1e-9, MaxNbrStep=1000000 + 10 * k + j)    # a fresh native handle per policy
+            dyn = jb.HamiltonianSystem(cfg["ham"], cfg["sign"])
+            r = jb.RadauTe(dyn, dyn.jacobian, cfg["tspan"].to(DEV), cfg["y0"].to(DEV), op)
+            r.solve()
+            outs.append((r.y.clone(), r.stats.raw.clone(), r.h.clone(), r.nstg.clone()))
+        for o in outs[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+        assert int(outs[0][3].max()) >= 3 and bool((outs[0][1][:, 5] > 10).all())
