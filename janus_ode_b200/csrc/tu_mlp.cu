@@ -93,7 +93,7 @@ __device__ __forceinline__ void enqueue(const State& S, long long i, int* cnt, i
     f0_list[append(&cnt[C_F0], 1)] = (int)i * 8;
   }
 }
-__global__ void prep_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* rows, int* trajs,
+__global__ void __launch_bounds__(128, 4) prep_kernel(const State S, const __grid_constant__ RadauParams P, int* cnt, int* rows, int* trajs,
                             int* lu_list) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= S.M) return;
@@ -191,7 +191,7 @@ static void launch_lu16(const State& S, const int* lu_list, int n, int min_stg, 
 // one Newton iteration = newton_pre_kernel (z = TI f, right-hand sides; one thread per trajectory)
 //                      -> solve16_kernel (Solvrad's triangular solves; 16 lanes per trajectory, lu16.cuh)
 //                      -> newton_post_kernel (norms, convergence logic, Estrad / controller; one thread)
-__global__ void newton_pre_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
+__global__ void __launch_bounds__(128, 4) newton_pre_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
                                   int n_in) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_in) return;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) solve16_kernel(const State S, const int* 
     *zi = bi;
   }
 }
-__global__ void newton_post_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
+__global__ void __launch_bounds__(128, 4) newton_post_kernel(const State S, const __grid_constant__ RadauParams P, const int* __restrict__ trajs_in,
                                    int n_in, int* cnt, int c_rows, int c_traj, int* rows_out, int* trajs_out, int* err_list,
                                    int* f0_list) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
